@@ -1,0 +1,118 @@
+"""ctypes binding of libmsda_b200.so (the C ABI declared in include/msda_b200.h).
+
+The library is built in-tree by :func:`build` (``nvcc`` for sm_100a only) and loaded lazily.
+There is no CPU or PyTorch fallback: if the library is missing every operator raises.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'libmsda_b200.so')
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
+SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu']
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-Xcompiler', '-fPIC']
+
+F32, F16, BF16 = 0, 1, 2
+
+_c_int, _c_vp, _c_f, _c_i64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_int64
+
+_SIGNATURES = {
+    'msda_abi_version': (_c_int, []),
+    'msda_last_error': (ctypes.c_char_p, []),
+    'msda_launch_count': (_c_i64, []),
+    'msda_fwd': (_c_int, [_c_vp] * 6 + [_c_int] * 10 + [_c_vp]),
+    'msda_bwd': (_c_int, [_c_vp] * 9 + [_c_int] * 10 + [_c_vp]),
+    'msda_host_scratch_bytes': (_c_i64, [_c_int] * 10),
+    'msda_fwd_host': (_c_int, [_c_vp] * 6 + [_c_int] * 9 + [_c_vp, _c_i64, _c_vp]),
+    'msda_fwd_bwd_host': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_vp, _c_i64, _c_vp]),
+    'bev_point_sampling': (_c_int, [_c_vp] * 3 + [_c_f, _c_f] + [_c_int] * 4 + [_c_vp] * 6),
+    'sca_fwd': (_c_int, [_c_vp] * 10 + [_c_int] * 11 + [_c_vp]),
+    'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 11 + [_c_vp]),
+    'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 8 + [_c_f, _c_int, _c_vp]),
+    'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 8 + [_c_f, _c_int, _c_vp]),
+}
+
+_lib = None
+
+
+def _stale():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into libmsda_b200.so with nvcc (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    objs = [os.path.join(CSRC, s[:-3] + '.o') for s in SOURCES]
+
+    def compile_one(args):
+        src, obj = args
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed for {src}:\n{r.stdout}\n{r.stderr}')
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        logs = list(ex.map(compile_one, zip(SOURCES, objs)))
+    if verbose:
+        sys.stderr.write('\n'.join(logs))
+    r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB_PATH]
+                       + objs,
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    for o in objs:
+        os.remove(o)
+    global _lib
+    _lib = None
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: the CUDA library has not been built. Run '
+                '`python -c "import __graft_entry__ as g; g.build()"` at the repo root. '
+                'There is no CPU fallback.')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().msda_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed (code {rc}): {msg}')
+
+
+def launch_count():
+    return int(lib().msda_launch_count())
+
+
+def header_symbols():
+    """Function names declared in include/msda_b200.h (used by the ABI export test)."""
+    import re
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b([a-z_0-9]+)\s*\(', text)) - {'defined'})

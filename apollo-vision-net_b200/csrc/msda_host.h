@@ -1,0 +1,62 @@
+// Host-side glue shared by the translation units of libmsda_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/msda_b200.h"
+
+namespace msda {
+
+// Arguments of the op-boundary calls, validated by abi.cu before any launch.
+struct Problem {
+  const void* value = nullptr;
+  const int64_t* shapes = nullptr;
+  const int64_t* starts = nullptr;
+  const void* loc = nullptr;
+  const void* attn = nullptr;
+  void* out = nullptr;
+  const void* grad_out = nullptr;
+  float* g_value = nullptr;
+  float* g_loc = nullptr;
+  float* g_attn = nullptr;
+  int B = 0, Nk = 0, M = 0, Dh = 0, L = 0, Nq = 0, P = 0;
+  int value_dtype = MSDA_F32, coord_dtype = MSDA_F32;
+};
+
+// Arguments of the fused attention cores (sca_* / tsa_*).
+struct FusedProblem {
+  const void* value = nullptr;
+  const int64_t* shapes = nullptr;
+  const int64_t* starts = nullptr;
+  const float* offsets = nullptr;
+  const float* logits = nullptr;
+  const float* ref = nullptr;          // ref_cam (SCA) or ref points (TSA / decoder)
+  const uint8_t* bev_mask = nullptr;   // SCA only
+  const uint32_t* hit_bits = nullptr;  // SCA only
+  void* out = nullptr;
+  float* attn_out = nullptr;
+  const void* g_out = nullptr;
+  float* g_value = nullptr;
+  float* g_offsets = nullptr;
+  float* g_logits = nullptr;
+  int bs = 0, groups = 0;              // groups = num_cam (SCA) or Q (TSA)
+  int Nk = 0, M = 0, Dh = 0, L = 0, P = 0, D = 1, Nq = 0, bev_w = 0;
+  float clamp = -1.f;
+  int value_dtype = MSDA_F32;
+};
+
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch();
+
+int launch_msda_fwd(const Problem& pr, cudaStream_t st);
+int launch_msda_bwd(const Problem& pr, cudaStream_t st);
+int launch_point_sampling(const float* ref_3d, const float* lidar2img, const double* pc,
+                          float img_h, float img_w, int bs, int num_cam, int HW, int D,
+                          float* ref_cam, uint8_t* bev_mask, uint32_t* hit_bits, int32_t* hit_index,
+                          int32_t* hit_count, cudaStream_t st);
+int launch_sca_fwd(const FusedProblem& fp, cudaStream_t st);
+int launch_sca_bwd(const FusedProblem& fp, cudaStream_t st);
+int launch_tsa_fwd(const FusedProblem& fp, cudaStream_t st);
+int launch_tsa_bwd(const FusedProblem& fp, cudaStream_t st);
+
+}  // namespace msda

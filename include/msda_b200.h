@@ -1,0 +1,197 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention library
+ * (libmsda_b200.so, built from apollo-vision-net_b200/csrc for sm_100a).
+ *
+ * This is the drop-in boundary for the hot path of HankerSia/Apollo-Vision-Net:
+ * every entry point below is what the reference's FFI for this path binds.  In the
+ * reference the binding is mmcv's compiled `_ext` module, loaded at
+ *   projects/mmdet3d_plugin/bevformer/modules/multi_scale_deformable_attn_function.py:8-10
+ * and called at :40-46 / :116-122 (forward) and :72-82 / :148-158 (backward).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / ATen types.
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *  - the caller owns and allocates every buffer (outputs and scratch included); the
+ *    library never frees or retains a pointer past the call.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *    asynchronous, stateless and re-entrant.
+ *  - return value: 0 on success, a negative MSDA_ERR_* code on failure;
+ *    msda_last_error() returns a thread-local message for the last failure
+ *    (mirrors the AT_ASSERTM / AT_ERROR behaviour of the reference-era ops, cf.
+ *    projects/mmdet3d_plugin/bevformer/backbones/ops_dcnv3/src/cuda/dcnv3_cuda.cu:28-53).
+ *  - spatial_shapes / level_start_index arrive as DEVICE int64 arrays exactly as the
+ *    reference passes them (transformer.py:251-254); they are read on the device,
+ *    there is no host synchronisation anywhere in this library.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* element types of `value` / `out` (and optionally of locations / weights) */
+#define MSDA_F32  0
+#define MSDA_F16  1
+#define MSDA_BF16 2
+
+#define MSDA_OK                 0
+#define MSDA_ERR_BAD_ARGUMENT  -1
+#define MSDA_ERR_UNSUPPORTED   -2
+#define MSDA_ERR_CUDA          -3
+
+#define MSDA_MAX_LEVELS 16
+
+int msda_abi_version(void);
+const char* msda_last_error(void);
+
+/* ---------------------------------------------------------------------------------
+ * Operator boundary: replaces ext_module.ms_deform_attn_forward
+ * (multi_scale_deformable_attn_function.py:40-46, :116-122).
+ *
+ *   value   (B, Nk, M, Dh)        value_dtype, contiguous
+ *   shapes  (L, 2) int64 (h, w);  starts (L,) int64
+ *   loc     (B, Nq, M, L, P, 2)   coord_dtype, normalised (x, y)
+ *   attn    (B, Nq, M, L, P)      coord_dtype
+ *   out     (B, Nq, M*Dh)         value_dtype, fully overwritten
+ *
+ * coord_dtype is MSDA_F32 or equal to value_dtype.  Accumulation is fp32.
+ * im2col_step has no meaning for these kernels; it is validated like mmcv does
+ * (B % min(B, im2col_step) == 0) and otherwise ignored.
+ * ------------------------------------------------------------------------------- */
+int msda_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
+             const void* loc, const void* attn, void* out,
+             int B, int Nk, int M, int Dh, int L, int Nq, int P,
+             int value_dtype, int coord_dtype, int im2col_step, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Replaces ext_module.ms_deform_attn_backward
+ * (multi_scale_deformable_attn_function.py:72-82, :148-158).
+ *
+ *   grad_out (B, Nq, M*Dh)       value_dtype, contiguous
+ *   g_value  (B, Nk, M, Dh)      fp32 ACCUMULATOR: the kernel adds into it, the caller
+ *                                zero-fills it first (the reference does the same with
+ *                                torch.zeros_like, :144)
+ *   g_loc    (B, Nq, M, L, P, 2) fp32, every element written exactly once
+ *   g_attn   (B, Nq, M, L, P)    fp32, every element written exactly once
+ * ------------------------------------------------------------------------------- */
+int msda_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
+             const void* loc, const void* attn, const void* grad_out,
+             float* g_value, float* g_loc, float* g_attn,
+             int B, int Nk, int M, int Dh, int L, int Nq, int P,
+             int value_dtype, int coord_dtype, int im2col_step, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Host-buffer variants of the two calls above (the end-to-end leg of bench.py and
+ * non-PyTorch callers): every tensor pointer is a HOST pointer (pinned memory gives
+ * asynchronous copies), `scratch` is a DEVICE buffer of at least
+ * msda_host_scratch_bytes(...) bytes.  Inputs are copied to the device, the kernel
+ * runs, results are copied back, all on `stream`; the call returns after the stream
+ * has been synchronised.
+ * ------------------------------------------------------------------------------- */
+int64_t msda_host_scratch_bytes(int B, int Nk, int M, int Dh, int L, int Nq, int P,
+                                int value_dtype, int coord_dtype, int with_backward);
+int msda_fwd_host(const void* value_host, const int64_t* shapes_host, const int64_t* starts_host,
+                  const void* loc_host, const void* attn_host, void* out_host,
+                  int B, int Nk, int M, int Dh, int L, int Nq, int P,
+                  int value_dtype, int coord_dtype, void* scratch, int64_t scratch_bytes,
+                  void* stream);
+int msda_fwd_bwd_host(const void* value_host, const int64_t* shapes_host, const int64_t* starts_host,
+                      const void* loc_host, const void* attn_host, const void* grad_out_host,
+                      void* out_host, float* g_value_host, float* g_loc_host, float* g_attn_host,
+                      int B, int Nk, int M, int Dh, int L, int Nq, int P,
+                      int value_dtype, int coord_dtype, void* scratch, int64_t scratch_bytes,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * BEV geometry: replaces BEVFormerEncoder.point_sampling (encoder.py:89-241) and the
+ * per-camera nonzero() compaction of SpatialCrossAttention.forward
+ * (spatial_cross_attention.py:135-139), with no host synchronisation.
+ *
+ *   ref_3d     (bs, D, HW, 3) fp32 pillar points in [0,1]^3 (get_reference_points,
+ *              encoder.py:62-72), exactly the `reference_points` argument of the reference
+ *   lidar2img  (bs, num_cam, 4, 4) fp32
+ *   pc_range_host  6 doubles on the HOST (x0, y0, z0, x1, y1, z1)
+ *   img_h/img_w    image size of camera 0 / sample 0 (the reference normalises every camera
+ *              with it, encoder.py:196-226)
+ *   ref_cam    (num_cam, bs, HW, D, 2) fp32   out
+ *   bev_mask   (num_cam, bs, HW, D) uint8 (0/1) out  -- bit-exact w.r.t. the reference
+ *   hit_bits   (bs, HW) uint32 out: bit i set <=> camera i sees query (any Z anchor)
+ *   hit_index  (num_cam, HW) int32 out: ascending query indices seen by camera i in
+ *              batch element 0 (the reference's quirk, :137); entries past the count
+ *              are -1
+ *   hit_count  (num_cam,) int32 out
+ * ------------------------------------------------------------------------------- */
+int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double* pc_range_host,
+                       float img_h, float img_w, int bs, int num_cam, int HW, int D,
+                       float* ref_cam, uint8_t* bev_mask, uint32_t* hit_bits,
+                       int32_t* hit_index, int32_t* hit_count, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fused spatial cross-attention core: everything between the Linear layers of
+ * SpatialCrossAttention / MSDeformableAttention3D
+ * (spatial_cross_attention.py:135-170 and :342-396): camera-hit gating, softmax over
+ * L*P, Z-anchor sampling locations, multi-level bilinear sampling, the sum over
+ * cameras and the division by the hit count -- without materialising
+ * sampling_locations, the rebatched queries or the scatter.
+ *
+ *   value    (bs*num_cam, Nk, M, Dh)  value_dtype (output of value_proj)
+ *   offsets  (bs, HW, M, L, P, 2)     fp32 raw output of sampling_offsets(query)
+ *   logits   (bs, HW, M, L*P)         fp32 raw output of attention_weights(query)
+ *   ref_cam, bev_mask, hit_bits       from bev_point_sampling
+ *   slots    (bs, HW, M*Dh)           value_dtype out: sum over hit cameras / count
+ *   attn_out (bs, HW, M, L*P)         fp32 out (softmax result, saved for backward) or NULL
+ * ------------------------------------------------------------------------------- */
+int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
+            const float* offsets, const float* logits, const float* ref_cam,
+            const uint8_t* bev_mask, const uint32_t* hit_bits, void* slots, float* attn_out,
+            int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
+            int bev_w, int value_dtype, void* stream);
+
+/*   g_slots   (bs, HW, M*Dh) value_dtype   gradient w.r.t. `slots`
+ *   g_value   (bs*num_cam, Nk, M, Dh) fp32 accumulator (zero-filled by the caller)
+ *   g_offsets (bs, HW, M, L, P, 2) fp32, fully written
+ *   g_logits  (bs, HW, M, L*P) fp32, fully written (softmax backward included)        */
+int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
+            const float* offsets, const float* logits, const float* ref_cam,
+            const uint8_t* bev_mask, const uint32_t* hit_bits, const void* g_slots,
+            float* g_value, float* g_offsets, float* g_logits,
+            int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
+            int bev_w, int value_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fused temporal self-attention / decoder cross-attention core
+ * (temporal_self_attention.py:204-279, decoder.py:299-350): softmax (with optional
+ * logit clamp), location = ref + offset / (W_l, H_l), sampling, and the mean over the
+ * `Q` queue entries (Q = 2 for TSA, Q = 1 for CustomMSDeformableAttention).
+ *
+ *   value    (bs*Q, Nk, M, Dh)        value_dtype; batch index = b*Q + j
+ *   offsets  (bs, Nq, M, Q, L, P, 2)  fp32 raw Linear output
+ *   logits   (bs, Nq, M, Q, L*P)      fp32 raw Linear output
+ *   ref      (bs*Q, Nq, L, 2)         fp32 reference points
+ *   out      (bs, Nq, M*Dh)           value_dtype: (1/Q) * sum_j MSDA_j
+ *   clamp    < 0 : no clamp; otherwise logits are clamped to [-clamp, clamp]
+ * ------------------------------------------------------------------------------- */
+int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
+            const float* offsets, const float* logits, const float* ref, void* out,
+            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq,
+            float clamp, int value_dtype, void* stream);
+
+int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
+            const float* offsets, const float* logits, const float* ref, const void* g_out,
+            float* g_value, float* g_offsets, float* g_logits,
+            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq,
+            float clamp, int value_dtype, void* stream);
+
+/* Number of kernel launches this library has enqueued since load (all entry points);
+ * bench.py reports the delta over its timed region as "gpu_launches". */
+int64_t msda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,256 @@
+"""Import the UNMODIFIED reference attention modules without mmcv (test infrastructure).
+
+The reference's hot-path files import ``mmcv`` / ``mmdet`` at module scope and
+those packages are absent from this image.  This shim
+installs a minimal stand-in for exactly the names those files import --
+registries, ``BaseModule``, ``xavier_init`` / ``constant_init``, identity
+``force_fp32`` / ``auto_fp16`` decorators, and a ``TransformerLayerSequence`` --
+and points ``mmcv.ops.multi_scale_deform_attn.multi_scale_deformable_attn_pytorch``
+at the reference's own in-tree restatement
+``multi_scale_deformable_attn_pytorch_2d`` (temporal_self_attention.py:293-348).
+The reference source files are then executed from where they lie under
+``/root/reference`` (nothing is copied).  Only ``tests/golden/make_golden.py`` and
+the ``not gpu`` oracle-pinning tests use it, and only when ``/root/reference``
+exists (it does not on the GPU box).
+"""
+import copy
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REFERENCE_ROOT = os.environ.get('APOLLO_REFERENCE_ROOT', '/root/reference')
+_MOD_DIR = os.path.join(REFERENCE_ROOT, 'projects', 'mmdet3d_plugin', 'bevformer', 'modules')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(_MOD_DIR, 'spatial_cross_attention.py'))
+
+
+class _Registry:
+    def __init__(self, name):
+        self.name = name
+        self.module_dict = {}
+
+    def register_module(self, name=None, force=False, module=None):
+        def deco(cls):
+            self.module_dict[name or cls.__name__] = cls
+            return cls
+        if module is not None:
+            return deco(module)
+        return deco
+
+    def get(self, key):
+        return self.module_dict.get(key)
+
+    def build(self, cfg, **default_args):
+        return _build_from_cfg(cfg, self, default_args or None)
+
+
+def _build_from_cfg(cfg, registry, default_args=None):
+    args = dict(cfg)
+    if default_args:
+        for k, v in default_args.items():
+            args.setdefault(k, v)
+    typ = args.pop('type')
+    cls = registry.get(typ) if isinstance(typ, str) else typ
+    if cls is None:
+        raise KeyError(f'{typ} is not in the {registry.name} registry')
+    return cls(**args)
+
+
+class _BaseModule(nn.Module):
+    def __init__(self, init_cfg=None):
+        super().__init__()
+        self._is_init = False
+        self.init_cfg = copy.deepcopy(init_cfg)
+
+    def init_weights(self):
+        pass
+
+
+class _ConfigDict(dict):
+    __getattr__ = dict.get
+    __setattr__ = dict.__setitem__
+
+
+def _identity_decorator_factory(*dargs, **dkwargs):
+    if len(dargs) == 1 and callable(dargs[0]) and not dkwargs:
+        return dargs[0]
+
+    def deco(fn):
+        return fn
+    return deco
+
+
+def _deprecated_api_warning(name_dict, cls_name=None):
+    def deco(fn):
+        return fn
+    return deco
+
+
+def _xavier_init(module, gain=1, bias=0, distribution='normal'):
+    if module is None:
+        return
+    if hasattr(module, 'weight') and module.weight is not None:
+        if distribution == 'uniform':
+            nn.init.xavier_uniform_(module.weight, gain=gain)
+        else:
+            nn.init.xavier_normal_(module.weight, gain=gain)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def _constant_init(module, val, bias=0):
+    if hasattr(module, 'weight') and module.weight is not None:
+        nn.init.constant_(module.weight, val)
+    if hasattr(module, 'bias') and module.bias is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+def _digit_version(v):
+    out = []
+    for tok in str(v).split('+')[0].split('.'):
+        num = ''.join(ch for ch in tok if ch.isdigit())
+        out.append(int(num) if num else 0)
+    return tuple(out)
+
+
+class _ExtLoader:
+    @staticmethod
+    def load_ext(name, funcs):
+        ext = types.SimpleNamespace()
+
+        def _missing(*a, **k):
+            raise RuntimeError('mmcv _ext is not available in the reference shim (CPU path only)')
+        for f in funcs:
+            setattr(ext, f, _missing)
+        return ext
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _load_file(modname, path):
+    spec = importlib.util.spec_from_file_location(modname, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_loaded = None
+
+
+def load_reference():
+    """Returns a namespace with the reference's own classes / functions (CPU branch)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise FileNotFoundError(f'reference sources not found under {REFERENCE_ROOT}')
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split('.')[0] in ('mmcv', 'mmdet', 'projects', 'matplotlib')}
+
+    ATTENTION = _Registry('attention')
+    FFN_REG = _Registry('feed-forward network')
+    POS_REG = _Registry('position encoding')
+    LAYER = _Registry('transformerLayer')
+    LAYER_SEQ = _Registry('transformer-layers sequence')
+
+    class TransformerLayerSequence(_BaseModule):
+        def __init__(self, transformerlayers=None, num_layers=None, init_cfg=None):
+            super().__init__(init_cfg)
+            if isinstance(transformerlayers, dict):
+                transformerlayers = [copy.deepcopy(transformerlayers) for _ in range(num_layers)]
+            self.num_layers = num_layers
+            self.layers = nn.ModuleList()
+            for cfg in (transformerlayers or []):
+                self.layers.append(_build_from_cfg(cfg, LAYER))
+
+    def build_attention(cfg, default_args=None):
+        return _build_from_cfg(cfg, ATTENTION, default_args)
+
+    tsa_path = os.path.join(_MOD_DIR, 'temporal_self_attention.py')
+
+    def _lazy_msda_pytorch(*args, **kwargs):
+        tsa = sys.modules['projects.mmdet3d_plugin.bevformer.modules.temporal_self_attention']
+        return tsa.multi_scale_deformable_attn_pytorch_2d(*args, **kwargs)
+
+    mmcv = _module('mmcv', ConfigDict=_ConfigDict, deprecated_api_warning=_deprecated_api_warning)
+    mmcv.__path__ = []
+    _module('mmcv.ops').__path__ = []
+    _module('mmcv.ops.multi_scale_deform_attn',
+            multi_scale_deformable_attn_pytorch=_lazy_msda_pytorch)
+    cnn = _module('mmcv.cnn', xavier_init=_xavier_init, constant_init=_constant_init,
+                  Linear=nn.Linear)
+    cnn.__path__ = []
+    _module('mmcv.cnn.bricks').__path__ = []
+    _module('mmcv.cnn.bricks.registry', ATTENTION=ATTENTION, TRANSFORMER_LAYER=LAYER,
+            TRANSFORMER_LAYER_SEQUENCE=LAYER_SEQ, FEEDFORWARD_NETWORK=FFN_REG,
+            POSITIONAL_ENCODING=POS_REG)
+    _module('mmcv.cnn.bricks.transformer', build_attention=build_attention,
+            TransformerLayerSequence=TransformerLayerSequence)
+    runner = _module('mmcv.runner', force_fp32=_identity_decorator_factory,
+                     auto_fp16=_identity_decorator_factory)
+    runner.__path__ = []
+    _module('mmcv.runner.base_module', BaseModule=_BaseModule, ModuleList=nn.ModuleList,
+            Sequential=nn.Sequential)
+    _module('mmcv.utils', ext_loader=_ExtLoader, ConfigDict=_ConfigDict,
+            build_from_cfg=_build_from_cfg, deprecated_api_warning=_deprecated_api_warning,
+            to_2tuple=lambda x: (x, x), TORCH_VERSION=torch.__version__,
+            digit_version=_digit_version)
+    if 'matplotlib' not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            _module('matplotlib').__path__ = []
+            _module('matplotlib.pyplot')
+
+    for pkg in ('projects', 'projects.mmdet3d_plugin', 'projects.mmdet3d_plugin.bevformer',
+                'projects.mmdet3d_plugin.bevformer.modules', 'projects.mmdet3d_plugin.models',
+                'projects.mmdet3d_plugin.models.utils'):
+        _module(pkg).__path__ = []
+    _module('projects.mmdet3d_plugin.models.utils.bricks',
+            run_time=lambda name: (lambda fn: fn))
+    _module('projects.mmdet3d_plugin.models.utils.visual', save_tensor=lambda *a, **k: None)
+    _module('projects.mmdet3d_plugin.bevformer.modules.custom_base_transformer_layer',
+            MyCustomBaseTransformerLayer=_BaseModule)
+
+    prefix = 'projects.mmdet3d_plugin.bevformer.modules.'
+    try:
+        fn_mod = _load_file(prefix + 'multi_scale_deformable_attn_function',
+                            os.path.join(_MOD_DIR, 'multi_scale_deformable_attn_function.py'))
+        tsa = _load_file(prefix + 'temporal_self_attention', tsa_path)
+        sca = _load_file(prefix + 'spatial_cross_attention',
+                         os.path.join(_MOD_DIR, 'spatial_cross_attention.py'))
+        enc = _load_file(prefix + 'encoder', os.path.join(_MOD_DIR, 'encoder.py'))
+        dec = _load_file(prefix + 'decoder', os.path.join(_MOD_DIR, 'decoder.py'))
+    finally:
+        # keep the synthetic entries only as long as needed by the loaded modules' globals
+        for k in list(sys.modules):
+            if k.split('.')[0] in ('mmcv', 'mmdet', 'projects') and k not in saved:
+                if not k.startswith(prefix):
+                    del sys.modules[k]
+        sys.modules.update(saved)
+
+    _loaded = types.SimpleNamespace(
+        msda_pytorch_2d=tsa.multi_scale_deformable_attn_pytorch_2d,
+        TemporalSelfAttention=tsa.TemporalSelfAttention,
+        SpatialCrossAttention=sca.SpatialCrossAttention,
+        MSDeformableAttention3D=sca.MSDeformableAttention3D,
+        BEVFormerEncoder=enc.BEVFormerEncoder,
+        BEVFormerLayer=enc.BEVFormerLayer,
+        CustomMSDeformableAttention=dec.CustomMSDeformableAttention,
+        Function_fp32=fn_mod.MultiScaleDeformableAttnFunction_fp32,
+        Function_fp16=fn_mod.MultiScaleDeformableAttnFunction_fp16,
+        ATTENTION=ATTENTION, build_attention=build_attention,
+        modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod))
+    return _loaded

@@ -1,0 +1,56 @@
+"""CPU-side checks: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/msda_b200.h declares; the product package never falls back to the oracle."""
+import os
+import re
+
+import pytest
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    import apollo_vision_net_b200 as pkg
+    pkg.build()
+    lib = pkg._lib.lib()
+    assert lib.msda_abi_version() == 1
+    syms = pkg._lib.header_symbols()
+    assert {'msda_fwd', 'msda_bwd', 'bev_point_sampling', 'sca_fwd', 'sca_bwd', 'tsa_fwd',
+            'tsa_bwd', 'msda_fwd_host', 'msda_fwd_bwd_host'} <= set(syms)
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in include/msda_b200.h but not exported'
+    assert set(pkg._lib._SIGNATURES) == set(syms)
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    import apollo_vision_net_b200 as pkg
+    pkg.build()
+    out = subprocess.run(['cuobjdump', '-lelf', pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_\d+a?', out))
+    assert archs == {'sm_100a'}, archs
+
+
+def test_cpu_tensors_raise_no_fallback():
+    import torch
+    import apollo_vision_net_b200 as pkg
+    from tests.util import make_op_inputs
+    args = make_op_inputs(1, [(4, 4)], 2, 32, 3, 2)
+    with pytest.raises(RuntimeError, match='CUDA tensor'):
+        pkg.MultiScaleDeformableAttnFunction_fp32.apply(*args, 64)
+
+
+def test_product_package_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg_dir = os.path.join(root, 'apollo-vision-net_b200')
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith('.py'):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+
+
+def test_host_scratch_size_is_consistent():
+    import apollo_vision_net_b200 as pkg
+    lib = pkg._lib.lib()
+    n_fwd = lib.msda_host_scratch_bytes(2, 100, 8, 32, 1, 50, 4, 0, 0, 0)
+    n_bwd = lib.msda_host_scratch_bytes(2, 100, 8, 32, 1, 50, 4, 0, 0, 1)
+    assert 0 < n_fwd < n_bwd
+    assert n_fwd >= 2 * 100 * 256 * 4 + 2 * 50 * 8 * 4 * 12 + 2 * 50 * 256 * 4
