@@ -9,6 +9,10 @@ when that library is missing.
 """
 from . import _lib
 from ._lib import build, launch_count
+from . import fused_ops, modules, registry, synthetic
+from .fused_ops import (QueueDeformAttnFunction, SpatialCrossAttnFunction, bev_point_sampling)
+from .registry import (ATTENTION, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, build_attention,
+                       build_transformer_layer, build_transformer_layer_sequence)
 from .multi_scale_deformable_attn_function import (
     MultiScaleDeformableAttnFunction_fp16, MultiScaleDeformableAttnFunction_fp32, ext_module,
     ms_deform_attn_backward, ms_deform_attn_forward)

@@ -1,0 +1,201 @@
+"""Python host side of the fused B200 kernels (C ABI: bev_point_sampling, sca_*, tsa_*).
+
+These replace the tensor plumbing between the Linear layers of the reference's attention
+modules (no rebatch, no materialised sampling_locations, no scatter, no host sync):
+
+* :func:`bev_point_sampling` -- ``BEVFormerEncoder.point_sampling`` (encoder.py:89-241) plus
+  the per-camera ``nonzero()`` compaction of ``SpatialCrossAttention.forward``
+  (spatial_cross_attention.py:135-139).
+* :class:`SpatialCrossAttnFunction` -- spatial_cross_attention.py:135-170 and :342-396.
+* :class:`QueueDeformAttnFunction` -- temporal_self_attention.py:204-279 (queue of 2) and
+  decoder.py:299-350 (queue of 1).
+"""
+import ctypes
+
+import torch
+from torch.autograd.function import Function, once_differentiable
+
+from . import _lib
+from .multi_scale_deformable_attn_function import (_DTYPE_CODE, _require_cuda, _stream_ptr,
+                                                   custom_bwd, custom_fwd)
+
+
+class BevGeometry:
+    """Result of :func:`bev_point_sampling`; everything stays on the device."""
+
+    def __init__(self, ref_cam, mask_u8, hit_bits, hit_index, hit_count, D):
+        self.reference_points_cam = ref_cam          # (num_cam, bs, HW, D, 2) fp32
+        self.mask_u8 = mask_u8                       # (num_cam, bs, HW, D) uint8
+        self.hit_bits = hit_bits                     # (bs, HW) int32 bit field over cameras
+        self.hit_index = hit_index                   # (num_cam, HW) int32, -1 padded
+        self.hit_count = hit_count                   # (num_cam,) int32
+        self.D = D
+
+    @property
+    def bev_mask(self):
+        """(num_cam, bs, HW, D) bool, the reference's ``bev_mask``."""
+        return self.mask_u8.view(torch.bool)
+
+
+def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w):
+    """ref_3d (bs, D, HW, 3) fp32 CUDA; lidar2img (bs, num_cam, 4, 4) -> :class:`BevGeometry`."""
+    _require_cuda(ref_3d=ref_3d)
+    dev = ref_3d.device
+    ref_3d = ref_3d.to(torch.float32).contiguous()
+    l2i = torch.as_tensor(lidar2img, dtype=torch.float32).to(dev).contiguous()
+    bs, D, HW, _ = ref_3d.shape
+    num_cam = l2i.shape[1]
+    assert l2i.shape == (bs, num_cam, 4, 4), l2i.shape
+    ref_cam = torch.empty((num_cam, bs, HW, D, 2), dtype=torch.float32, device=dev)
+    mask = torch.empty((num_cam, bs, HW, D), dtype=torch.uint8, device=dev)
+    hit_bits = torch.empty((bs, HW), dtype=torch.int32, device=dev)
+    hit_index = torch.empty((num_cam, HW), dtype=torch.int32, device=dev)
+    hit_count = torch.empty((num_cam,), dtype=torch.int32, device=dev)
+    pc = (ctypes.c_double * 6)(*[float(x) for x in pc_range])
+    with torch.cuda.device(dev):
+        rc = _lib.lib().bev_point_sampling(
+            ref_3d.data_ptr(), l2i.data_ptr(), ctypes.cast(pc, ctypes.c_void_p), float(img_h),
+            float(img_w), bs, num_cam, HW, D, ref_cam.data_ptr(), mask.data_ptr(),
+            hit_bits.data_ptr(), hit_index.data_ptr(), hit_count.data_ptr(), _stream_ptr(ref_3d))
+    _lib.check(rc, 'bev_point_sampling')
+    return BevGeometry(ref_cam, mask, hit_bits, hit_index, hit_count, D)
+
+
+def hit_bits_from_mask(bev_mask):
+    """(num_cam, bs, HW, D) bool -> (bs, HW) int32 camera bit field (for callers that bring
+    their own ``bev_mask`` instead of calling :func:`bev_point_sampling`)."""
+    num_cam = bev_mask.shape[0]
+    any_d = bev_mask.any(-1).to(torch.int32)                       # (num_cam, bs, HW)
+    w = (2 ** torch.arange(num_cam, device=bev_mask.device, dtype=torch.int64)).view(-1, 1, 1)
+    bits = (any_d.to(torch.int64) * w).sum(0)
+    bits = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits)
+    return bits.to(torch.int32).contiguous()
+
+
+def _check_value(value):
+    if value.dtype not in _DTYPE_CODE:
+        raise RuntimeError(f'unsupported value dtype {value.dtype}')
+    return value.contiguous()
+
+
+class SpatialCrossAttnFunction(Function):
+    """slots = (sum over hit cameras of MSDA(value_cam, ref_cam + offsets / (W, H), softmax(logits))) / count.
+
+    value (bs*num_cam, Nk, M, Dh); offsets (bs, HW, M, L, P, 2) and logits (bs, HW, M, L*P)
+    are the raw outputs of the ``sampling_offsets`` / ``attention_weights`` Linear layers on the
+    BEV queries (computed once per query, not once per (camera, query) pair).
+    """
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref_cam,
+                mask_u8, hit_bits, num_cam):
+        _require_cuda(value=value, offsets=offsets, logits=logits, ref_cam=ref_cam,
+                      mask=mask_u8, hit_bits=hit_bits)
+        value = _check_value(value)
+        offsets = offsets.to(torch.float32).contiguous()
+        logits = logits.to(torch.float32).contiguous()
+        shapes = spatial_shapes.to(torch.int64).contiguous()
+        starts = level_start_index.to(torch.int64).contiguous()
+        ref_cam = ref_cam.to(torch.float32).contiguous()
+        mask_u8 = mask_u8.contiguous()
+        hit_bits = hit_bits.contiguous()
+        Bc, Nk, M, Dh = value.shape
+        bs, HW, M2, L, P, _ = offsets.shape
+        D = ref_cam.shape[3]
+        assert Bc == bs * num_cam and M2 == M and logits.shape == (bs, HW, M, L * P)
+        assert ref_cam.shape == (num_cam, bs, HW, D, 2) and hit_bits.shape == (bs, HW)
+        slots = torch.empty((bs, HW, M * Dh), dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().sca_fwd(
+                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
+                slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, 0,
+                _DTYPE_CODE[value.dtype], _stream_ptr(value))
+        _lib.check(rc, 'sca_fwd')
+        ctx.save_for_backward(value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits)
+        ctx.num_cam = num_cam
+        return slots
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, g_slots):
+        value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits = ctx.saved_tensors
+        num_cam = ctx.num_cam
+        Bc, Nk, M, Dh = value.shape
+        bs, HW, _, L, P, _ = offsets.shape
+        D = ref_cam.shape[3]
+        g_slots = g_slots.to(value.dtype).contiguous()
+        g_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        g_off = torch.empty_like(offsets)
+        g_log = torch.empty_like(logits)
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().sca_bwd(
+                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
+                g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
+                bs, num_cam, Nk, M, Dh, L, P, D, HW, 0, _DTYPE_CODE[value.dtype],
+                _stream_ptr(value))
+        _lib.check(rc, 'sca_bwd')
+        return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None)
+
+
+class QueueDeformAttnFunction(Function):
+    """out = mean over the queue of MSDA(value[b*Q+j], ref[b*Q+j] + offsets_j / (W, H), softmax(logits_j)).
+
+    value (bs*Q, Nk, M, Dh); offsets (bs, Nq, M, Q, L, P, 2); logits (bs, Nq, M, Q, L*P);
+    ref (bs*Q, Nq, L, 2).  Q = 2 is TemporalSelfAttention, Q = 1 CustomMSDeformableAttention.
+    """
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref, clamp):
+        _require_cuda(value=value, offsets=offsets, logits=logits, ref=ref)
+        value = _check_value(value)
+        offsets = offsets.to(torch.float32).contiguous()
+        logits = logits.to(torch.float32).contiguous()
+        ref = ref.to(torch.float32).contiguous()
+        shapes = spatial_shapes.to(torch.int64).contiguous()
+        starts = level_start_index.to(torch.int64).contiguous()
+        BQ, Nk, M, Dh = value.shape
+        bs, Nq, M2, Q, L, P, _ = offsets.shape
+        assert BQ == bs * Q and M2 == M and logits.shape == (bs, Nq, M, Q, L * P)
+        assert ref.shape == (bs * Q, Nq, L, 2), (ref.shape, (bs * Q, Nq, L, 2))
+        clamp = -1.0 if clamp is None else float(clamp)
+        out = torch.empty((bs, Nq, M * Dh), dtype=value.dtype, device=value.device)
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().tsa_fwd(
+                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                logits.data_ptr(), ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
+                clamp, _DTYPE_CODE[value.dtype], _stream_ptr(value))
+        _lib.check(rc, 'tsa_fwd')
+        ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
+        ctx.clamp = clamp
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, g_out):
+        value, shapes, starts, offsets, logits, ref = ctx.saved_tensors
+        BQ, Nk, M, Dh = value.shape
+        bs, Nq, _, Q, L, P, _ = offsets.shape
+        g_out = g_out.to(value.dtype).contiguous()
+        g_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        g_off = torch.empty_like(offsets)
+        g_log = torch.empty_like(logits)
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().tsa_bwd(
+                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+                logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
+                g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.clamp,
+                _DTYPE_CODE[value.dtype], _stream_ptr(value))
+        _lib.check(rc, 'tsa_bwd')
+        g_ref = None
+        if ctx.needs_input_grad[5]:
+            # loc = ref + off / (W, H)  =>  d ref = sum over heads and points of d off * (W, H)
+            wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(torch.float32)      # (L, 2)
+            g_ref = (g_off * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
+            g_ref = g_ref.permute(0, 2, 1, 3, 4).reshape(bs * Q, Nq, L, 2)
+        return g_value.to(value.dtype), None, None, g_off, g_log, g_ref, None

@@ -1,0 +1,212 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors for this path, so these are
+produced from the reference's own code: the in-tree operator restatement
+``multi_scale_deformable_attn_pytorch_2d`` (temporal_self_attention.py:293-348) and the
+reference's module classes ``SpatialCrossAttention`` / ``MSDeformableAttention3D`` /
+``TemporalSelfAttention`` / ``CustomMSDeformableAttention`` / ``BEVFormerEncoder`` (its
+``get_reference_points`` and ``point_sampling``), imported through ``oracle/refshim`` (a
+stand-in for the absent mmcv) and executed on their CPU branch.  Inputs, parameters and
+outputs are all stored, so the tests do not depend on RNG streams.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings('ignore')
+
+from oracle.refshim import load_reference  # noqa: E402
+import apollo_vision_net_b200.synthetic as syn  # noqa: E402  (numpy-only input generator)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _randomize(module, gen):
+    """Non-degenerate parameters (the reference init gives zero offset weights / uniform
+    attention, spatial_cross_attention.py:259,272): N(0, 0.02) on the offset / weight Linears."""
+    for name, p in module.named_parameters():
+        if name.endswith('sampling_offsets.weight') or name.endswith('attention_weights.weight'):
+            p.data = torch.randn(p.shape, generator=gen) * 0.02
+        elif name.endswith('attention_weights.bias'):
+            p.data = torch.randn(p.shape, generator=gen) * 0.5
+
+
+def _state(module, prefix):
+    return {prefix + k: _np(v) for k, v in module.state_dict().items()}
+
+
+def op_case(ref, gen):
+    B, M, Dh, Nq, P = 2, 4, 16, 37, 3
+    levels = [(9, 13), (5, 7), (3, 4)]
+    L = len(levels)
+    Nk = sum(h * w for h, w in levels)
+    value = torch.randn(B, Nk, M, Dh, generator=gen)
+    loc = torch.rand(B, Nq, M, L, P, 2, generator=gen) * 1.3 - 0.15
+    att = torch.softmax(torch.randn(B, Nq, M, L * P, generator=gen), -1).view(B, Nq, M, L, P)
+    shapes = torch.tensor(levels)
+    v, s, a = (t.clone().requires_grad_(True) for t in (value, loc, att))
+    out = ref.msda_pytorch_2d(v, shapes, s, a)
+    go = torch.randn(out.shape, generator=gen)
+    out.backward(go)
+    # float64 run of the same reference function: the yardstick for gradient tolerances
+    v64, s64, a64 = (t.double().clone().requires_grad_(True) for t in (value, loc, att))
+    out64 = ref.msda_pytorch_2d(v64, shapes, s64, a64)
+    out64.backward(go.double())
+    return dict(value=_np(value), loc=_np(loc), attn=_np(att), shapes=np.array(levels, np.int64),
+                out=_np(out), grad_out=_np(go), grad_value=_np(v.grad), grad_loc=_np(s.grad),
+                grad_attn=_np(a.grad), out64=_np(out64), grad_value64=_np(v64.grad),
+                grad_loc64=_np(s64.grad), grad_attn64=_np(a64.grad))
+
+
+def geometry_case(ref):
+    bs, H, W, D = 2, 50, 50, 4
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs, jitter=4.0, seed=3)
+    r3 = ref.BEVFormerEncoder.get_reference_points(H, W, 8.0, D, dim='3d', bs=bs, device='cpu',
+                                                   dtype=torch.float32)
+    r2 = ref.BEVFormerEncoder.get_reference_points(H, W, dim='2d', bs=bs, device='cpu',
+                                                   dtype=torch.float32)
+    metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6)
+             for b in range(bs)]
+
+    class _Self:  # point_sampling only reads self.debug_nan
+        pass
+    uv, mask = ref.BEVFormerEncoder.point_sampling(_Self(), r3, syn.PC_RANGE, metas)
+    lists = [m[0].sum(-1).nonzero().squeeze(-1) for m in mask]
+    out = dict(lidar2img=l2i, img_shape=np.array(img_shape), pc_range=np.array(syn.PC_RANGE),
+               bev_hw=np.array([H, W]), D=np.array(D), ref_3d=_np(r3), ref_2d=_np(r2),
+               ref_cam=_np(uv), mask_packed=np.packbits(_np(mask).astype(np.uint8)),
+               mask_shape=np.array(mask.shape), hit_count=np.array([len(x) for x in lists]))
+    for i, x in enumerate(lists):
+        out[f'hit_index_{i}'] = _np(x).astype(np.int32)
+    return out
+
+
+def sca_case(ref, gen):
+    bs, H, W, C, heads, P, D = 2, 12, 14, 64, 4, 8, 4
+    levels = [(12, 20), (6, 10)]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs, jitter=4.0, seed=5)
+    r3 = ref.BEVFormerEncoder.get_reference_points(H, W, 8.0, D, dim='3d', bs=bs, device='cpu',
+                                                   dtype=torch.float32)
+    metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6)
+             for b in range(bs)]
+
+    class _Self:
+        pass
+    uv, mask = ref.BEVFormerEncoder.point_sampling(_Self(), r3, syn.PC_RANGE, metas)
+    mod = ref.SpatialCrossAttention(
+        embed_dims=C, num_cams=6, pc_range=syn.PC_RANGE, dropout=0.1, batch_first=True,
+        deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C, num_heads=heads,
+                                  num_points=P, num_levels=len(levels), attn_logits_clamp=0.01))
+    _randomize(mod, gen)
+    mod.eval()
+    query = torch.randn(bs, H * W, C, generator=gen).requires_grad_(True)
+    feat = torch.randn(6, Nk, bs, C, generator=gen).requires_grad_(True)
+    qpos = torch.randn(bs, H * W, C, generator=gen)
+    shapes = torch.tensor(shapes_l)
+    starts = torch.tensor(starts_l)
+    out = mod(query, feat, feat, query_pos=qpos, reference_points_cam=uv, bev_mask=mask,
+              spatial_shapes=shapes, level_start_index=starts)
+    go = torch.randn(out.shape, generator=gen)
+    out.backward(go)
+    res = dict(query=_np(query), feat=_np(feat), query_pos=_np(qpos), ref_cam=_np(uv),
+               mask=_np(mask), shapes=np.array(shapes_l, np.int64), starts=np.array(starts_l, np.int64),
+               out=_np(out), grad_out=_np(go), grad_query=_np(query.grad), grad_feat=_np(feat.grad),
+               cfg=np.array([bs, H, W, C, heads, P, D]))
+    res.update(_state(mod, 'param.'))
+    for n, p in mod.named_parameters():
+        res['pgrad.' + n] = _np(p.grad)
+    # the stand-alone MSDeformableAttention3D on a rebatched slice (its own call contract)
+    da = mod.deformable_attention
+    idx = mask[0][0].sum(-1).nonzero().squeeze(-1)
+    q1 = query.detach()[:1, idx]
+    r1 = uv[0][:1, idx]
+    v1 = feat.detach()[0].permute(1, 0, 2)[:1]
+    res['da_query'], res['da_ref'], res['da_value'] = _np(q1), _np(r1), _np(v1)
+    res['da_out'] = _np(da(query=q1, key=v1, value=v1, reference_points=r1, spatial_shapes=shapes,
+                           level_start_index=starts))
+    return res
+
+
+def tsa_case(ref, gen, with_prev):
+    bs, H, W, C, heads, P = 2, 9, 11, 64, 4, 4
+    mod = ref.TemporalSelfAttention(embed_dims=C, num_heads=heads, num_levels=1, num_points=P,
+                                    attn_logits_clamp=0.6)
+    _randomize(mod, gen)
+    mod.eval()
+    query = torch.randn(bs, H * W, C, generator=gen).requires_grad_(True)
+    qpos = torch.randn(bs, H * W, C, generator=gen)
+    r2 = ref.BEVFormerEncoder.get_reference_points(H, W, dim='2d', bs=bs, device='cpu',
+                                                   dtype=torch.float32)
+    shift = torch.tensor([[0.03, -0.02], [-0.05, 0.01]])
+    hybrid = torch.stack([r2 + shift[:, None, None, :], r2], 1).reshape(bs * 2, H * W, 1, 2)
+    prev = torch.randn(bs * 2, H * W, C, generator=gen).requires_grad_(True) if with_prev else None
+    out = mod(query, prev, prev, query_pos=qpos, reference_points=hybrid,
+              spatial_shapes=torch.tensor([[H, W]]), level_start_index=torch.tensor([0]))
+    go = torch.randn(out.shape, generator=gen)
+    out.backward(go)
+    res = dict(query=_np(query), query_pos=_np(qpos), ref=_np(hybrid), out=_np(out), grad_out=_np(go),
+               grad_query=_np(query.grad), cfg=np.array([bs, H, W, C, heads, P]))
+    if with_prev:
+        res['prev'] = _np(prev)
+        res['grad_prev'] = _np(prev.grad)
+    res.update(_state(mod, 'param.'))
+    for n, p in mod.named_parameters():
+        res['pgrad.' + n] = _np(p.grad)
+    return res
+
+
+def decoder_case(ref, gen):
+    bs, H, W, C, heads, P, Nq = 2, 10, 10, 64, 4, 4, 60
+    mod = ref.CustomMSDeformableAttention(embed_dims=C, num_heads=heads, num_levels=1, num_points=P,
+                                          attn_logits_clamp=0.8)
+    _randomize(mod, gen)
+    mod.eval()
+    query = torch.randn(Nq, bs, C, generator=gen).requires_grad_(True)
+    qpos = torch.randn(Nq, bs, C, generator=gen)
+    value = torch.randn(H * W, bs, C, generator=gen).requires_grad_(True)
+    refp = torch.rand(bs, Nq, 1, 2, generator=gen).requires_grad_(True)
+    out = mod(query, None, value, query_pos=qpos, reference_points=refp,
+              spatial_shapes=torch.tensor([[H, W]]), level_start_index=torch.tensor([0]))
+    go = torch.randn(out.shape, generator=gen)
+    out.backward(go)
+    res = dict(query=_np(query), query_pos=_np(qpos), value=_np(value), ref=_np(refp), out=_np(out),
+               grad_out=_np(go), grad_query=_np(query.grad), grad_value=_np(value.grad),
+               grad_ref=_np(refp.grad), cfg=np.array([bs, H, W, C, heads, P, Nq]))
+    res.update(_state(mod, 'param.'))
+    for n, p in mod.named_parameters():
+        res['pgrad.' + n] = _np(p.grad)
+    return res
+
+
+def main():
+    ref = load_reference()
+    gen = torch.Generator().manual_seed(20261018)
+    cases = {
+        'op_small': op_case(ref, gen),
+        'geometry_tiny': geometry_case(ref),
+        'sca_small': sca_case(ref, gen),
+        'tsa_prev': tsa_case(ref, gen, True),
+        'tsa_first_frame': tsa_case(ref, gen, False),
+        'decoder_small': decoder_case(ref, gen),
+    }
+    for name, arrays in cases.items():
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, **arrays)
+        print(f'{name}: {len(arrays)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')
+
+
+if __name__ == '__main__':
+    main()

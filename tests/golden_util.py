@@ -1,0 +1,106 @@
+"""Helpers to replay the golden fixtures (tests/golden/*.npz) through the oracle or CUDA modules."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + '.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+def T(a, device='cpu', grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    if grad:
+        t.requires_grad_(True)
+    return t
+
+
+def params(g):
+    return {k[len('param.'):]: torch.from_numpy(v) for k, v in g.items() if k.startswith('param.')}
+
+
+def pgrads(g):
+    return {k[len('pgrad.'):]: v for k, v in g.items() if k.startswith('pgrad.')}
+
+
+def unpack_mask(g):
+    shape = tuple(int(x) for x in g['mask_shape'])
+    n = int(np.prod(shape))
+    return np.unpackbits(g['mask_packed'])[:n].reshape(shape).astype(bool)
+
+
+def build_sca(g, kind, device='cpu'):
+    bs, H, W, C, heads, P, D = (int(x) for x in g['cfg'])
+    L = len(g['shapes'])
+    cfg = dict(embed_dims=C, num_cams=6, dropout=0.1, batch_first=True,
+               deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                         num_heads=heads, num_points=P, num_levels=L,
+                                         attn_logits_clamp=0.01))
+    if kind == 'oracle':
+        from oracle.modules_oracle import OracleSpatialCrossAttention as cls
+    else:
+        from apollo_vision_net_b200.modules import SpatialCrossAttention as cls
+    m = cls(**cfg)
+    m.load_state_dict(params(g))
+    return m.to(device).eval()
+
+
+def build_tsa(g, kind, device='cpu'):
+    bs, H, W, C, heads, P = (int(x) for x in g['cfg'])
+    cfg = dict(embed_dims=C, num_heads=heads, num_levels=1, num_points=P, attn_logits_clamp=0.6)
+    if kind == 'oracle':
+        from oracle.modules_oracle import OracleTemporalSelfAttention as cls
+    else:
+        from apollo_vision_net_b200.modules import TemporalSelfAttention as cls
+    m = cls(**cfg)
+    m.load_state_dict(params(g))
+    return m.to(device).eval()
+
+
+def build_decoder(g, kind, device='cpu'):
+    bs, H, W, C, heads, P, Nq = (int(x) for x in g['cfg'])
+    cfg = dict(embed_dims=C, num_heads=heads, num_levels=1, num_points=P, attn_logits_clamp=0.8)
+    if kind == 'oracle':
+        from oracle.modules_oracle import OracleCustomMSDeformableAttention as cls
+    else:
+        from apollo_vision_net_b200.modules import CustomMSDeformableAttention as cls
+    m = cls(**cfg)
+    m.load_state_dict(params(g))
+    return m.to(device).eval()
+
+
+def run_sca(m, g, device='cpu'):
+    q = T(g['query'], device, True)
+    feat = T(g['feat'], device, True)
+    out = m(q, feat, feat, query_pos=T(g['query_pos'], device),
+            reference_points_cam=T(g['ref_cam'], device), bev_mask=T(g['mask'], device),
+            spatial_shapes=T(g['shapes'], device), level_start_index=T(g['starts'], device))
+    out.backward(T(g['grad_out'], device))
+    return out, q.grad, feat.grad
+
+
+def run_tsa(m, g, device='cpu'):
+    bs, H, W, C, heads, P = (int(x) for x in g['cfg'])
+    q = T(g['query'], device, True)
+    prev = T(g['prev'], device, True) if 'prev' in g else None
+    out = m(q, prev, prev, query_pos=T(g['query_pos'], device), reference_points=T(g['ref'], device),
+            spatial_shapes=torch.tensor([[H, W]], device=device),
+            level_start_index=torch.tensor([0], device=device))
+    out.backward(T(g['grad_out'], device))
+    return out, q.grad, (prev.grad if prev is not None else None)
+
+
+def run_decoder(m, g, device='cpu'):
+    bs, H, W, C, heads, P, Nq = (int(x) for x in g['cfg'])
+    q = T(g['query'], device, True)
+    v = T(g['value'], device, True)
+    r = T(g['ref'], device, True)
+    out = m(q, None, v, query_pos=T(g['query_pos'], device), reference_points=r,
+            spatial_shapes=torch.tensor([[H, W]], device=device),
+            level_start_index=torch.tensor([0], device=device))
+    out.backward(T(g['grad_out'], device))
+    return out, q.grad, v.grad, r.grad

@@ -1,0 +1,318 @@
+"""GPU parity of the fused kernels and the registry-named modules against (a) the golden
+vectors produced by the unmodified reference and (b) the CPU oracle on larger seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry_oracle as G
+from oracle.modules_oracle import (OracleBEVFormerEncoder, OracleCustomMSDeformableAttention,
+                                   OracleSpatialCrossAttention, OracleTemporalSelfAttention)
+from tests import golden_util as gu
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+FWD, BWD = 1e-5, 1e-4        # north_star: forward 1e-5 relative in fp32, gradients 1e-4
+
+
+def _randomize(m, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for n, p in m.named_parameters():
+        if n.endswith('sampling_offsets.weight') or n.endswith('attention_weights.weight'):
+            p.data = torch.randn(p.shape, generator=g) * 0.02
+        elif n.endswith('attention_weights.bias'):
+            p.data = torch.randn(p.shape, generator=g) * 0.5
+
+
+# ------------------------------------------------------------------ geometry (bit-exact) ---
+def _check_geometry(l2i, img_shape, H, W, D, bs, pc_range):
+    import apollo_vision_net_b200 as pkg
+    r3 = G.reference_points_3d(H, W, pc_range[5] - pc_range[2], D, bs=bs)
+    uv, mask = G.point_sampling(r3, pc_range, l2i, img_shape[0], img_shape[1])
+    lists, max_len = G.camera_hit_lists(mask)
+    geo = pkg.bev_point_sampling(r3.to(DEV), pc_range, l2i, img_shape[0], img_shape[1])
+    torch.cuda.synchronize()
+    assert torch.equal(geo.bev_mask.cpu(), mask)                       # bit-exact
+    assert torch.equal(geo.reference_points_cam.cpu(), uv)             # same op order => identical
+    counts = geo.hit_count.cpu().tolist()
+    assert counts == [len(x) for x in lists]
+    for i, x in enumerate(lists):
+        assert torch.equal(geo.hit_index[i, :counts[i]].cpu().long(), x)
+        assert bool((geo.hit_index[i, counts[i]:] == -1).all())
+    bits = geo.hit_bits.cpu()
+    for i in range(mask.shape[0]):
+        assert torch.equal(((bits >> i) & 1).bool(), mask[i].any(-1))
+    return geo
+
+
+def test_point_sampling_golden():
+    g = gu.load('geometry_tiny')
+    import apollo_vision_net_b200 as pkg
+    H, W = (int(x) for x in g['bev_hw'])
+    geo = pkg.bev_point_sampling(gu.T(g['ref_3d'], DEV), list(g['pc_range']), g['lidar2img'],
+                                 int(g['img_shape'][0]), int(g['img_shape'][1]))
+    assert np.array_equal(geo.bev_mask.cpu().numpy(), gu.unpack_mask(g))
+    assert np.array_equal(geo.reference_points_cam.cpu().numpy(), g['ref_cam'])
+    assert geo.hit_count.cpu().tolist() == g['hit_count'].tolist()
+    for i in range(6):
+        n = int(g['hit_count'][i])
+        assert np.array_equal(geo.hit_index[i, :n].cpu().numpy(), g[f'hit_index_{i}'])
+
+
+@pytest.mark.parametrize('H,W,scale,bs', [(50, 50, 0.5, 1), (200, 200, 1.0, 1), (37, 61, 0.5, 3),
+                                          (400, 400, 1.0, 1)])
+def test_point_sampling_bit_exact(H, W, scale, bs):
+    import apollo_vision_net_b200.synthetic as syn
+    l2i, img_shape = syn.camera_rig(scale, bs=bs, jitter=5.0, seed=H)
+    _check_geometry(l2i, img_shape, H, W, 4, bs, syn.PC_RANGE)
+
+
+def test_point_sampling_boundary_grazing():
+    """Points that land exactly on z = eps, u = 0, u = 1, v = 0, v = 1: the strict inequalities of
+    encoder.py:186,228-231 must exclude them.  Exactly representable arithmetic (integer camera
+    matrix, power-of-two image size, pc_range mapping [0,1] -> integers)."""
+    H, W, D = 8, 8, 2
+    pc_range = [0.0, 0.0, 0.0, 8.0, 8.0, 8.0]
+    # u = 64 * X / Z, v = 64 * Y / Z with image 256 x 256: X/Z = 4 -> u_norm = 1 exactly; X = 0 never
+    # happens (cell centres), so add a second camera with an offset that puts centres on u = 0.
+    l2i = np.zeros((1, 3, 4, 4), np.float32)
+    l2i[0, 0] = [[64, 0, 0, 0], [0, 64, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    l2i[0, 1] = [[64, 0, 0, -32], [0, 64, 0, -96], [0, 0, 1, 0], [0, 0, 0, 1]]    # centres hit u=0 / v=0
+    l2i[0, 2] = [[64, 0, 0, 0], [0, 64, 0, 0], [0, 0, 1, -2], [0, 0, 0, 1]]        # z - 2: z=2 -> 0 <= eps
+    geo = _check_geometry(l2i, (256, 256, 3), H, W, D, 1, pc_range)
+    assert 0 < int(geo.mask_u8.sum()) < geo.mask_u8.numel()
+
+
+# ------------------------------------------------------------------ modules vs golden ------
+def test_sca_module_golden():
+    g = gu.load('sca_small')
+    m = gu.build_sca(g, 'cuda', DEV)
+    out, gq, gf = gu.run_sca(m, g, DEV)
+    assert rel_err(out, g['out']) <= FWD
+    assert rel_err(gq, g['grad_query']) <= BWD
+    assert rel_err(gf, g['grad_feat']) <= BWD
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, gu.pgrads(g)[n]) <= BWD, n
+    da = m.deformable_attention        # stand-alone contract: op-boundary path
+    o = da(query=gu.T(g['da_query'], DEV), key=gu.T(g['da_value'], DEV), value=gu.T(g['da_value'], DEV),
+           reference_points=gu.T(g['da_ref'], DEV), spatial_shapes=gu.T(g['shapes'], DEV),
+           level_start_index=gu.T(g['starts'], DEV))
+    assert rel_err(o, g['da_out']) <= FWD
+
+
+@pytest.mark.parametrize('name', ['tsa_prev', 'tsa_first_frame'])
+def test_tsa_module_golden(name):
+    g = gu.load(name)
+    m = gu.build_tsa(g, 'cuda', DEV)
+    out, gq, gp = gu.run_tsa(m, g, DEV)
+    assert rel_err(out, g['out']) <= FWD
+    assert rel_err(gq, g['grad_query']) <= BWD
+    if gp is not None:
+        assert rel_err(gp, g['grad_prev']) <= BWD
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, gu.pgrads(g)[n]) <= BWD, n
+
+
+def test_decoder_module_golden():
+    g = gu.load('decoder_small')
+    m = gu.build_decoder(g, 'cuda', DEV)
+    out, gq, gv, gr = gu.run_decoder(m, g, DEV)
+    assert rel_err(out, g['out']) <= FWD
+    assert rel_err(gq, g['grad_query']) <= BWD
+    assert rel_err(gv, g['grad_value']) <= BWD
+    assert rel_err(gr, g['grad_ref']) <= BWD
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, gu.pgrads(g)[n]) <= BWD, n
+
+
+# ------------------------------------------------------------------ modules vs oracle ------
+def _sca_inputs(bs, H, W, levels, C, seed, scale=0.5):
+    import apollo_vision_net_b200.synthetic as syn
+    g = torch.Generator().manual_seed(seed)
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(scale, bs=bs, jitter=4.0, seed=seed)
+    r3 = G.reference_points_3d(H, W, 8.0, 4, bs=bs)
+    uv, mask = G.point_sampling(r3, syn.PC_RANGE, l2i, img_shape[0], img_shape[1])
+    q = torch.randn(bs, H * W, C, generator=g)
+    feat = torch.randn(6, Nk, bs, C, generator=g)
+    go = torch.randn(bs, H * W, C, generator=g)
+    return q, feat, go, uv, mask, torch.tensor(shapes_l), torch.tensor(starts_l)
+
+
+@pytest.mark.parametrize('bs,H,W,levels', [
+    (1, 50, 50, [(28, 48)]),                                      # BASELINE config 1 (tiny)
+    (2, 30, 40, [(29, 50), (15, 25), (8, 13), (4, 7)]),           # 4 levels, bs=2 (batch-0 quirk)
+])
+def test_sca_module_vs_oracle(bs, H, W, levels):
+    from apollo_vision_net_b200.modules import SpatialCrossAttention
+    import apollo_vision_net_b200.synthetic as syn
+    C = 256
+    cfg = dict(embed_dims=C, pc_range=syn.PC_RANGE, batch_first=True,
+               deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                         num_points=8, num_levels=len(levels)))
+    o = OracleSpatialCrossAttention(**cfg)
+    _randomize(o, 3)
+    o.eval()
+    m = SpatialCrossAttention(**cfg)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).eval()
+    q, feat, go, uv, mask, shapes, starts = _sca_inputs(bs, H, W, levels, C, seed=11)
+    q1, f1 = q.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    ref = o(q1, f1, f1, reference_points_cam=uv, bev_mask=mask, spatial_shapes=shapes,
+            level_start_index=starts)
+    ref.backward(go)
+    q2, f2 = q.to(DEV).requires_grad_(True), feat.to(DEV).requires_grad_(True)
+    out = m(q2, f2, f2, reference_points_cam=uv.to(DEV), bev_mask=mask.to(DEV),
+            spatial_shapes=shapes.to(DEV), level_start_index=starts.to(DEV))
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= FWD
+    assert rel_err(q2.grad, q1.grad) <= BWD
+    assert rel_err(f2.grad, f1.grad) <= BWD
+    og = dict(o.named_parameters())
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, og[n].grad) <= BWD, n
+
+
+def test_tsa_module_vs_oracle_tiny_config():
+    from apollo_vision_net_b200.modules import TemporalSelfAttention
+    bs, H, W, C = 1, 50, 50, 256
+    o = OracleTemporalSelfAttention(embed_dims=C, num_levels=1, num_points=4)
+    _randomize(o, 5)
+    o.eval()
+    m = TemporalSelfAttention(embed_dims=C, num_levels=1, num_points=4)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).eval()
+    g = torch.Generator().manual_seed(2)
+    q = torch.randn(bs, H * W, C, generator=g)
+    prev = torch.randn(bs * 2, H * W, C, generator=g)
+    pos = torch.randn(bs, H * W, C, generator=g)
+    go = torch.randn(bs, H * W, C, generator=g)
+    r2 = G.reference_points_2d(H, W, bs=bs)
+    hy = torch.stack([r2 + 0.013, r2], 1).reshape(bs * 2, H * W, 1, 2)
+    kw = dict(spatial_shapes=torch.tensor([[H, W]]), level_start_index=torch.tensor([0]))
+    q1, p1 = q.clone().requires_grad_(True), prev.clone().requires_grad_(True)
+    ref = o(q1, p1, p1, query_pos=pos, reference_points=hy, **kw)
+    ref.backward(go)
+    q2, p2 = q.to(DEV).requires_grad_(True), prev.to(DEV).requires_grad_(True)
+    out = m(q2, p2, p2, query_pos=pos.to(DEV), reference_points=hy.to(DEV),
+            **{k: v.to(DEV) for k, v in kw.items()})
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= FWD
+    assert rel_err(q2.grad, q1.grad) <= BWD
+    assert rel_err(p2.grad, p1.grad) <= BWD
+    og = dict(o.named_parameters())
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, og[n].grad) <= BWD, n
+
+
+def test_maptrv2_cross_attention_config4():
+    """BASELINE config 4: (50 + 300) vectors x 20 points = 7000 queries, L=1, P=4, BEV 50x50."""
+    from apollo_vision_net_b200.modules import CustomMSDeformableAttention
+    bs, H, W, C, Nq = 1, 50, 50, 256, 7000
+    o = OracleCustomMSDeformableAttention(embed_dims=C, num_levels=1)
+    _randomize(o, 8)
+    o.eval()
+    m = CustomMSDeformableAttention(embed_dims=C, num_levels=1)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).eval()
+    g = torch.Generator().manual_seed(6)
+    q = torch.randn(Nq, bs, C, generator=g)
+    pos = torch.randn(Nq, bs, C, generator=g)
+    val = torch.randn(H * W, bs, C, generator=g)
+    rp = torch.rand(bs, Nq, 1, 2, generator=g)
+    go = torch.randn(Nq, bs, C, generator=g)
+    kw = dict(spatial_shapes=torch.tensor([[H, W]]), level_start_index=torch.tensor([0]))
+    q1, v1 = q.clone().requires_grad_(True), val.clone().requires_grad_(True)
+    ref = o(q1, None, v1, query_pos=pos, reference_points=rp, **kw)
+    ref.backward(go)
+    q2, v2 = q.to(DEV).requires_grad_(True), val.to(DEV).requires_grad_(True)
+    out = m(q2, None, v2, query_pos=pos.to(DEV), reference_points=rp.to(DEV),
+            **{k: v.to(DEV) for k, v in kw.items()})
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= FWD
+    assert rel_err(q2.grad, q1.grad) <= BWD
+    assert rel_err(v2.grad, v1.grad) <= BWD
+
+
+def test_encoder_tiny_config1_vs_oracle():
+    """BASELINE config 1: tiny encoder (3 layers, 50x50 BEV, 6 cams, 1 level, dim 256),
+    forward + backward, against the oracle encoder (same state_dict)."""
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    bs, H, W, C = 1, 50, 50, 256
+    levels = syn.LEVELS_TINY
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs)
+    o = OracleBEVFormerEncoder(num_layers=3, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+                               embed_dims=C, feedforward_channels=512, num_levels=1)
+    _randomize(o, 12)
+    o.eval()
+    enc = pkg.build_transformer_layer_sequence(dict(
+        type='BEVFormerEncoder', num_layers=3, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+        return_intermediate=False,
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1),
+                       dict(type='SpatialCrossAttention', pc_range=syn.PC_RANGE, embed_dims=C,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_points=8, num_levels=1))],
+            feedforward_channels=512, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    enc.load_state_dict(o.state_dict())
+    enc.to(DEV).eval()
+    g = torch.Generator().manual_seed(21)
+    bevq = torch.randn(H * W, bs, C, generator=g)
+    pos = torch.randn(H * W, bs, C, generator=g)
+    prev = torch.randn(H * W, bs, C, generator=g)
+    feat = torch.randn(6, Nk, bs, C, generator=g)
+    go = torch.randn(bs, H * W, C, generator=g)
+    shift = torch.tensor([[0.01, -0.02]])
+    shapes, starts = torch.tensor(shapes_l), torch.tensor(starts_l)
+    for prev_in in (prev, None):
+        o.zero_grad()
+        enc.zero_grad()
+        f1 = feat.clone().requires_grad_(True)
+        ref = o(bevq, f1, f1, bev_h=H, bev_w=W, bev_pos=pos, spatial_shapes=shapes,
+                level_start_index=starts, prev_bev=prev_in, shift=shift, lidar2img=l2i,
+                img_h=img_shape[0], img_w=img_shape[1])
+        ref.backward(go)
+        f2 = feat.to(DEV).requires_grad_(True)
+        metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6)
+                 for b in range(bs)]
+        out = enc(bevq.to(DEV), f2, f2, bev_h=H, bev_w=W, bev_pos=pos.to(DEV),
+                  spatial_shapes=shapes.to(DEV), level_start_index=starts.to(DEV),
+                  prev_bev=None if prev_in is None else prev_in.to(DEV), shift=shift.to(DEV),
+                  img_metas=metas)
+        out.backward(go.to(DEV))
+        assert rel_err(out, ref) <= 2e-5          # 3 layers deep
+        assert rel_err(f2.grad, f1.grad) <= 2e-4
+        og = dict(o.named_parameters())
+        for n, p in enc.named_parameters():
+            assert rel_err(p.grad, og[n].grad) <= 5e-4, n
+
+
+def test_fused_bf16_within_tolerance():
+    """bf16 value path of the fused SCA kernel: within 1e-2 of the fp32 oracle (north_star)."""
+    from apollo_vision_net_b200.modules import SpatialCrossAttention
+    import apollo_vision_net_b200.synthetic as syn
+    C = 256
+    levels = [(29, 50), (15, 25)]
+    cfg = dict(embed_dims=C, pc_range=syn.PC_RANGE, batch_first=True,
+               deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                         num_points=8, num_levels=len(levels)))
+    o = OracleSpatialCrossAttention(**cfg)
+    _randomize(o, 3)
+    o.eval()
+    m = SpatialCrossAttention(**cfg)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).to(torch.bfloat16).eval()
+    q, feat, go, uv, mask, shapes, starts = _sca_inputs(1, 30, 30, levels, C, seed=4)
+    ref = o(q, feat, feat, reference_points_cam=uv, bev_mask=mask, spatial_shapes=shapes,
+            level_start_index=starts)
+    out = m(q.to(DEV).bfloat16(), feat.to(DEV).bfloat16(), feat.to(DEV).bfloat16(),
+            reference_points_cam=uv.to(DEV), bev_mask=mask.to(DEV),
+            spatial_shapes=shapes.to(DEV), level_start_index=starts.to(DEV))
+    assert out.dtype == torch.bfloat16
+    # compare the attention contribution (output minus the residual query) at bf16 resolution
+    assert rel_err(out.float().cpu() - q.bfloat16().float(), ref - q) <= 3e-2
+    assert rel_err(out, ref) <= 1e-2
