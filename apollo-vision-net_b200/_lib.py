@@ -110,6 +110,46 @@ def launch_count():
     return int(lib().msda_launch_count())
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing on the launching stream (used by bench.py for the
+    live roofline measurement).  While installed, every C-ABI launch is bracketed by two events."""
+
+    def __init__(self):
+        self.records = {}
+
+    def summary(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, evs in self.records.items():
+            ms = [s.elapsed_time(e) for s, e in evs]
+            out[name] = dict(launches=len(ms), mean_us=1e3 * sum(ms) / len(ms), min_us=1e3 * min(ms))
+        return out
+
+
+_timer = None
+
+
+def set_timer(timer):
+    global _timer
+    _timer = timer
+
+
+def call(name, *args):
+    """Invoke C entry point `name`; raises on a non-zero return code."""
+    fn = getattr(lib(), name)
+    if _timer is None:
+        rc = fn(*args)
+    else:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _timer.records.setdefault(name, []).append((s, e))
+    check(rc, name)
+
+
 def header_symbols():
     """Function names declared in include/msda_b200.h (used by the ABI export test)."""
     import re

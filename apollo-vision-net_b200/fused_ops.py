@@ -53,11 +53,9 @@ def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w):
     hit_count = torch.empty((num_cam,), dtype=torch.int32, device=dev)
     pc = (ctypes.c_double * 6)(*[float(x) for x in pc_range])
     with torch.cuda.device(dev):
-        rc = _lib.lib().bev_point_sampling(
-            ref_3d.data_ptr(), l2i.data_ptr(), ctypes.cast(pc, ctypes.c_void_p), float(img_h),
+        _lib.call('bev_point_sampling', ref_3d.data_ptr(), l2i.data_ptr(), ctypes.cast(pc, ctypes.c_void_p), float(img_h),
             float(img_w), bs, num_cam, HW, D, ref_cam.data_ptr(), mask.data_ptr(),
             hit_bits.data_ptr(), hit_index.data_ptr(), hit_count.data_ptr(), _stream_ptr(ref_3d))
-    _lib.check(rc, 'bev_point_sampling')
     return BevGeometry(ref_cam, mask, hit_bits, hit_index, hit_count, D)
 
 
@@ -107,12 +105,10 @@ class SpatialCrossAttnFunction(Function):
         assert ref_cam.shape == (num_cam, bs, HW, D, 2) and hit_bits.shape == (bs, HW)
         slots = torch.empty((bs, HW, M * Dh), dtype=value.dtype, device=value.device)
         with torch.cuda.device(value.device):
-            rc = _lib.lib().sca_fwd(
-                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+            _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, 0,
                 _DTYPE_CODE[value.dtype], _stream_ptr(value))
-        _lib.check(rc, 'sca_fwd')
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits)
         ctx.num_cam = num_cam
         return slots
@@ -131,13 +127,11 @@ class SpatialCrossAttnFunction(Function):
         g_off = torch.empty_like(offsets)
         g_log = torch.empty_like(logits)
         with torch.cuda.device(value.device):
-            rc = _lib.lib().sca_bwd(
-                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+            _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
                 bs, num_cam, Nk, M, Dh, L, P, D, HW, 0, _DTYPE_CODE[value.dtype],
                 _stream_ptr(value))
-        _lib.check(rc, 'sca_bwd')
         return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None)
 
 
@@ -165,11 +159,9 @@ class QueueDeformAttnFunction(Function):
         clamp = -1.0 if clamp is None else float(clamp)
         out = torch.empty((bs, Nq, M * Dh), dtype=value.dtype, device=value.device)
         with torch.cuda.device(value.device):
-            rc = _lib.lib().tsa_fwd(
-                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+            _lib.call('tsa_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
                 clamp, _DTYPE_CODE[value.dtype], _stream_ptr(value))
-        _lib.check(rc, 'tsa_fwd')
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
         ctx.clamp = clamp
         return out
@@ -186,12 +178,10 @@ class QueueDeformAttnFunction(Function):
         g_off = torch.empty_like(offsets)
         g_log = torch.empty_like(logits)
         with torch.cuda.device(value.device):
-            rc = _lib.lib().tsa_bwd(
-                value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
+            _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
                 g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.clamp,
                 _DTYPE_CODE[value.dtype], _stream_ptr(value))
-        _lib.check(rc, 'tsa_bwd')
         g_ref = None
         if ctx.needs_input_grad[5]:
             # loc = ref + off / (W, H)  =>  d ref = sum over heads and points of d off * (W, H)

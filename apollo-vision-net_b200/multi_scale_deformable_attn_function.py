@@ -94,11 +94,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     B, Nk, M, Dh, L, Nq, P = _dims(value, loc, attn, shapes, starts)
     out = torch.empty((B, Nq, M * Dh), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
-        rc = _lib.lib().msda_fwd(value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+        _lib.call('msda_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
                                  loc.data_ptr(), attn.data_ptr(), out.data_ptr(),
                                  B, Nk, M, Dh, L, Nq, P, _DTYPE_CODE[value.dtype],
                                  _DTYPE_CODE[loc.dtype], int(im2col_step), _stream_ptr(value))
-    _lib.check(rc, 'ms_deform_attn_forward')
     return out
 
 
@@ -109,12 +108,11 @@ def _backward_raw(value, shapes, starts, loc, attn, grad_output, im2col_step):
     g_loc = torch.empty(loc.shape, dtype=torch.float32, device=value.device)
     g_attn = torch.empty(attn.shape, dtype=torch.float32, device=value.device)
     with torch.cuda.device(value.device):
-        rc = _lib.lib().msda_bwd(value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
+        _lib.call('msda_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(),
                                  loc.data_ptr(), attn.data_ptr(), grad_output.data_ptr(),
                                  g_value.data_ptr(), g_loc.data_ptr(), g_attn.data_ptr(),
                                  B, Nk, M, Dh, L, Nq, P, _DTYPE_CODE[value.dtype],
                                  _DTYPE_CODE[loc.dtype], int(im2col_step), _stream_ptr(value))
-    _lib.check(rc, 'ms_deform_attn_backward')
     return g_value, g_loc, g_attn
 
 

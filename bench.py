@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: BEVFormer-base encoder forward+backward on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A *step* is one pass of the hot path over one frame: the 6-layer BEVFormer-base encoder
+(BASELINE.json configs[1]: 200x200 BEV, 6 cameras, 4 feature levels, 8 points x 4 Z-anchors,
+bf16) forward + backward -- temporal self-attention, spatial cross-attention, LayerNorm, FFN,
+with the image features requiring grad.  The metric is sampled points per second: the
+(batch, query, head, level, point) bilinear samples the deformable attention takes in one
+forward pass of the step (SCA over the cameras that see each query + TSA), divided by the
+fwd+bwd step time.  `value` is measured with every input resident in HBM; `e2e` is the same
+step driven from pinned HOST buffers (H2D of the frame's inputs, D2H of the BEV output and the
+loss inside the timed region).  With N > 1 every rank runs its own frame (batch-level data
+parallelism, the reference's only strategy, apis/mmdet_train.py:71-85) and the parameter
+gradients are all-reduced over NCCL each step.
+
+`--impl reference` times the reference's own CPU implementation of the same path (the oracle
+port of its CPU branch: multi_scale_deformable_attn_pytorch inside SCA/TSA, fp32, all host
+threads) on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'BEVFormer-base encoder MSDeformAttn fwd+bwd sampled-points/s'
+UNIT = 'points/s'
+C, HEADS, FFN_DIM, SCA_POINTS, TSA_POINTS, PILLAR = 256, 8, 512, 8, 4, 4
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# --------------------------------------------------------------------------- workload ------
+def encoder_cfg(num_layers, num_levels, pc_range):
+    return dict(
+        type='BEVFormerEncoder', num_layers=num_layers, pc_range=pc_range,
+        num_points_in_pillar=PILLAR, return_intermediate=False,
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[
+                dict(type='TemporalSelfAttention', embed_dims=C, num_points=TSA_POINTS, num_levels=1),
+                dict(type='SpatialCrossAttention', pc_range=pc_range, embed_dims=C,
+                     deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                               num_points=SCA_POINTS, num_levels=num_levels))],
+            feedforward_channels=FFN_DIM, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
+
+
+def randomize(module, seed):
+    """Reference init, then N(0, 0.02) on the offset / weight Linears so that offsets and the
+    softmax are non-degenerate."""
+    g = torch.Generator().manual_seed(seed)
+    for n, p in module.named_parameters():
+        if n.endswith('sampling_offsets.weight') or n.endswith('attention_weights.weight'):
+            p.data = (torch.randn(p.shape, generator=g) * 0.02).to(p.dtype)
+
+
+def host_inputs(bev_h, bev_w, levels, seed, dtype, pin):
+    import apollo_vision_net_b200.synthetic as syn
+    g = torch.Generator().manual_seed(seed)
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    HW = bev_h * bev_w
+
+    def mk(*shape):
+        t = torch.randn(*shape, generator=g).to(dtype)
+        return t.pin_memory() if pin else t
+    return dict(feat=mk(6, Nk, 1, C), bev_query=mk(HW, 1, C), bev_pos=mk(HW, 1, C),
+                prev_bev=mk(HW, 1, C), grad_w=mk(1, HW, C),
+                shift=torch.tensor([[0.005, 0.003]]),
+                shapes=torch.tensor(shapes_l, dtype=torch.int64),
+                starts=torch.tensor(starts_l, dtype=torch.int64))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower() == 'active':
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------- B200 arm ------
+def run_b200(args):
+    import torch.distributed as dist
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    from apollo_vision_net_b200 import _lib
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    if args.gpus > 1 and world == 1:
+        raise SystemExit('launch N > 1 with torch.distributed.run (one rank per GPU)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    pkg.build()
+
+    dtype = torch.bfloat16
+    bev_h = bev_w = args.bev
+    levels = syn.LEVELS_BASE
+    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE))
+    randomize(enc, 0)
+    enc.to(dev).to(dtype).train()
+    for m in enc.modules():                       # dropout off: deterministic, parity-checked config
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    params = [p for p in enc.parameters() if p.requires_grad]
+    l2i, img_shape = syn.camera_rig(1.0, bs=1)
+    l2i_dev = torch.as_tensor(l2i).to(dev)
+
+    host = host_inputs(bev_h, bev_w, levels, seed=1 + rank, dtype=dtype, pin=True)
+    devin = {k: v.to(dev) for k, v in host.items()}
+    shapes, starts = devin['shapes'], devin['starts']
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def encoder_step(feat, bev_query, bev_pos, prev_bev, grad_w, shift):
+        for p in params:
+            p.grad = None
+        feat.requires_grad_(True)
+        out = enc(bev_query, feat, feat, bev_h=bev_h, bev_w=bev_w, bev_pos=bev_pos,
+                  spatial_shapes=shapes, level_start_index=starts, prev_bev=prev_bev, shift=shift,
+                  lidar2img=l2i_dev, img_shape=img_shape)
+        loss = (out.float() * grad_w.float()).sum() * (1.0 / out.numel())
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return out, loss
+
+    def step_device():
+        flush.zero_()                              # L2 flushed between iterations (inside the timed region)
+        return encoder_step(devin['feat'].detach(), devin['bev_query'], devin['bev_pos'],
+                            devin['prev_bev'], devin['grad_w'], devin['shift'])
+
+    out_host = torch.empty((1, bev_h * bev_w, C), dtype=dtype).pin_memory()
+    h2d_keys = ('feat', 'bev_query', 'bev_pos', 'prev_bev', 'grad_w', 'shift')
+
+    def step_e2e():
+        flush.zero_()
+        d = {k: host[k].to(dev, non_blocking=True) for k in h2d_keys}
+        out, loss = encoder_step(d['feat'], d['bev_query'], d['bev_pos'], d['prev_bev'],
+                                 d['grad_w'], d['shift'])
+        out_host.copy_(out.detach(), non_blocking=True)
+        return float(loss.item())                  # D2H read of the step's result (syncs)
+
+    # sampled points of one forward pass (what the metric counts)
+    ref3d = enc.get_reference_points(bev_h, bev_w, syn.PC_RANGE[5] - syn.PC_RANGE[2], PILLAR,
+                                     dim='3d', bs=1, device=dev, dtype=torch.float32)
+    geo = pkg.bev_point_sampling(ref3d, syn.PC_RANGE, l2i, img_shape[0], img_shape[1])
+    pairs = int(geo.hit_count.sum().item())
+    HW = bev_h * bev_w
+    sca_points = pairs * HEADS * len(levels) * SCA_POINTS
+    tsa_points = 2 * HW * HEADS * TSA_POINTS
+    points_per_step = args.layers * (sca_points + tsa_points)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    timer = _lib.KernelTimer()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        _lib.set_timer(timer)
+        ms = timed(step_device, args.steps)
+        _lib.set_timer(None)
+    launches = _lib.launch_count() - launches0
+    kern = timer.summary()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    ms_per_step = ms / args.steps
+    value = world * points_per_step * args.steps / (ms / 1e3)
+    e2e_value = world * points_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in h2d_keys)
+    d2h = out_host.numel() * out_host.element_size() + 4
+
+    # ---- roofline of the dominant kernel (largest share of the step among our launches) ----
+    peak, peak_src = measured_peak()
+    Nk = sum(h * w for h, w in levels)
+    L, P, M, Dh = len(levels), SCA_POINTS, HEADS, C // HEADS
+    ev = 2                                                           # bf16 value / grads
+    sca_fwd_bytes = (6 * Nk * C * ev + HW * M * L * P * 2 * 4 + HW * M * L * P * 4
+                     + 6 * HW * PILLAR * 2 * 4 + HW * 4 + HW * C * ev)
+    sca_bwd_bytes = (sca_fwd_bytes + 2 * 6 * Nk * C * 4 + HW * M * L * P * 2 * 4 + HW * M * L * P * 4)
+    tsa_s = 2 * 1 * TSA_POINTS
+    tsa_fwd_bytes = 2 * HW * C * ev + HW * M * tsa_s * 3 * 4 + 2 * HW * 2 * 4 + HW * C * ev
+    tsa_bwd_bytes = tsa_fwd_bytes + 2 * 2 * HW * C * 4 + HW * M * tsa_s * 3 * 4
+    algo = dict(sca_fwd=sca_fwd_bytes, sca_bwd=sca_bwd_bytes, tsa_fwd=tsa_fwd_bytes,
+                tsa_bwd=tsa_bwd_bytes)
+    kernels = {}
+    for name, st in kern.items():
+        row = dict(launches_per_step=st['launches'] / args.steps, mean_us=round(st['mean_us'], 2))
+        if name in algo:
+            row['algorithmic_bytes'] = algo[name]
+            row['achieved_gbs'] = round(algo[name] / st['mean_us'] / 1e3, 1)
+            row['frac_of_measured_peak'] = round(algo[name] / st['mean_us'] / 1e3 / peak, 4)
+        row['share_of_step'] = round(st['mean_us'] * st['launches'] / args.steps / (ms_per_step * 1e3), 4)
+        kernels[name] = row
+    dominant = max((k for k in kernels if k in algo), key=lambda k: kernels[k]['share_of_step'])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            traffic = json.load(f).get(dominant)
+    except Exception:
+        pass
+    roofline = dict(bound='hbm', kernel=dominant, achieved=kernels[dominant]['achieved_gbs'],
+                    peak=peak, peak_source=peak_src, unit='GB/s',
+                    frac=kernels[dominant]['frac_of_measured_peak'], traffic=traffic,
+                    algorithmic_bytes_per_launch=algo[dominant],
+                    mean_launch_us=kernels[dominant]['mean_us'])
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_reference_sample(steps=1, warmup=0)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {
+                'workload': f'BEVFormer-base encoder fwd+bwd, {bev_h}x{bev_w} BEV, 6 cams, 4 levels '
+                            f'(116x200..15x25), 8 points x 4 Z-anchors, {args.layers} layers, '
+                            'bs=1 frame per GPU, bf16 value / fp32 accumulation (BASELINE configs[1])',
+                'points_per_step': points_per_step, 'sca_points_per_layer': sca_points,
+                'tsa_points_per_layer': tsa_points, 'camera_query_pairs': pairs,
+                'parallelism': f'dp{world}' if world > 1 else 'single',
+                'l2': 'flushed every step (192 MiB write inside the timed region); the step\'s '
+                      'working set (> 1 GB of activations) also exceeds the 126 MB L2',
+                'weights': 'random-init (reference init + N(0,0.02) offset/weight Linears)',
+            },
+            'frames_per_s': world * args.steps / (ms / 1e3),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches,
+            'kernels': kernels,
+            'roofline': roofline,
+            'cpu_baseline': cpu_baseline,
+            'clocks': clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------- reference arm ------
+def run_reference_sample(steps, warmup):
+    """The reference's CPU path (oracle port) on a bounded sample of the workload: ONE of the
+    six encoder layers of the base configuration (200x200 BEV, 4 levels, 6 cameras, 8x4 points),
+    fp32, forward + backward, all host threads (BENCH_REF_BEV shrinks the BEV for quick checks)."""
+    from oracle.modules_oracle import OracleBEVFormerEncoder
+    import apollo_vision_net_b200.synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    bev = int(os.environ.get('BENCH_REF_BEV', '200'))
+    levels = syn.LEVELS_BASE
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    enc = OracleBEVFormerEncoder(num_layers=1, pc_range=syn.PC_RANGE, num_points_in_pillar=PILLAR,
+                                 embed_dims=C, feedforward_channels=FFN_DIM, num_levels=len(levels),
+                                 dropout=0.0)
+    randomize(enc, 0)
+    enc.train()
+    host = host_inputs(bev, bev, levels, seed=1, dtype=torch.float32, pin=False)
+    l2i, img_shape = syn.camera_rig(1.0, bs=1)
+    from oracle import geometry_oracle as G
+    r3 = G.reference_points_3d(bev, bev, 8.0, PILLAR, bs=1)
+    _, mask = G.point_sampling(r3, syn.PC_RANGE, l2i, img_shape[0], img_shape[1])
+    pairs = int(sum(len(x) for x in G.camera_hit_lists(mask)[0]))
+    max_len = G.camera_hit_lists(mask)[1]
+    # the reference computes 6 * max_len padded rows; the metric counts the real (cam, query) pairs
+    points = pairs * HEADS * len(levels) * SCA_POINTS + 2 * bev * bev * HEADS * TSA_POINTS
+
+    def step():
+        enc.zero_grad()
+        feat = host['feat'].clone().requires_grad_(True)
+        out = enc(host['bev_query'], feat, feat, bev_h=bev, bev_w=bev, bev_pos=host['bev_pos'],
+                  spatial_shapes=host['shapes'], level_start_index=host['starts'],
+                  prev_bev=host['prev_bev'], shift=host['shift'], lidar2img=l2i,
+                  img_h=img_shape[0], img_w=img_shape[1])
+        loss = (out * host['grad_w']).sum() * (1.0 / out.numel())
+        loss.backward()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    cpu = ''
+    try:
+        with open('/proc/cpuinfo') as f:
+            cpu = next(l.split(':', 1)[1].strip() for l in f if l.startswith('model name'))
+    except Exception:
+        pass
+    return dict(value=points * steps / dt, unit=UNIT, cores=torch.get_num_threads(), kind='port',
+                sample=f'1 of 6 encoder layers, {bev}x{bev} BEV, full 4-level '
+                       f'6-camera value maps, fp32 fwd+bwd, {steps} step(s), padded max_len={max_len}; '
+                       f'oracle port of the reference CPU branch (multi_scale_deformable_attn_pytorch)',
+                seconds_per_step=dt / steps, points_per_step=points, cpu_model=cpu)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    base = run_reference_sample(steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1),
+        'ms_per_step': base['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BEVFormer-base encoder fwd+bwd (BASELINE configs[1]) -- reference CPU '
+                               'path on a bounded sample: ' + base['sample']},
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--bev', type=int, default=200)
+    ap.add_argument('--layers', type=int, default=6)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        args.steps = min(args.steps, 3)
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()
