@@ -34,8 +34,8 @@ _SIGNATURES = {
     'bev_point_sampling': (_c_int, [_c_vp] * 3 + [_c_f, _c_f] + [_c_int] * 4 + [_c_vp] * 6),
     'sca_fwd': (_c_int, [_c_vp] * 10 + [_c_int] * 11 + [_c_vp]),
     'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 11 + [_c_vp]),
-    'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 8 + [_c_f, _c_int, _c_vp]),
-    'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 8 + [_c_f, _c_int, _c_vp]),
+    'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_vp]),
+    'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_vp]),
 }
 
 _lib = None

@@ -275,12 +275,12 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
             const float* logits, const float* ref, void* out, int bs, int Q, int Nk, int M, int Dh,
-            int L, int P, int Nq, float clamp, int value_dtype, void* stream) {
+            int L, int P, int Nq, int bev_w, float clamp, int value_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.out = out;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
-  f.clamp = clamp; f.value_dtype = value_dtype;
+  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype;
   if (int rc = validate_fused(f, false, false, "tsa_fwd")) return rc;
   if ((long long)bs * Nq == 0) return MSDA_OK;
   return launch_tsa_fwd(f, static_cast<cudaStream_t>(stream));
@@ -289,12 +289,12 @@ int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
             const float* logits, const float* ref, const void* g_out, float* g_value,
             float* g_offsets, float* g_logits, int bs, int Q, int Nk, int M, int Dh, int L, int P,
-            int Nq, float clamp, int value_dtype, void* stream) {
+            int Nq, int bev_w, float clamp, int value_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.g_out = g_out; f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
-  f.clamp = clamp; f.value_dtype = value_dtype;
+  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype;
   if (int rc = validate_fused(f, true, false, "tsa_bwd")) return rc;
   if ((long long)bs * Nq == 0) return MSDA_OK;
   return launch_tsa_bwd(f, static_cast<cudaStream_t>(stream));

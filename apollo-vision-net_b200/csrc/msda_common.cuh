@@ -39,6 +39,10 @@ template <> struct Vec16<float> {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
                       __float_as_uint(f[2]), __float_as_uint(f[3]));
   }
+  __device__ __forceinline__ static void unpack2(const uint4& u, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
+    f[1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
+  }
 };
 
 template <> struct Vec16<__nv_bfloat16> {
@@ -49,6 +53,13 @@ template <> struct Vec16<__nv_bfloat16> {
     f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
     f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+  // the two channels of a 32-bit word land in an aligned register pair, ready for FFMA2
+  __device__ __forceinline__ static void unpack2(const uint4& u, float2 (&f)[4]) {
+    f[0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    f[1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    f[2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+    f[3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
   }
   __device__ __forceinline__ static uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -70,6 +81,12 @@ template <> struct Vec16<__half> {
       f[2 * i] = p.x; f[2 * i + 1] = p.y;
     }
   }
+  __device__ __forceinline__ static void unpack2(const uint4& u, float2 (&f)[4]) {
+    f[0] = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    f[1] = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    f[2] = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
+    f[3] = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  }
   __device__ __forceinline__ static uint32_t pack2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -88,6 +105,27 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2: two IEEE fp32 operations per instruction,
+// each half rounded exactly like the scalar instruction).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // 128-bit read-only global load (value maps are re-read many times: keep them in L1/L2).
 __device__ __forceinline__ uint4 ldg128(const void* p) {
@@ -161,6 +199,45 @@ __device__ __forceinline__ Bilinear bilinear_setup(float loc_x, float loc_y, int
   b.vy0 = b.in_range && (b.y0 >= 0);
   b.vy1 = b.in_range && (b.y0 + 1 <= H - 1);
   return b;
+}
+
+// Bilinear corner set-up with CLAMPED (always loadable) corner offsets: a corner outside the map
+// or a sample outside the open interval keeps a valid address but gets weight zero and a cleared
+// `valid` bit, so the loads need no predicates and can be hoisted freely.
+struct Corners {
+  int o00, o01, o10, o11;      // element offsets from the level base
+  float w00, w01, w10, w11;    // bilinear weights (0 for invalid corners)
+  float lw, lh, hw, hh;
+  unsigned valid;              // bit0..3: corner 00, 01, 10, 11 contributes
+};
+
+__device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H, int W, int pix_stride) {
+  Corners c;
+  const float x = loc_x * (float)W - 0.5f;
+  const float y = loc_y * (float)H - 0.5f;
+  const bool in = (y > -1.0f) && (x > -1.0f) && (y < (float)H) && (x < (float)W);
+  const float xf = floorf(x), yf = floorf(y);
+  const int x0 = (int)xf, y0 = (int)yf;             // cvt saturates; NaN -> 0
+  c.lw = x - xf;
+  c.lh = y - yf;
+  c.hw = 1.f - c.lw;
+  c.hh = 1.f - c.lh;
+  const bool vx0 = in && x0 >= 0, vx1 = in && x0 + 1 <= W - 1;
+  const bool vy0 = in && y0 >= 0, vy1 = in && y0 + 1 <= H - 1;
+  const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+  const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+  const int ra = ya * W, rb = yb * W;
+  c.o00 = (ra + xa) * pix_stride;
+  c.o01 = (ra + xb) * pix_stride;
+  c.o10 = (rb + xa) * pix_stride;
+  c.o11 = (rb + xb) * pix_stride;
+  c.w00 = (vy0 && vx0) ? c.hh * c.hw : 0.f;
+  c.w01 = (vy0 && vx1) ? c.hh * c.lw : 0.f;
+  c.w10 = (vy1 && vx0) ? c.lh * c.hw : 0.f;
+  c.w11 = (vy1 && vx1) ? c.lh * c.lw : 0.f;
+  c.valid = (unsigned)(vy0 && vx0) | ((unsigned)(vy0 && vx1) << 1) | ((unsigned)(vy1 && vx0) << 2) |
+            ((unsigned)(vy1 && vx1) << 3);
+  return c;
 }
 
 }  // namespace msda

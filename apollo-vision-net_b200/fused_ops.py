@@ -87,7 +87,7 @@ class SpatialCrossAttnFunction(Function):
     @staticmethod
     @custom_fwd(cast_inputs=None)
     def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref_cam,
-                mask_u8, hit_bits, num_cam):
+                mask_u8, hit_bits, num_cam, bev_w=0):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref_cam=ref_cam,
                       mask=mask_u8, hit_bits=hit_bits)
         value = _check_value(value)
@@ -107,10 +107,11 @@ class SpatialCrossAttnFunction(Function):
         with torch.cuda.device(value.device):
             _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
-                slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, 0,
+                slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, int(bev_w or 0),
                 _DTYPE_CODE[value.dtype], _stream_ptr(value))
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits)
         ctx.num_cam = num_cam
+        ctx.bev_w = int(bev_w or 0)
         return slots
 
     @staticmethod
@@ -130,9 +131,9 @@ class SpatialCrossAttnFunction(Function):
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
-                bs, num_cam, Nk, M, Dh, L, P, D, HW, 0, _DTYPE_CODE[value.dtype],
+                bs, num_cam, Nk, M, Dh, L, P, D, HW, ctx.bev_w, _DTYPE_CODE[value.dtype],
                 _stream_ptr(value))
-        return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None)
+        return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None, None)
 
 
 class QueueDeformAttnFunction(Function):
@@ -144,7 +145,8 @@ class QueueDeformAttnFunction(Function):
 
     @staticmethod
     @custom_fwd(cast_inputs=None)
-    def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref, clamp):
+    def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref, clamp,
+                bev_w=0):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref=ref)
         value = _check_value(value)
         offsets = offsets.to(torch.float32).contiguous()
@@ -161,9 +163,10 @@ class QueueDeformAttnFunction(Function):
         with torch.cuda.device(value.device):
             _lib.call('tsa_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
-                clamp, _DTYPE_CODE[value.dtype], _stream_ptr(value))
+                int(bev_w or 0), clamp, _DTYPE_CODE[value.dtype], _stream_ptr(value))
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
         ctx.clamp = clamp
+        ctx.bev_w = int(bev_w or 0)
         return out
 
     @staticmethod
@@ -180,7 +183,7 @@ class QueueDeformAttnFunction(Function):
         with torch.cuda.device(value.device):
             _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
-                g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.clamp,
+                g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.bev_w, ctx.clamp,
                 _DTYPE_CODE[value.dtype], _stream_ptr(value))
         g_ref = None
         if ctx.needs_input_grad[5]:
@@ -188,4 +191,4 @@ class QueueDeformAttnFunction(Function):
             wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(torch.float32)      # (L, 2)
             g_ref = (g_off * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
             g_ref = g_ref.permute(0, 2, 1, 3, 4).reshape(bs * Q, Nq, L, 2)
-        return g_value.to(value.dtype), None, None, g_off, g_log, g_ref, None
+        return g_value.to(value.dtype), None, None, g_off, g_log, g_ref, None, None

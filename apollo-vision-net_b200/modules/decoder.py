@@ -63,7 +63,7 @@ class CustomMSDeformableAttention(DeformAttnBase):
             output = QueueDeformAttnFunction.apply(
                 value, spatial_shapes, level_start_index,
                 offsets.view(bs, num_query, M, 1, L, P, 2), logits.view(bs, num_query, M, 1, L * P),
-                reference_points, self.attn_logits_clamp)
+                reference_points, self.attn_logits_clamp, 0)
         elif reference_points.shape[-1] == 4:
             if self.attn_logits_clamp is not None:
                 c = float(self.attn_logits_clamp)

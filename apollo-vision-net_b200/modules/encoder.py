@@ -107,7 +107,7 @@ class BEVFormerLayer(BaseModule):
                     query, prev_bev, prev_bev, identity if self.pre_norm else None,
                     query_pos=bev_pos, key_pos=bev_pos, key_padding_mask=query_key_padding_mask,
                     reference_points=ref_2d, spatial_shapes=tsa_shapes[0],
-                    level_start_index=tsa_shapes[1], **kwargs)
+                    level_start_index=tsa_shapes[1], bev_h=bev_h, bev_w=bev_w, **kwargs)
                 attn_index += 1
                 identity = query
             elif op == 'norm':
@@ -119,7 +119,7 @@ class BEVFormerLayer(BaseModule):
                     key_pos=key_pos, reference_points=ref_3d,
                     reference_points_cam=reference_points_cam, mask=mask,
                     key_padding_mask=key_padding_mask, spatial_shapes=spatial_shapes,
-                    level_start_index=level_start_index, **kwargs)
+                    level_start_index=level_start_index, bev_h=bev_h, bev_w=bev_w, **kwargs)
                 attn_index += 1
                 identity = query
             elif op == 'ffn':

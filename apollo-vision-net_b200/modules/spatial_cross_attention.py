@@ -104,10 +104,18 @@ class SpatialCrossAttention(BaseModule):
     def init_weight(self):
         xavier_init(self.output_proj, distribution='uniform', bias=0.)
 
+    @staticmethod
+    def _grid_w(bev_h, bev_w, num_query):
+        """Width of the BEV grid when the caller says the queries are its row-major cells (lets
+        the kernel tile the work in 2-D patches); 0 when unknown."""
+        if bev_h and bev_w and int(bev_h) * int(bev_w) == num_query:
+            return int(bev_w)
+        return 0
+
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, reference_points_cam=None,
                 bev_mask=None, level_start_index=None, flag='encoder', bev_geometry=None,
-                **kwargs):
+                bev_h=None, bev_w=None, **kwargs):
         """query (bs, HW, C); key = value (num_cam, Nk, bs, C); reference_points_cam
         (num_cam, bs, HW, D, 2); bev_mask (num_cam, bs, HW, D) -> (bs, HW, C).
 
@@ -139,6 +147,6 @@ class SpatialCrossAttention(BaseModule):
         v = v.view(bs * self.num_cams, l, da.num_heads, -1)
         slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, off, logits,
                                                reference_points_cam, mask_u8, hit_bits,
-                                               self.num_cams)
+                                               self.num_cams, self._grid_w(bev_h, bev_w, num_query))
         slots = self.output_proj(slots.to(query.dtype))
         return self.dropout(slots) + inp_residual

@@ -32,7 +32,7 @@ class TemporalSelfAttention(DeformAttnBase):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, flag='decoder', **kwargs):
+                level_start_index=None, flag='decoder', bev_h=None, bev_w=None, **kwargs):
         """query (bs, HW, C) [batch_first]; value (bs*2, HW, C) = stack([prev_bev, bev], 1) or
         None (first frame); reference_points (bs*2, HW, L, 2) -> (bs, HW, C)."""
         if value is None:
@@ -59,12 +59,14 @@ class TemporalSelfAttention(DeformAttnBase):
         offsets = self.sampling_offsets(query).view(bs, num_query, M, Q, L, P, 2)
         logits = self.attention_weights(query).view(bs, num_query, M, Q, L * P)
 
+        grid_w = int(bev_w) if (bev_h and bev_w and int(bev_h) * int(bev_w) == num_query
+                                and num_value == num_query) else 0
         if reference_points.shape[-1] == 2:
             if reference_points.shape[2] != L:          # a single reference broadcast over levels
                 reference_points = reference_points.expand(-1, -1, L, -1)
             output = QueueDeformAttnFunction.apply(value, spatial_shapes, level_start_index,
                                                    offsets, logits, reference_points,
-                                                   self.attn_logits_clamp)
+                                                   self.attn_logits_clamp, grid_w)
         elif reference_points.shape[-1] == 4:
             # box-shaped references (:246-250): rare path, run on the op boundary
             if self.attn_logits_clamp is not None:

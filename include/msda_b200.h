@@ -142,7 +142,9 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
  *   value    (bs*num_cam, Nk, M, Dh)  value_dtype (output of value_proj)
  *   offsets  (bs, HW, M, L, P, 2)     fp32 raw output of sampling_offsets(query)
  *   logits   (bs, HW, M, L*P)         fp32 raw output of attention_weights(query)
- *   ref_cam, bev_mask, hit_bits       from bev_point_sampling
+ *   ref_cam, bev_mask, hit_bits       from bev_point_sampling (the kernels read the per-query
+ *                                      camera bit field; bev_mask is accepted for the contract)
+ *   bev_w    > 0: the HW queries are a row-major (HW / bev_w) x bev_w grid (2-D work tiles); 0: unknown
  *   slots    (bs, HW, M*Dh)           value_dtype out: sum over hit cameras / count
  *   attn_out (bs, HW, M, L*P)         fp32 out (softmax result, saved for backward) or NULL
  * ------------------------------------------------------------------------------- */
@@ -175,16 +177,18 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *   ref      (bs*Q, Nq, L, 2)         fp32 reference points
  *   out      (bs, Nq, M*Dh)           value_dtype: (1/Q) * sum_j MSDA_j
  *   clamp    < 0 : no clamp; otherwise logits are clamped to [-clamp, clamp]
+ *   bev_w    > 0 when the Nq queries are the cells of a (Nq / bev_w) x bev_w grid in row-major
+ *            order (TSA): work is tiled in 2-D patches of that grid; 0 otherwise (decoder)
  * ------------------------------------------------------------------------------- */
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const float* offsets, const float* logits, const float* ref, void* out,
-            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq,
+            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
             float clamp, int value_dtype, void* stream);
 
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const float* offsets, const float* logits, const float* ref, const void* g_out,
             float* g_value, float* g_offsets, float* g_logits,
-            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq,
+            int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
             float clamp, int value_dtype, void* stream);
 
 /* Number of kernel launches this library has enqueued since load (all entry points);

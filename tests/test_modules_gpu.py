@@ -268,14 +268,25 @@ def test_encoder_tiny_config1_vs_oracle():
     go = torch.randn(bs, H * W, C, generator=g)
     shift = torch.tensor([[0.01, -0.02]])
     shapes, starts = torch.tensor(shapes_l), torch.tensor(starts_l)
+    import copy
+    o64 = copy.deepcopy(o).double()
     for prev_in in (prev, None):
         o.zero_grad()
+        o64.zero_grad()
         enc.zero_grad()
         f1 = feat.clone().requires_grad_(True)
         ref = o(bevq, f1, f1, bev_h=H, bev_w=W, bev_pos=pos, spatial_shapes=shapes,
                 level_start_index=starts, prev_bev=prev_in, shift=shift, lidar2img=l2i,
                 img_h=img_shape[0], img_w=img_shape[1])
         ref.backward(go)
+        # float64 run of the oracle: the truth; the fp32 oracle's own error is the yardstick
+        # for a 3-layer-deep fp32 computation
+        f0 = feat.double().requires_grad_(True)
+        tru = o64(bevq.double(), f0, f0, bev_h=H, bev_w=W, bev_pos=pos.double(),
+                  spatial_shapes=shapes, level_start_index=starts,
+                  prev_bev=None if prev_in is None else prev_in.double(), shift=shift.double(),
+                  lidar2img=l2i, img_h=img_shape[0], img_w=img_shape[1])
+        tru.backward(go.double())
         f2 = feat.to(DEV).requires_grad_(True)
         metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6)
                  for b in range(bs)]
@@ -284,11 +295,15 @@ def test_encoder_tiny_config1_vs_oracle():
                   prev_bev=None if prev_in is None else prev_in.to(DEV), shift=shift.to(DEV),
                   img_metas=metas)
         out.backward(go.to(DEV))
-        assert rel_err(out, ref) <= 2e-5          # 3 layers deep
-        assert rel_err(f2.grad, f1.grad) <= 2e-4
-        og = dict(o.named_parameters())
+
+        def ok(mine, oracle32, truth, tol):
+            return rel_err(mine, truth) <= max(tol, 3.0 * rel_err(oracle32, truth))
+        assert ok(out, ref, tru, 1e-5)
+        assert ok(f2.grad, f1.grad, f0.grad, 1e-4)
+        og, tg = dict(o.named_parameters()), dict(o64.named_parameters())
         for n, p in enc.named_parameters():
-            assert rel_err(p.grad, og[n].grad) <= 5e-4, n
+            # parameter gradients are 2500-row reductions done by cuBLAS (GPU) vs MKL (oracle)
+            assert ok(p.grad, og[n].grad, tg[n].grad, 1e-3), n
 
 
 def test_fused_bf16_within_tolerance():
