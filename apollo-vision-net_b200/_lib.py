@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libmsda_b200.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
-SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu']
+SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'rowops.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -36,6 +36,10 @@ _SIGNATURES = {
     'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 11 + [_c_vp]),
     'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_vp]),
     'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_vp]),
+    'rowops_workspace_rows': (_c_int, []),
+    'ln_fwd': (_c_int, [_c_vp] * 6 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
+    'ln_bwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
+    'colsum': (_c_int, [_c_vp] * 3 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
 }
 
 _lib = None

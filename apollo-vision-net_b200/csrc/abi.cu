@@ -300,4 +300,31 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
   return launch_tsa_bwd(f, static_cast<cudaStream_t>(stream));
 }
 
+int rowops_workspace_rows(void) { return rowops_partial_rows(); }
+
+int ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+           int64_t rows, int C, float eps, int dtype, void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_fwd: invalid sizes");
+  if (rows == 0) return MSDA_OK;
+  if (!x || !gamma || !beta || !y || !mean || !rstd) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_fwd: NULL pointer");
+  return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
+                   dtype, static_cast<cudaStream_t>(stream));
+}
+
+int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
+           void* dx, void* dgamma_dbeta, float* partial, int64_t rows, int C, int dtype, void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd: invalid sizes");
+  if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma_dbeta || !partial)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd: NULL pointer");
+  return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
+                   dx, dgamma_dbeta, partial, rows, C, 0.f, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,
+           void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: invalid sizes");
+  if (!x || !out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: NULL pointer");
+  return launch_colsum(x, out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

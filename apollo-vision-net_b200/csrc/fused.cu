@@ -76,6 +76,7 @@ struct FusedArgs {
   int tiles_per_sample;
   long long num_tiles;         // bs * tiles_per_sample
   int vec_ok;                  // rows can be written with 16-byte stores
+  int debug;                   // MSDA_DEBUG experiment switches (0 in production)
 };
 
 // Sample `b` and query index of local slot `lq` in tile `t`; -1 when the slot is outside the grid.
@@ -413,7 +414,7 @@ fused_bwd_kernel(const FusedArgs a) {
         const uint4 u11 = ldg128(vb + c.o11);
         auto scatter = [&](int off, float cw) {
           const float aw = w * cw;
-          if (aw == 0.f) return;                         // invalid corner, or a zero contribution
+          if (aw == 0.f || (a.debug & 1)) return;        // invalid corner, or a zero contribution
           const float2 aw2 = splat2(aw);
           float* dst = gb + off;
 #pragma unroll
@@ -616,6 +617,8 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   if (e != cudaSuccess) return set_error(MSDA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   // MSDA_FUSED_WAVES=k > 0: persistent grid of k CTAs per SM striding over the tiles;
   // default: one tile per CTA (the hardware scheduler balances the uneven tiles).
+  static const int dbg = [] { const char* v = getenv("MSDA_DEBUG"); return v ? atoi(v) : 0; }();
+  a.debug = dbg;
   static const int waves = [] { const char* v = getenv("MSDA_FUSED_WAVES"); return v ? atoi(v) : 0; }();
   long long grid_ll = a.num_tiles;
   if (waves > 0 && grid_ll > (long long)sm_count() * waves) grid_ll = (long long)sm_count() * waves;

@@ -9,6 +9,7 @@ import torch.nn as nn
 from ..multi_scale_deformable_attn_function import (MultiScaleDeformableAttnFunction_fp16,
                                                     MultiScaleDeformableAttnFunction_fp32)
 from ..registry import BaseModule, constant_init, xavier_init
+from ..rowops import Linear
 
 
 def _is_power_of_2(n):
@@ -54,12 +55,12 @@ class DeformAttnBase(BaseModule):
         self.attn_logits_clamp = attn_logits_clamp
         self.debug_attn_nan = bool(debug_attn_nan)
         self._queue = queue
-        self.sampling_offsets = nn.Linear(embed_dims * queue,
+        self.sampling_offsets = Linear(embed_dims * queue,
                                           queue * num_heads * num_levels * num_points * 2)
-        self.attention_weights = nn.Linear(embed_dims * queue,
+        self.attention_weights = Linear(embed_dims * queue,
                                            queue * num_heads * num_levels * num_points)
-        self.value_proj = nn.Linear(embed_dims, embed_dims)
-        self.output_proj = nn.Linear(embed_dims, embed_dims) if with_output_proj else None
+        self.value_proj = Linear(embed_dims, embed_dims)
+        self.output_proj = Linear(embed_dims, embed_dims) if with_output_proj else None
 
     def init_weights(self):
         constant_init(self.sampling_offsets, 0.)

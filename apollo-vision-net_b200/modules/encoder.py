@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..fused_ops import BevGeometry, bev_point_sampling
+from ..rowops import LayerNorm, Linear
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
                         build_transformer_layer)
 
@@ -36,10 +37,10 @@ class FFN(BaseModule):
         layers = []
         in_channels = embed_dims
         for _ in range(num_fcs - 1):
-            layers.append(nn.Sequential(nn.Linear(in_channels, feedforward_channels),
+            layers.append(nn.Sequential(Linear(in_channels, feedforward_channels),
                                         nn.ReLU(inplace=True), nn.Dropout(ffn_drop)))
             in_channels = feedforward_channels
-        layers.append(nn.Linear(feedforward_channels, embed_dims))
+        layers.append(Linear(feedforward_channels, embed_dims))
         layers.append(nn.Dropout(ffn_drop))
         self.layers = nn.Sequential(*layers)
         self.add_identity = add_identity
@@ -87,7 +88,7 @@ class BEVFormerLayer(BaseModule):
         ffn_cfgs.setdefault('ffn_drop', ffn_dropout)
         self.ffns = nn.ModuleList([FFN(**copy.deepcopy(ffn_cfgs))
                                    for _ in range(self.operation_order.count('ffn'))])
-        self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims)
+        self.norms = nn.ModuleList([LayerNorm(self.embed_dims)
                                     for _ in range(self.operation_order.count('norm'))])
         self.fp16_enabled = False
 

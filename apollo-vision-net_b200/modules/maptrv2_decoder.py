@@ -15,6 +15,7 @@ import torch.nn as nn
 from ..registry import (ATTENTION, HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                         BaseModule, build_attention, build_transformer_layer)
 from .decoder import inverse_sigmoid
+from ..rowops import LayerNorm
 from .encoder import FFN
 
 if not HAVE_MMCV:
@@ -86,7 +87,7 @@ class MapTRv2DecoupledDetrTransformerDecoderLayer(BaseModule):
                                        feedforward_channels=feedforward_channels,
                                        num_fcs=ffn_num_fcs, ffn_drop=ffn_dropout)
                                    for _ in range(self.operation_order.count('ffn'))])
-        self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims)
+        self.norms = nn.ModuleList([LayerNorm(self.embed_dims)
                                     for _ in range(self.operation_order.count('norm'))])
         self.num_vec = num_vec
         self.num_pts_per_vec = num_pts_per_vec

@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from ..fused_ops import SpatialCrossAttnFunction, hit_bits_from_mask
 from ..registry import ATTENTION, BaseModule, build_attention, xavier_init
+from ..rowops import Linear
 from .deform_common import DeformAttnBase, msda_apply
 
 
@@ -97,7 +98,7 @@ class SpatialCrossAttention(BaseModule):
         self.deformable_attention = build_attention(deformable_attention)
         self.embed_dims = embed_dims
         self.num_cams = num_cams
-        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.output_proj = Linear(embed_dims, embed_dims)
         self.batch_first = batch_first
         self.init_weight()
 

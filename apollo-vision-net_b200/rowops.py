@@ -1,0 +1,150 @@
+"""Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section 8f
+rank 3): LayerNorm and Linear with sm_100a kernels for the pieces where the stock kernels were
+the largest non-attention items of the measured step (LayerNorm backward, bias-gradient column
+sums).  ``LayerNorm`` / ``Linear`` subclass the torch modules, so parameter names, initialisation
+and ``state_dict`` layout are unchanged (the reference builds them through mmcv's
+``build_norm_layer(dict(type='LN'))`` / ``nn.Linear``, custom_base_transformer_layer.py:142-161).
+
+The GEMMs themselves stay on cuBLAS (library GEMMs, tensor cores): only the reductions and the
+normalisation are ours.  CPU tensors and unsupported widths take the torch implementation --
+these are not hot-path operators.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd.function import Function, once_differentiable
+
+from . import _lib
+from .multi_scale_deformable_attn_function import _DTYPE_CODE, _stream_ptr, custom_bwd, custom_fwd
+
+_workspaces = {}
+
+
+def _workspace(device, floats):
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < floats:
+        ws = torch.empty(max(floats, 1 << 20), dtype=torch.float32, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ln_supported(x, weight, bias):
+    if not x.is_cuda or weight is None or bias is None or x.dtype not in _DTYPE_CODE:
+        return False
+    C = x.shape[-1]
+    vec = 4 if x.dtype == torch.float32 else 8
+    return C % (32 * vec) == 0 and C <= 1024 and weight.dtype == x.dtype and bias.dtype == x.dtype
+
+
+class LayerNormFunction(Function):
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        C = shape[-1]
+        x2 = x.reshape(-1, C).contiguous()
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        w, b = weight.contiguous(), bias.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.call('ln_fwd', x2.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                      mean.data_ptr(), rstd.data_ptr(), rows, C, float(eps), _DTYPE_CODE[x.dtype],
+                      _stream_ptr(x))
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        rows, C = x2.shape
+        dy2 = dy.reshape(rows, C).to(x2.dtype).contiguous()
+        dx = torch.empty_like(x2)
+        dgb = torch.empty((2, C), dtype=x2.dtype, device=x2.device)
+        nrows = _lib.lib().rowops_workspace_rows()
+        ws = _workspace(x2.device, nrows * 2 * C)
+        with torch.cuda.device(x2.device):
+            _lib.call('ln_bwd', x2.data_ptr(), dy2.data_ptr(), w.data_ptr(), mean.data_ptr(),
+                      rstd.data_ptr(), dx.data_ptr(), dgb.data_ptr(), ws.data_ptr(), rows, C,
+                      _DTYPE_CODE[x2.dtype], _stream_ptr(x2))
+        return dx.view(ctx.shape), dgb[0], dgb[1], None
+
+
+class LayerNorm(nn.LayerNorm):
+    """``torch.nn.LayerNorm`` over the last dimension with sm_100a forward / backward kernels."""
+
+    def forward(self, x):
+        if len(self.normalized_shape) == 1 and _ln_supported(x, self.weight, self.bias):
+            return LayerNormFunction.apply(x, self.weight, self.bias, self.eps)
+        return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+
+
+def column_sum(x2, out_dtype=None):
+    """Sum over the rows of a (rows, C) CUDA matrix (fp32 accumulation)."""
+    rows, C = x2.shape
+    out_dtype = out_dtype or x2.dtype
+    out = torch.empty(C, dtype=out_dtype, device=x2.device)
+    ws = _workspace(x2.device, _lib.lib().rowops_workspace_rows() * C)
+    with torch.cuda.device(x2.device):
+        _lib.call('colsum', x2.data_ptr(), out.data_ptr(), ws.data_ptr(), rows, C,
+                  _DTYPE_CODE[x2.dtype], _DTYPE_CODE[out_dtype], _stream_ptr(x2))
+    return out
+
+
+def _colsum_supported(g2):
+    if not g2.is_cuda or g2.dtype not in _DTYPE_CODE:
+        return False
+    vec = 4 if g2.dtype == torch.float32 else 8
+    C = g2.shape[1]
+    return C % vec == 0 and C // vec <= 256 and g2.shape[0] >= 1024
+
+
+class LinearFunction(Function):
+    """y = x W^T + b with cuBLAS GEMMs and our column-sum kernel for the bias gradient."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        # write into a freshly allocated tensor of the final shape: the result must not be a
+        # view (callers apply in-place activations to it, e.g. the FFN's ReLU(inplace=True))
+        out = torch.empty(x.shape[:-1] + (weight.shape[0],), dtype=x.dtype, device=x.device)
+        x2 = x.reshape(-1, x.shape[-1])
+        o2 = out.view(-1, weight.shape[0])
+        if bias is not None:
+            torch.addmm(bias, x2, weight.t(), out=o2)
+        else:
+            torch.mm(x2, weight.t(), out=o2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
+            db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)
+        return dx, dw, db
+
+
+class Linear(nn.Linear):
+    """``torch.nn.Linear`` whose backward computes the bias gradient with the column-sum kernel."""
+
+    def forward(self, x):
+        if x.is_cuda and torch.is_grad_enabled() and x.dtype == self.weight.dtype and x.dtype in _DTYPE_CODE:
+            return LinearFunction.apply(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)

@@ -191,6 +191,26 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
             float clamp, int value_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section
+ * 8f rank 3, "encoder remainder"; the reference builds them through mmcv bricks,
+ * custom_base_transformer_layer.py:142-161): LayerNorm forward / backward over (rows, C)
+ * activations, and the column sum that is the bias gradient of a Linear layer.
+ *
+ *   x, y, dy, dx  (rows, C) dtype;  gamma, beta (C,) dtype;  mean, rstd (rows,) fp32
+ *   dgamma_dbeta  (2, C) dtype out: row 0 = d gamma, row 1 = d beta
+ *   partial       fp32 scratch of rowops_workspace_rows() * 2 * C floats (ln_bwd) or
+ *                 rowops_workspace_rows() * C floats (colsum)
+ *   C must be 128, 256, 512 or 1024 for LayerNorm; a multiple of 16 bytes per row for colsum.
+ * ------------------------------------------------------------------------------- */
+int rowops_workspace_rows(void);
+int ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
+           int64_t rows, int C, float eps, int dtype, void* stream);
+int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
+           void* dx, void* dgamma_dbeta, float* partial, int64_t rows, int C, int dtype, void* stream);
+int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,
+           void* stream);
+
 /* Number of kernel launches this library has enqueued since load (all entry points);
  * bench.py reports the delta over its timed region as "gpu_launches". */
 int64_t msda_launch_count(void);
