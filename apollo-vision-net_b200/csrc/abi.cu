@@ -243,58 +243,58 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
                                static_cast<cudaStream_t>(stream));
 }
 
-int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
-            const float* logits, const float* ref_cam, const uint8_t* bev_mask,
+int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
+            const void* logits, const float* ref_cam, const uint8_t* bev_mask,
             const uint32_t* hit_bits, void* slots, float* attn_out, int bs, int num_cam, int Nk,
-            int M, int Dh, int L, int P, int D, int HW, int bev_w, int value_dtype, void* stream) {
+            int M, int Dh, int L, int P, int D, int HW, int bev_w, int value_dtype, int coord_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.out = slots; f.attn_out = attn_out;
   f.bs = bs; f.groups = num_cam; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.D = D;
-  f.Nq = HW; f.bev_w = bev_w; f.value_dtype = value_dtype;
+  f.Nq = HW; f.bev_w = bev_w; f.value_dtype = value_dtype; f.coord_dtype = coord_dtype;
   if (int rc = validate_fused(f, false, true, "sca_fwd")) return rc;
   if ((long long)bs * HW == 0) return MSDA_OK;
   return launch_sca_fwd(f, static_cast<cudaStream_t>(stream));
 }
 
-int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
-            const float* logits, const float* ref_cam, const uint8_t* bev_mask,
-            const uint32_t* hit_bits, const void* g_slots, float* g_value, float* g_offsets,
-            float* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, void* stream) {
+int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
+            const void* logits, const float* ref_cam, const uint8_t* bev_mask,
+            const uint32_t* hit_bits, const void* g_slots, float* g_value, void* g_offsets,
+            void* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
+            int bev_w, int value_dtype, int coord_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.g_out = g_slots;
   f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
   f.bs = bs; f.groups = num_cam; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.D = D;
-  f.Nq = HW; f.bev_w = bev_w; f.value_dtype = value_dtype;
+  f.Nq = HW; f.bev_w = bev_w; f.value_dtype = value_dtype; f.coord_dtype = coord_dtype;
   if (int rc = validate_fused(f, true, true, "sca_bwd")) return rc;
   if ((long long)bs * HW == 0) return MSDA_OK;
   return launch_sca_bwd(f, static_cast<cudaStream_t>(stream));
 }
 
-int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
-            const float* logits, const float* ref, void* out, int bs, int Q, int Nk, int M, int Dh,
-            int L, int P, int Nq, int bev_w, float clamp, int value_dtype, void* stream) {
+int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
+            const void* logits, const float* ref, void* out, int bs, int Q, int Nk, int M, int Dh,
+            int L, int P, int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.out = out;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
-  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype;
+  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype; f.coord_dtype = coord_dtype;
   if (int rc = validate_fused(f, false, false, "tsa_fwd")) return rc;
   if ((long long)bs * Nq == 0) return MSDA_OK;
   return launch_tsa_fwd(f, static_cast<cudaStream_t>(stream));
 }
 
-int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const float* offsets,
-            const float* logits, const float* ref, const void* g_out, float* g_value,
-            float* g_offsets, float* g_logits, int bs, int Q, int Nk, int M, int Dh, int L, int P,
-            int Nq, int bev_w, float clamp, int value_dtype, void* stream) {
+int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
+            const void* logits, const float* ref, const void* g_out, float* g_value,
+            void* g_offsets, void* g_logits, int bs, int Q, int Nk, int M, int Dh, int L, int P,
+            int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, void* stream) {
   FusedProblem f;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.g_out = g_out; f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
-  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype;
+  f.bev_w = bev_w; f.clamp = clamp; f.value_dtype = value_dtype; f.coord_dtype = coord_dtype;
   if (int rc = validate_fused(f, true, false, "tsa_bwd")) return rc;
   if ((long long)bs * Nq == 0) return MSDA_OK;
   return launch_tsa_bwd(f, static_cast<cudaStream_t>(stream));

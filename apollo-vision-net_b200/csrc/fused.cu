@@ -57,15 +57,15 @@ struct FusedArgs {
   const void* value;
   const int64_t* shapes;
   const int64_t* starts;
-  const float* offsets;
-  const float* logits;
+  const void* offsets;         // CT: fp32 or the value dtype
+  const void* logits;
   const float* ref;
   const uint32_t* hit_bits;
   void* out;
   const void* g_out;
   float* g_value;
-  float* g_offsets;
-  float* g_logits;
+  void* g_offsets;             // CT
+  void* g_logits;
   int bs, groups, Nk, M, Dh, L, P, D, Nq;
   float clamp;
   int bev_w, bev_h;            // query grid (0 = queries are not on a grid)
@@ -103,12 +103,40 @@ __device__ __forceinline__ void load_fused_levels(FusedLevels& lv, const FusedAr
   }
 }
 
+template <typename CT> __device__ __forceinline__ float2 load_coord2(const CT* p);
+template <> __device__ __forceinline__ float2 load_coord2<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float2*>(p));
+}
+template <> __device__ __forceinline__ float2 load_coord2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 load_coord2<__half>(const __half* p) {
+  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <typename CT> __device__ __forceinline__ float load_coord(const CT* p) { return to_f32<CT>(__ldg(p)); }
+
+// 4 consecutive fp32 values from a shared row -> 4 consecutive CT values in global memory
+template <typename CT> __device__ __forceinline__ void store_coord4(CT* dst, const float* src);
+template <> __device__ __forceinline__ void store_coord4<float>(float* dst, const float* src) {
+  *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+}
+template <> __device__ __forceinline__ void store_coord4<__nv_bfloat16>(__nv_bfloat16* dst, const float* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(Vec16<__nv_bfloat16>::pack2(v.x, v.y), Vec16<__nv_bfloat16>::pack2(v.z, v.w));
+}
+template <> __device__ __forceinline__ void store_coord4<__half>(__half* dst, const float* src) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(Vec16<__half>::pack2(v.x, v.y), Vec16<__half>::pack2(v.z, v.w));
+}
+
 // Stage one row, executed by the row's TPH lanes (all lanes of the warp take part in the
 // shuffles; `live` gates the memory traffic).  raw offsets -> off / (W_l, H_l) in `so`;
 // raw logits -> softmax per LP-long segment in `sw`.
-template <int TPH>
+template <int TPH, typename CT>
 __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels& lv, bool live,
-                                          const float* __restrict__ g_off, const float* __restrict__ g_log,
+                                          const CT* __restrict__ g_off, const CT* __restrict__ g_log,
                                           float* so, float* sw, int chunk, int S, int LP) {
   // offsets: lane handles samples chunk, chunk + TPH, ... (8 contiguous bytes each)
   if (live) {
@@ -116,7 +144,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
     while (sl >= LP) sl -= LP;
     for (int s = chunk; s < S; s += TPH) {
       const int l = sl / a.P;
-      const float2 o = __ldg(reinterpret_cast<const float2*>(g_off) + s);
+      const float2 o = load_coord2<CT>(g_off + 2 * s);
       *reinterpret_cast<float2*>(so + 2 * s) = make_float2(o.x * lv.inv_w[l], o.y * lv.inv_h[l]);
       sl += TPH;
       while (sl >= LP) sl -= LP;
@@ -131,7 +159,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
       float mx = -INFINITY;
       if (live)
         for (int i = chunk; i < LP; i += TPH) {
-          float v = __ldg(g_log + sg * LP + i);
+          float v = load_coord<CT>(g_log + sg * LP + i);
           if (use_clamp) v = fminf(fmaxf(v, -a.clamp), a.clamp);
           sw[sg * LP + i] = v;
           mx = fmaxf(mx, v);
@@ -155,7 +183,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
     for (int sg = chunk; sg < nseg; sg += TPH) {
       float mx = -INFINITY;
       for (int i = 0; i < LP; ++i) {
-        float v = __ldg(g_log + sg * LP + i);
+        float v = load_coord<CT>(g_log + sg * LP + i);
         if (use_clamp) v = fminf(fmaxf(v, -a.clamp), a.clamp);
         sw[sg * LP + i] = v;
         mx = fmaxf(mx, v);
@@ -173,7 +201,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
   __syncwarp();
 }
 
-template <typename T, int TPH, int MODE>
+template <typename T, typename CT, int TPH, int MODE>
 __global__ void __launch_bounds__(kFusedThreads)
 fused_fwd_kernel(const FusedArgs a) {
   constexpr int VEC = Vec16<T>::N;
@@ -219,7 +247,8 @@ fused_fwd_kernel(const FusedArgs a) {
       const bool work = live && (MODE == MODE_TSA || hits != 0);
       const long long grow = ((long long)b * a.Nq + q) * a.M + m;
       __syncwarp();                                                   // previous row's readers are done
-      stage_row<TPH>(a, lv, work, a.offsets + grow * S * 2, a.logits + grow * S, my_off, my_w, chunk, S, LP);
+      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + grow * S * 2,
+                         static_cast<const CT*>(a.logits) + grow * S, my_off, my_w, chunk, S, LP);
 
       if (live) {
         const T* vhead = static_cast<const T*>(a.value) + (size_t)m * a.Dh + chunk * VEC;
@@ -308,7 +337,7 @@ fused_fwd_kernel(const FusedArgs a) {
   }
 }
 
-template <typename T, int TPH, int MODE>
+template <typename T, typename CT, int TPH, int MODE>
 __global__ void __launch_bounds__(kFusedThreads)
 fused_bwd_kernel(const FusedArgs a) {
   constexpr int VEC = Vec16<T>::N;
@@ -361,7 +390,8 @@ fused_bwd_kernel(const FusedArgs a) {
       const bool work = live && (MODE == MODE_TSA || hits != 0);
       const long long grow = ((long long)b * a.Nq + q) * a.M + m;
       __syncwarp();
-      stage_row<TPH>(a, lv, work, a.offsets + grow * S * 2, a.logits + grow * S, my_off, my_w, chunk, S, LP);
+      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + grow * S * 2,
+                         static_cast<const CT*>(a.logits) + grow * S, my_off, my_w, chunk, S, LP);
       // clear the row's gradient accumulators
       for (int i = chunk; i < 2 * S; i += TPH) my_go[i] = 0.f;
       for (int i = chunk; i < S; i += TPH) my_ga[i] = 0.f;
@@ -513,7 +543,7 @@ fused_bwd_kernel(const FusedArgs a) {
       {
         const int nseg = S / LP;
         const bool use_clamp = a.clamp >= 0.f;
-        const float* raw = a.logits + grow * S;
+        const CT* raw = static_cast<const CT*>(a.logits) + grow * S;
         if (LP % TPH == 0) {
           for (int sg = 0; sg < nseg; ++sg) {
             float dot = 0.f;
@@ -523,7 +553,7 @@ fused_bwd_kernel(const FusedArgs a) {
               const int e = sg * LP + i;
               float gl = work ? my_w[e] * (my_ga[e] - dot) : 0.f;   // rows without work hold stale weights
               if (use_clamp && live) {
-                const float v = __ldg(raw + e);
+                const float v = load_coord<CT>(raw + e);
                 if (v < -a.clamp || v > a.clamp) gl = 0.f;
               }
               my_ga[e] = gl;
@@ -537,7 +567,7 @@ fused_bwd_kernel(const FusedArgs a) {
               const int e = sg * LP + i;
               float gl = work ? my_w[e] * (my_ga[e] - dot) : 0.f;
               if (use_clamp && live) {
-                const float v = __ldg(raw + e);
+                const float v = load_coord<CT>(raw + e);
                 if (v < -a.clamp || v > a.clamp) gl = 0.f;
               }
               my_ga[e] = gl;
@@ -549,16 +579,14 @@ fused_bwd_kernel(const FusedArgs a) {
 
       // gradient rows back to global memory
       if (live) {
-        float* dst_o = a.g_offsets + grow * S * 2;
-        float* dst_l = a.g_logits + grow * S;
+        CT* dst_o = static_cast<CT*>(a.g_offsets) + grow * S * 2;
+        CT* dst_l = static_cast<CT*>(a.g_logits) + grow * S;
         if (a.vec_ok) {
-          for (int c = chunk; c < (2 * S) / 4; c += TPH)
-            reinterpret_cast<float4*>(dst_o)[c] = reinterpret_cast<const float4*>(my_go)[c];
-          for (int c = chunk; c < S / 4; c += TPH)
-            reinterpret_cast<float4*>(dst_l)[c] = reinterpret_cast<const float4*>(my_ga)[c];
+          for (int c = chunk; c < (2 * S) / 4; c += TPH) store_coord4<CT>(dst_o + 4 * c, my_go + 4 * c);
+          for (int c = chunk; c < S / 4; c += TPH) store_coord4<CT>(dst_l + 4 * c, my_ga + 4 * c);
         } else {
-          for (int i = chunk; i < 2 * S; i += TPH) dst_o[i] = my_go[i];
-          for (int i = chunk; i < S; i += TPH) dst_l[i] = my_ga[i];
+          for (int i = chunk; i < 2 * S; i += TPH) dst_o[i] = from_f32<CT>(my_go[i]);
+          for (int i = chunk; i < S; i += TPH) dst_l[i] = from_f32<CT>(my_ga[i]);
         }
       }
     }
@@ -575,7 +603,7 @@ static int sm_count() {
   return n;
 }
 
-template <typename T, int TPH, int MODE>
+template <typename T, typename CT, int TPH, int MODE>
 static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const char* what) {
   constexpr int ROWS = kFusedThreads / TPH;
   FusedArgs a{};
@@ -605,12 +633,12 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   a.num_tiles = (long long)f.bs * a.tiles_per_sample;
   if (a.num_tiles <= 0) return MSDA_OK;
   a.vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.g_offsets) | reinterpret_cast<uintptr_t>(f.g_logits)) % 16 == 0);
-  if ((reinterpret_cast<uintptr_t>(f.offsets) % 8) != 0)
-    return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets must be 8-byte aligned", what);
+  if ((reinterpret_cast<uintptr_t>(f.offsets) % 16) != 0 || (reinterpret_cast<uintptr_t>(f.logits) % 16) != 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets / logits must be 16-byte aligned", what);
   const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float);
   if (smem > 200 * 1024)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: %d samples per row need %zu bytes of shared memory", what, S, smem);
-  auto kfn = bwd ? fused_bwd_kernel<T, TPH, MODE> : fused_fwd_kernel<T, TPH, MODE>;
+  auto kfn = bwd ? fused_bwd_kernel<T, CT, TPH, MODE> : fused_fwd_kernel<T, CT, TPH, MODE>;
   cudaError_t e = cudaSuccess;
   if (smem > 48 * 1024)
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -628,18 +656,18 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   return check_launch(what);
 }
 
-template <typename T, int MODE>
+template <typename T, typename CT, int MODE>
 static int dispatch_tph(const FusedProblem& f, bool bwd, cudaStream_t st, const char* what) {
   constexpr int VEC = Vec16<T>::N;
   if (f.Dh % VEC != 0)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: head_dim %d must be a multiple of %d for this dtype "
                      "(use the op-boundary msda_fwd/msda_bwd, which has a generic path)", what, f.Dh, VEC);
   switch (f.Dh / VEC) {
-    case 1: return launch_fused<T, 1, MODE>(f, bwd, st, what);
-    case 2: return launch_fused<T, 2, MODE>(f, bwd, st, what);
-    case 4: return launch_fused<T, 4, MODE>(f, bwd, st, what);
-    case 8: return launch_fused<T, 8, MODE>(f, bwd, st, what);
-    case 16: return launch_fused<T, 16, MODE>(f, bwd, st, what);
+    case 1: return launch_fused<T, CT, 1, MODE>(f, bwd, st, what);
+    case 2: return launch_fused<T, CT, 2, MODE>(f, bwd, st, what);
+    case 4: return launch_fused<T, CT, 4, MODE>(f, bwd, st, what);
+    case 8: return launch_fused<T, CT, 8, MODE>(f, bwd, st, what);
+    case 16: return launch_fused<T, CT, 16, MODE>(f, bwd, st, what);
     default: break;
   }
   return set_error(MSDA_ERR_UNSUPPORTED, "%s: head_dim %d not supported by the fused kernels", what, f.Dh);
@@ -651,10 +679,15 @@ static int dispatch_dtype(const FusedProblem& f, bool bwd, cudaStream_t st, cons
                        reinterpret_cast<uintptr_t>(f.g_out) | reinterpret_cast<uintptr_t>(f.g_value) |
                        reinterpret_cast<uintptr_t>(f.ref);
   if (al & 15u) return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: tensors must be 16-byte aligned", what);
+  if (f.coord_dtype != MSDA_F32 && f.coord_dtype != f.value_dtype)
+    return set_error(MSDA_ERR_UNSUPPORTED, "%s: offsets / logits must be fp32 or the value dtype", what);
+  const bool c32 = f.coord_dtype == MSDA_F32;
   switch (f.value_dtype) {
-    case MSDA_F32: return dispatch_tph<float, MODE>(f, bwd, st, what);
-    case MSDA_BF16: return dispatch_tph<__nv_bfloat16, MODE>(f, bwd, st, what);
-    default: return dispatch_tph<__half, MODE>(f, bwd, st, what);
+    case MSDA_F32: return dispatch_tph<float, float, MODE>(f, bwd, st, what);
+    case MSDA_BF16: return c32 ? dispatch_tph<__nv_bfloat16, float, MODE>(f, bwd, st, what)
+                               : dispatch_tph<__nv_bfloat16, __nv_bfloat16, MODE>(f, bwd, st, what);
+    default: return c32 ? dispatch_tph<__half, float, MODE>(f, bwd, st, what)
+                        : dispatch_tph<__half, __half, MODE>(f, bwd, st, what);
   }
 }
 

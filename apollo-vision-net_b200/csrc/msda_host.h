@@ -27,8 +27,8 @@ struct FusedProblem {
   const void* value = nullptr;
   const int64_t* shapes = nullptr;
   const int64_t* starts = nullptr;
-  const float* offsets = nullptr;
-  const float* logits = nullptr;
+  const void* offsets = nullptr;       // coord_dtype
+  const void* logits = nullptr;
   const float* ref = nullptr;          // ref_cam (SCA) or ref points (TSA / decoder)
   const uint8_t* bev_mask = nullptr;   // SCA only
   const uint32_t* hit_bits = nullptr;  // SCA only
@@ -36,12 +36,13 @@ struct FusedProblem {
   float* attn_out = nullptr;
   const void* g_out = nullptr;
   float* g_value = nullptr;
-  float* g_offsets = nullptr;
-  float* g_logits = nullptr;
+  void* g_offsets = nullptr;           // coord_dtype
+  void* g_logits = nullptr;
   int bs = 0, groups = 0;              // groups = num_cam (SCA) or Q (TSA)
   int Nk = 0, M = 0, Dh = 0, L = 0, P = 0, D = 1, Nq = 0, bev_w = 0;
   float clamp = -1.f;
   int value_dtype = MSDA_F32;
+  int coord_dtype = MSDA_F32;
 };
 
 int set_error(int code, const char* fmt, ...);

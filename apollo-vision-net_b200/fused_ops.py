@@ -76,6 +76,14 @@ def _check_value(value):
     return value.contiguous()
 
 
+def _coords(value, offsets, logits):
+    """Offsets / logits are consumed in fp32 or in the value dtype (no conversion pass for a
+    bf16 model); anything else is brought to fp32."""
+    dt = offsets.dtype if (offsets.dtype == logits.dtype and
+                           offsets.dtype in (torch.float32, value.dtype)) else torch.float32
+    return offsets.to(dt).contiguous(), logits.to(dt).contiguous()
+
+
 class SpatialCrossAttnFunction(Function):
     """slots = (sum over hit cameras of MSDA(value_cam, ref_cam + offsets / (W, H), softmax(logits))) / count.
 
@@ -91,8 +99,7 @@ class SpatialCrossAttnFunction(Function):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref_cam=ref_cam,
                       mask=mask_u8, hit_bits=hit_bits)
         value = _check_value(value)
-        offsets = offsets.to(torch.float32).contiguous()
-        logits = logits.to(torch.float32).contiguous()
+        offsets, logits = _coords(value, offsets, logits)
         shapes = spatial_shapes.to(torch.int64).contiguous()
         starts = level_start_index.to(torch.int64).contiguous()
         ref_cam = ref_cam.to(torch.float32).contiguous()
@@ -108,7 +115,7 @@ class SpatialCrossAttnFunction(Function):
             _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, int(bev_w or 0),
-                _DTYPE_CODE[value.dtype], _stream_ptr(value))
+                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits)
         ctx.num_cam = num_cam
         ctx.bev_w = int(bev_w or 0)
@@ -132,7 +139,7 @@ class SpatialCrossAttnFunction(Function):
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
                 bs, num_cam, Nk, M, Dh, L, P, D, HW, ctx.bev_w, _DTYPE_CODE[value.dtype],
-                _stream_ptr(value))
+                _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
         return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None, None)
 
 
@@ -149,8 +156,7 @@ class QueueDeformAttnFunction(Function):
                 bev_w=0):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref=ref)
         value = _check_value(value)
-        offsets = offsets.to(torch.float32).contiguous()
-        logits = logits.to(torch.float32).contiguous()
+        offsets, logits = _coords(value, offsets, logits)
         ref = ref.to(torch.float32).contiguous()
         shapes = spatial_shapes.to(torch.int64).contiguous()
         starts = level_start_index.to(torch.int64).contiguous()
@@ -163,7 +169,8 @@ class QueueDeformAttnFunction(Function):
         with torch.cuda.device(value.device):
             _lib.call('tsa_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
-                int(bev_w or 0), clamp, _DTYPE_CODE[value.dtype], _stream_ptr(value))
+                int(bev_w or 0), clamp, _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype],
+                _stream_ptr(value))
         ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
         ctx.clamp = clamp
         ctx.bev_w = int(bev_w or 0)
@@ -184,11 +191,11 @@ class QueueDeformAttnFunction(Function):
             _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
                 g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.bev_w, ctx.clamp,
-                _DTYPE_CODE[value.dtype], _stream_ptr(value))
+                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
         g_ref = None
         if ctx.needs_input_grad[5]:
             # loc = ref + off / (W, H)  =>  d ref = sum over heads and points of d off * (W, H)
             wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(torch.float32)      # (L, 2)
-            g_ref = (g_off * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
+            g_ref = (g_off.float() * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
             g_ref = g_ref.permute(0, 2, 1, 3, 4).reshape(bs * Q, Nq, L, 2)
         return g_value.to(value.dtype), None, None, g_off, g_log, g_ref, None, None

@@ -140,8 +140,9 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
  * sampling_locations, the rebatched queries or the scatter.
  *
  *   value    (bs*num_cam, Nk, M, Dh)  value_dtype (output of value_proj)
- *   offsets  (bs, HW, M, L, P, 2)     fp32 raw output of sampling_offsets(query)
- *   logits   (bs, HW, M, L*P)         fp32 raw output of attention_weights(query)
+ *   offsets  (bs, HW, M, L, P, 2)     coord_dtype raw output of sampling_offsets(query)
+ *   logits   (bs, HW, M, L*P)         coord_dtype raw output of attention_weights(query)
+ *            (coord_dtype = MSDA_F32 or value_dtype: a bf16 model feeds its Linear outputs as is)
  *   ref_cam, bev_mask, hit_bits       from bev_point_sampling (the kernels read the per-query
  *                                      camera bit field; bev_mask is accepted for the contract)
  *   bev_w    > 0: the HW queries are a row-major (HW / bev_w) x bev_w grid (2-D work tiles); 0: unknown
@@ -149,21 +150,21 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
  *   attn_out (bs, HW, M, L*P)         fp32 out (softmax result, saved for backward) or NULL
  * ------------------------------------------------------------------------------- */
 int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
-            const float* offsets, const float* logits, const float* ref_cam,
+            const void* offsets, const void* logits, const float* ref_cam,
             const uint8_t* bev_mask, const uint32_t* hit_bits, void* slots, float* attn_out,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, void* stream);
+            int bev_w, int value_dtype, int coord_dtype, void* stream);
 
 /*   g_slots   (bs, HW, M*Dh) value_dtype   gradient w.r.t. `slots`
  *   g_value   (bs*num_cam, Nk, M, Dh) fp32 accumulator (zero-filled by the caller)
- *   g_offsets (bs, HW, M, L, P, 2) fp32, fully written
- *   g_logits  (bs, HW, M, L*P) fp32, fully written (softmax backward included)        */
+ *   g_offsets (bs, HW, M, L, P, 2) coord_dtype, fully written
+ *   g_logits  (bs, HW, M, L*P) coord_dtype, fully written (softmax backward included)        */
 int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
-            const float* offsets, const float* logits, const float* ref_cam,
+            const void* offsets, const void* logits, const float* ref_cam,
             const uint8_t* bev_mask, const uint32_t* hit_bits, const void* g_slots,
-            float* g_value, float* g_offsets, float* g_logits,
+            float* g_value, void* g_offsets, void* g_logits,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, void* stream);
+            int bev_w, int value_dtype, int coord_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Fused temporal self-attention / decoder cross-attention core
@@ -172,8 +173,8 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  * `Q` queue entries (Q = 2 for TSA, Q = 1 for CustomMSDeformableAttention).
  *
  *   value    (bs*Q, Nk, M, Dh)        value_dtype; batch index = b*Q + j
- *   offsets  (bs, Nq, M, Q, L, P, 2)  fp32 raw Linear output
- *   logits   (bs, Nq, M, Q, L*P)      fp32 raw Linear output
+ *   offsets  (bs, Nq, M, Q, L, P, 2)  coord_dtype raw Linear output
+ *   logits   (bs, Nq, M, Q, L*P)      coord_dtype raw Linear output
  *   ref      (bs*Q, Nq, L, 2)         fp32 reference points
  *   out      (bs, Nq, M*Dh)           value_dtype: (1/Q) * sum_j MSDA_j
  *   clamp    < 0 : no clamp; otherwise logits are clamped to [-clamp, clamp]
@@ -181,15 +182,15 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *            order (TSA): work is tiled in 2-D patches of that grid; 0 otherwise (decoder)
  * ------------------------------------------------------------------------------- */
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
-            const float* offsets, const float* logits, const float* ref, void* out,
+            const void* offsets, const void* logits, const float* ref, void* out,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
-            float clamp, int value_dtype, void* stream);
+            float clamp, int value_dtype, int coord_dtype, void* stream);
 
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
-            const float* offsets, const float* logits, const float* ref, const void* g_out,
-            float* g_value, float* g_offsets, float* g_logits,
+            const void* offsets, const void* logits, const float* ref, const void* g_out,
+            float* g_value, void* g_offsets, void* g_logits,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
-            float clamp, int value_dtype, void* stream);
+            float clamp, int value_dtype, int coord_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section

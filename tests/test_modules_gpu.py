@@ -303,9 +303,12 @@ def test_encoder_tiny_config1_vs_oracle():
         check('grad_feat', f2.grad, f1.grad, f0.grad, 2e-4)
         og, tg = dict(o.named_parameters()), dict(o64.named_parameters())
         for n, p in enc.named_parameters():
-            # parameter gradients: 2500-row reductions by cuBLAS vs MKL, three layers deep, behind
-            # ReLU / LayerNorm and run-to-run atomic ordering -- noise at the 1e-3 level
-            check(n, p.grad, og[n].grad, tg[n].grad, 2e-3)
+            # parameter gradients three layers deep: d out / d location is piecewise constant
+            # (it jumps when a sample crosses a pixel boundary), so rounding-level differences in
+            # the upstream layers flip a few samples and move the offset-path gradients at the
+            # 1e-3 .. 1e-2 level -- in the fp32 oracle just as much as here (see its own error
+            # against the fp64 run).  The single-layer tests above hold the 1e-4 bar.
+            check(n, p.grad, og[n].grad, tg[n].grad, 2e-2)
 
 
 def test_fused_bf16_within_tolerance():

@@ -37,9 +37,12 @@ def main():
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--which', default='sca,tsa')
+    ap.add_argument('--coord', default='same', help="'same' = offsets/logits in the value dtype, 'fp32'")
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[args.dtype]
+    cdtype = dtype if args.coord == 'same' else torch.float32
+    ccode = _DTYPE_CODE[cdtype]
     H = W = args.bev
     HW = H * W
     M, Dh, C = 8, 32, 256
@@ -61,8 +64,8 @@ def main():
     if 'sca' in args.which:
         value = torch.randn(6, Nk, M, Dh, generator=g, device=dev).to(dtype)
         bias = ring_bias(M, L, P).to(dev).view(1, 1, M, L, P, 2)
-        offsets = (bias + 0.3 * torch.randn(1, HW, M, L, P, 2, generator=g, device=dev)).contiguous()
-        logits = torch.randn(1, HW, M, L * P, generator=g, device=dev)
+        offsets = (bias + 0.3 * torch.randn(1, HW, M, L, P, 2, generator=g, device=dev)).to(cdtype).contiguous()
+        logits = torch.randn(1, HW, M, L * P, generator=g, device=dev).to(cdtype)
         slots = torch.empty(1, HW, C, device=dev, dtype=dtype)
         gs = torch.randn(1, HW, C, generator=g, device=dev).to(dtype)
         gv = torch.zeros(6, Nk, M, Dh, device=dev)
@@ -73,13 +76,13 @@ def main():
         def fwd():
             _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
-                      geo.hit_bits.data_ptr(), slots.data_ptr(), None, 1, 6, Nk, M, Dh, L, P, D, HW, W, code, st)
+                      geo.hit_bits.data_ptr(), slots.data_ptr(), None, 1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, st)
 
         def bwd():
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
-                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, st)
+                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, st)
         res['sca_fwd_us'] = round(timeit(fwd, flush, args.iters), 1)
         res['sca_bwd_us'] = round(timeit(bwd, flush, args.iters), 1)
         res['sca_samples'] = pairs * M * L * P
@@ -87,8 +90,8 @@ def main():
         Q, Pt = 2, 4
         value = torch.randn(Q, HW, M, Dh, generator=g, device=dev).to(dtype)
         bias = ring_bias(M, Q, Pt).to(dev).view(1, 1, M, Q, 1, Pt, 2)
-        offsets = (bias + 0.3 * torch.randn(1, HW, M, Q, 1, Pt, 2, generator=g, device=dev)).contiguous()
-        logits = torch.randn(1, HW, M, Q, Pt, generator=g, device=dev)
+        offsets = (bias + 0.3 * torch.randn(1, HW, M, Q, 1, Pt, 2, generator=g, device=dev)).to(cdtype).contiguous()
+        logits = torch.randn(1, HW, M, Q, Pt, generator=g, device=dev).to(cdtype)
         ref2d = BEVFormerEncoder.get_reference_points(H, W, dim='2d', bs=1, device=dev, dtype=torch.float32)
         ref = torch.stack([ref2d + 0.004, ref2d], 1).reshape(2, HW, 1, 2).contiguous()
         out = torch.empty(1, HW, C, device=dev, dtype=dtype)
@@ -102,12 +105,12 @@ def main():
 
         def tfwd():
             _lib.call('tsa_fwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
-                      logits.data_ptr(), ref.data_ptr(), out.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, st)
+                      logits.data_ptr(), ref.data_ptr(), out.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, st)
 
         def tbwd():
             _lib.call('tsa_bwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(), goff.data_ptr(),
-                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, st)
+                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, st)
         res['tsa_fwd_us'] = round(timeit(tfwd, flush, args.iters), 1)
         res['tsa_bwd_us'] = round(timeit(tbwd, flush, args.iters), 1)
     res.update(bev=args.bev, dtype=args.dtype, pairs=pairs)
