@@ -36,6 +36,15 @@ class BevGeometry:
         """(num_cam, bs, HW, D) bool, the reference's ``bev_mask``."""
         return self.mask_u8.view(torch.bool)
 
+    def rows(self, q0, q1):
+        """Geometry of the query slice [q0, q1) (BEV row sharding).  The camera gating of the
+        reference reads batch element 0 (quirk 1), so the slice keeps that convention; the
+        compacted hit lists are global and are not sliced."""
+        return BevGeometry(self.reference_points_cam[:, :, q0:q1].contiguous(),
+                           self.mask_u8[:, :, q0:q1].contiguous(),
+                           self.hit_bits[:, q0:q1].contiguous(), self.hit_index, self.hit_count,
+                           self.D)
+
 
 def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w):
     """ref_3d (bs, D, HW, 3) fp32 CUDA; lidar2img (bs, num_cam, 4, 4) -> :class:`BevGeometry`."""

@@ -211,9 +211,17 @@ class BEVFormerEncoder(BaseModule):
     def forward(self, bev_query, key, value, *args, bev_z=None, bev_h=None, bev_w=None,
                 bev_pos=None, spatial_shapes=None, level_start_index=None, valid_ratios=None,
                 prev_bev=None, shift=0., img_metas=None, lidar2img=None, img_shape=None,
-                **kwargs):
+                row_shard=None, **kwargs):
         """bev_query, bev_pos (HW, bs, C); key = value (num_cam, Nk, bs, C); prev_bev
-        (HW, bs, C) or None; shift (bs, 2).  Returns (bs, HW, C) (or the stacked intermediates)."""
+        (HW, bs, C) or None; shift (bs, 2).  Returns (bs, HW, C) (or the stacked intermediates).
+
+        ``row_shard=(rank, world)`` runs only this rank's contiguous block of BEV rows
+        (``parallel.bev_row_range``) and returns (bs, rows*bev_w, C): BEV queries are independent
+        units of SCA / TSA / FFN / LayerNorm, the value tensors (image features, the
+        [prev_bev, bev] pair) stay replicated, and with history (``prev_bev`` given) no layer
+        needs an exchange -- the caller all-gathers the rows once at encoder exit
+        (``parallel.all_gather_bev_rows``).  Without history the TSA value is the current layer
+        input, which would need a per-layer all-gather: that case is refused here."""
         output = bev_query
         intermediate = []
         bs = bev_query.size(1)
@@ -252,9 +260,24 @@ class BEVFormerEncoder(BaseModule):
             hybird_ref_2d = torch.stack([ref_2d, ref_2d], 1).reshape(
                 bs * 2, len_bev, num_bev_level, 2)
 
+        shard_h = bev_h
+        if row_shard is not None:
+            from ..parallel import bev_row_range
+            if prev_bev is None:
+                raise RuntimeError('row sharding needs prev_bev: without history the TSA value is '
+                                   'the current layer input and every layer would need an all-gather')
+            y0, y1 = bev_row_range(bev_h, int(row_shard[0]), int(row_shard[1]))
+            q0, q1 = y0 * bev_w, y1 * bev_w
+            shard_h = y1 - y0
+            bev_query = bev_query[:, q0:q1].contiguous()
+            bev_pos = bev_pos[:, q0:q1].contiguous()
+            hybird_ref_2d = hybird_ref_2d[:, q0:q1].contiguous()
+            geo = geo.rows(q0, q1)
+            kwargs = dict(kwargs, row_slice=(q0, q1))
+
         for layer in self.layers:
             output = layer(bev_query, key, value, *args, bev_pos=bev_pos, ref_2d=hybird_ref_2d,
-                           ref_3d=ref_3d, bev_h=bev_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
+                           ref_3d=ref_3d, bev_h=shard_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
                            level_start_index=level_start_index,
                            reference_points_cam=geo.reference_points_cam, bev_mask=geo.bev_mask,
                            bev_geometry=geo, prev_bev=prev_bev, _tsa_shapes=tsa_shapes, **kwargs)

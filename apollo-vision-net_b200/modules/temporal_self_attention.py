@@ -32,7 +32,8 @@ class TemporalSelfAttention(DeformAttnBase):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, flag='decoder', bev_h=None, bev_w=None, **kwargs):
+                level_start_index=None, flag='decoder', bev_h=None, bev_w=None, row_slice=None,
+                **kwargs):
         """query (bs, HW, C) [batch_first]; value (bs*2, HW, C) = stack([prev_bev, bev], 1) or
         None (first frame); reference_points (bs*2, HW, L, 2) -> (bs, HW, C)."""
         if value is None:
@@ -51,7 +52,10 @@ class TemporalSelfAttention(DeformAttnBase):
         assert self.num_bev_queue == 2
         M, L, P, Q = self.num_heads, self.num_levels, self.num_points, self.num_bev_queue
 
-        query = torch.cat([value[:bs], query], -1)
+        # value[:bs] pairs every query with the same cell of the first queue entry; under BEV row
+        # sharding the queries are the slice ``row_slice`` of the value's cells
+        paired = value[:bs] if row_slice is None else value[:bs, row_slice[0]:row_slice[1]]
+        query = torch.cat([paired, query], -1)
         value = self.value_proj(value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
@@ -59,8 +63,7 @@ class TemporalSelfAttention(DeformAttnBase):
         offsets = self.sampling_offsets(query).view(bs, num_query, M, Q, L, P, 2)
         logits = self.attention_weights(query).view(bs, num_query, M, Q, L * P)
 
-        grid_w = int(bev_w) if (bev_h and bev_w and int(bev_h) * int(bev_w) == num_query
-                                and num_value == num_query) else 0
+        grid_w = int(bev_w) if (bev_h and bev_w and int(bev_h) * int(bev_w) == num_query) else 0
         if reference_points.shape[-1] == 2:
             if reference_points.shape[2] != L:          # a single reference broadcast over levels
                 reference_points = reference_points.expand(-1, -1, L, -1)

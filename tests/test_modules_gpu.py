@@ -372,3 +372,41 @@ def test_layernorm_and_linear_kernels(dtype, C):
     out.backward(g2)
     assert rel_err(lin.bias.grad, g2.double().sum(0)) <= (1e-5 if dtype == torch.float32 else 1e-2)
     assert rel_err(lin.weight.grad, g2.double().t() @ x2.detach().double()) <= (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+def test_row_sharded_encoder_matches_full_on_one_gpu():
+    """BEV row sharding (parallel.py) with the CUDA encoder: the ranks of a 3-way split, run one
+    after the other on one GPU, reproduce the unsharded forward (no collective involved here;
+    the gloo tests cover the all-gather)."""
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    bs, H, W, C = 1, 23, 30, 256
+    levels = [(29, 50), (15, 25)]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs)
+    enc = pkg.build_transformer_layer_sequence(dict(
+        type='BEVFormerEncoder', num_layers=2, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1),
+                       dict(type='SpatialCrossAttention', pc_range=syn.PC_RANGE, embed_dims=C,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_points=8, num_levels=len(levels)))],
+            feedforward_channels=512, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    _randomize(enc, 2)
+    enc.to(DEV).eval()
+    g = torch.Generator().manual_seed(9)
+    bevq, pos, prev = (torch.randn(H * W, bs, C, generator=g).to(DEV) for _ in range(3))
+    feat = torch.randn(6, Nk, bs, C, generator=g).to(DEV)
+    kw = dict(bev_h=H, bev_w=W, bev_pos=pos, spatial_shapes=torch.tensor(shapes_l, device=DEV),
+              level_start_index=torch.tensor(starts_l, device=DEV), prev_bev=prev,
+              shift=torch.tensor([[0.01, 0.02]], device=DEV), lidar2img=l2i, img_shape=img_shape)
+    with torch.no_grad():
+        full = enc(bevq, feat, feat, **kw)
+        parts = [enc(bevq, feat, feat, row_shard=(r, 3), **kw) for r in range(3)]
+    got = torch.cat(parts, 1)
+    assert got.shape == full.shape
+    assert rel_err(got, full) <= 1e-5
+    with pytest.raises(RuntimeError, match='prev_bev'):
+        enc(bevq, feat, feat, row_shard=(0, 2), **dict(kw, prev_bev=None))
