@@ -86,6 +86,8 @@ static int validate_fused(const FusedProblem& f, bool bwd, bool sca, const char*
   if (!bwd && !f.out) return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: out is NULL", fn);
   if (bwd && (!f.g_out || !f.g_value || !f.g_offsets || !f.g_logits))
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: NULL gradient pointer", fn);
+  if (bwd && f.acc_half && (f.value_dtype == MSDA_F32 || !f.acc_scale))
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: the fp16 accumulator needs a 16-bit value dtype and a scale", fn);
   return MSDA_OK;
 }
 
@@ -259,10 +261,12 @@ int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 
 int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
             const void* logits, const float* ref_cam, const uint8_t* bev_mask,
-            const uint32_t* hit_bits, const void* g_slots, float* g_value, void* g_offsets,
+            const uint32_t* hit_bits, const void* g_slots, void* g_value, void* g_offsets,
             void* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, int coord_dtype, void* stream) {
+            int bev_w, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
+            void* stream) {
   FusedProblem f;
+  f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.g_out = g_slots;
   f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
@@ -287,10 +291,12 @@ int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 }
 
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
-            const void* logits, const float* ref, const void* g_out, float* g_value,
+            const void* logits, const float* ref, const void* g_out, void* g_value,
             void* g_offsets, void* g_logits, int bs, int Q, int Nk, int M, int Dh, int L, int P,
-            int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, void* stream) {
+            int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, int accum_dtype,
+            const float* accum_scale, void* stream) {
   FusedProblem f;
+  f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.g_out = g_out; f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
@@ -325,6 +331,18 @@ int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dt
   if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: invalid sizes");
   if (!x || !out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: NULL pointer");
   return launch_colsum(x, out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream) {
+  if (n < 0 || !ws || (n > 0 && !g)) return set_error(MSDA_ERR_BAD_ARGUMENT, "grad_amax_scale: bad argument");
+  return launch_grad_scale(g, n, dtype, ws, static_cast<cudaStream_t>(stream));
+}
+
+int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype, void* stream) {
+  if (n < 0 || (n > 0 && (!acc_f16 || !out || !scale)))
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: bad argument");
+  if (n == 0) return MSDA_OK;
+  return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -63,7 +63,9 @@ struct FusedArgs {
   const uint32_t* hit_bits;
   void* out;
   const void* g_out;
-  float* g_value;
+  void* g_value;               // fp32 accumulator, or fp16 (scaled by *acc_scale) when acc_half
+  const float* acc_scale;
+  int acc_half;
   void* g_offsets;             // CT
   void* g_logits;
   int bs, groups, Nk, M, Dh, L, P, D, Nq;
@@ -403,7 +405,12 @@ fused_bwd_kernel(const FusedArgs a) {
       // lane c scatters channels [4c, 4c+4) and [4*TPH + 4c, 4*TPH + 4c + 4), so that the TPH lanes
       // of a head cover 16*TPH contiguous bytes per reduction instruction (whole sectors); the dot
       // products use the natural [8c, 8c+8) ownership of the 128-bit value loads.
-      float* ghead = a.g_value + head_off + 4 * chunk;
+      float* ghead = static_cast<float*>(a.g_value) + head_off + 4 * chunk;
+      // fp16 accumulator (16-bit value dtypes): one 16-byte red.v4.f16x2 carries the lane's 8
+      // channels in their natural order, scaled by a power of two chosen from max|g_out|
+      __half* ghead16 = static_cast<__half*>(a.g_value) + head_off + chunk * VEC;
+      const bool acc_half = (VEC == 8) && a.acc_half;
+      const float acc_scale = acc_half ? __ldg(a.acc_scale) : 1.f;
 
       float2 g[V2], gs[V2];
       {
@@ -445,6 +452,18 @@ fused_bwd_kernel(const FusedArgs a) {
         auto scatter = [&](int off, float cw) {
           const float aw = w * cw;
           if (aw == 0.f || (a.debug & 1)) return;        // invalid corner, or a zero contribution
+          if (VEC == 8 && acc_half) {
+            const float2 aw2 = splat2(aw * acc_scale);
+            uint32_t h[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 pk = fmul2(aw2, g[k % V2]);
+              const __half2 hk = __floats2half2_rn(pk.x, pk.y);
+              h[k] = *reinterpret_cast<const uint32_t*>(&hk);
+            }
+            red_add_f16x8(ghead16 + boff + off, h[0], h[1], h[2], h[3]);
+            return;
+          }
           const float2 aw2 = splat2(aw);
           float* dst = gb + off;
 #pragma unroll
@@ -610,7 +629,7 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   a.value = f.value; a.shapes = f.shapes; a.starts = f.starts; a.offsets = f.offsets;
   a.logits = f.logits; a.ref = f.ref; a.hit_bits = f.hit_bits;
   a.out = f.out; a.g_out = f.g_out; a.g_value = f.g_value; a.g_offsets = f.g_offsets;
-  a.g_logits = f.g_logits;
+  a.g_logits = f.g_logits; a.acc_scale = f.acc_scale; a.acc_half = f.acc_half;
   a.bs = f.bs; a.groups = f.groups; a.Nk = f.Nk; a.M = f.M; a.Dh = f.Dh; a.L = f.L; a.P = f.P;
   a.D = f.D; a.Nq = f.Nq; a.clamp = f.clamp;
   if (f.M > ROWS)

@@ -137,6 +137,11 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 16-byte reduction of 8 packed fp16 values (4 x f16x2) at L2: half the sectors of the fp32 form
+__device__ __forceinline__ void red_add_f16x8(__half* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};"
+               :: "l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(a), "f"(b) : "memory");
 }

@@ -35,7 +35,9 @@ struct FusedProblem {
   void* out = nullptr;
   float* attn_out = nullptr;
   const void* g_out = nullptr;
-  float* g_value = nullptr;
+  void* g_value = nullptr;             // fp32, or fp16 scaled by *acc_scale when acc_half
+  const float* acc_scale = nullptr;
+  int acc_half = 0;
   void* g_offsets = nullptr;           // coord_dtype
   void* g_logits = nullptr;
   int bs = 0, groups = 0;              // groups = num_cam (SCA) or Q (TSA)
@@ -65,5 +67,8 @@ int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const 
               long long rows, int C, float eps, int dtype, cudaStream_t st);
 int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype,
                   int out_dtype, cudaStream_t st);
+int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st);
+int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
+                        cudaStream_t st);
 
 }  // namespace msda

@@ -29,6 +29,39 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Final stage of the column reductions, run by the LAST CTA to finish (ticket counter in the
+// workspace header, reset for the next launch): out[c] = sum over the gridDim.x partial rows.
+constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the partial rows
+
+template <typename TO>
+__device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __restrict__ out, int ncols) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* counter = reinterpret_cast<unsigned*>(ws);
+    const unsigned ticket = atomicAdd(counter, 1u);
+    last = (ticket == gridDim.x - 1);
+    if (last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const float* partial = ws + kWsHeaderFloats;
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < (int)gridDim.x; r += 4) {
+      s0 += __ldcg(partial + (size_t)(r + 0) * ncols + c);
+      s1 += __ldcg(partial + (size_t)(r + 1) * ncols + c);
+      s2 += __ldcg(partial + (size_t)(r + 2) * ncols + c);
+      s3 += __ldcg(partial + (size_t)(r + 3) * ncols + c);
+    }
+    for (; r < (int)gridDim.x; ++r) s0 += __ldcg(partial + (size_t)r * ncols + c);
+    out[c] = from_f32<TO>((s0 + s1) + (s2 + s3));
+  }
+}
+
 // One warp per row; every lane keeps its slice of the row (C / 32 elements, <= 32) in registers.
 template <typename T, int PER_LANE>
 __global__ void __launch_bounds__(kRowThreads)
@@ -84,7 +117,7 @@ template <typename T, int PER_LANE>
 __global__ void __launch_bounds__(kRowThreads)
 ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-              float* __restrict__ partial, long long rows, int C) {
+              float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
   extern __shared__ float sm[];                       // [warps][2][C]
@@ -149,26 +182,16 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kRowThreads / 32; ++w) s += sm[(size_t)w * 2 * C + c];
-    partial[(size_t)blockIdx.x * 2 * C + c] = s;
+    ws[kWsHeaderFloats + (size_t)blockIdx.x * 2 * C + c] = s;
   }
-}
-
-// out[c] = sum over `n` rows of partial[r][c]  (final stage of the two column reductions)
-template <typename TO>
-__global__ void __launch_bounds__(256)
-colsum_final_kernel(const float* __restrict__ partial, TO* __restrict__ out, int n, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int r = 0; r < n; ++r) s += partial[(size_t)r * C + c];
-  out[c] = from_f32<TO>(s);
+  finalize_columns<T>(ws, dgamma_dbeta, 2 * C);
 }
 
 // Column sums of a (rows, C) matrix: stage 1, per-CTA partials (gridDim.x, C) fp32.  A thread
 // owns 16 bytes of columns; a CTA's threads cover C/VEC column groups x (256 / (C/VEC)) row lanes.
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(kRowThreads)
-colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, long long rows, int C) {
+colsum_kernel(const T* __restrict__ x, float* __restrict__ ws, TO* __restrict__ out, long long rows, int C) {
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ float sm[];                       // [row_lanes][C]
   const int groups = C / VEC;                         // <= 256
@@ -178,7 +201,19 @@ colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, long
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   if (rl < row_lanes) {
-    for (long long r = (long long)blockIdx.x * row_lanes + rl; r < rows; r += (long long)gridDim.x * row_lanes) {
+    const long long step = (long long)gridDim.x * row_lanes;
+    long long r = (long long)blockIdx.x * row_lanes + rl;
+    // four independent 16-byte loads in flight per thread
+    for (; r + 3 * step < rows; r += 4 * step) {
+      float t0[VEC], t1[VEC], t2[VEC], t3[VEC];
+      Vec16IO<T>::load(x + r * C + gidx * VEC, t0);
+      Vec16IO<T>::load(x + (r + step) * C + gidx * VEC, t1);
+      Vec16IO<T>::load(x + (r + 2 * step) * C + gidx * VEC, t2);
+      Vec16IO<T>::load(x + (r + 3 * step) * C + gidx * VEC, t3);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
+    }
+    for (; r < rows; r += step) {
       float t[VEC];
       Vec16IO<T>::load(x + r * C + gidx * VEC, t);
 #pragma unroll
@@ -191,8 +226,9 @@ colsum_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, long
   for (int c = threadIdx.x; c < C; c += kRowThreads) {
     float s = 0.f;
     for (int w = 0; w < row_lanes; ++w) s += sm[(size_t)w * C + c];
-    partial[(size_t)blockIdx.x * C + c] = s;
+    ws[kWsHeaderFloats + (size_t)blockIdx.x * C + c] = s;
   }
+  finalize_columns<TO>(ws, out, C);
 }
 
 static int row_grid() {
@@ -206,8 +242,8 @@ int rowops_partial_rows() { return row_grid(); }
 
 template <typename T, int PER_LANE>
 static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
-                     float* mean, float* rstd, void* dx, float* partial, long long rows, int C, float eps,
-                     cudaStream_t st) {
+                     float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
+                     float eps, cudaStream_t st) {
   const long long need = (rows + kRowThreads / 32 - 1) / (kRowThreads / 32);
   const int grid = (int)(need < row_grid() ? need : row_grid());
   if (grid <= 0) return MSDA_OK;
@@ -221,47 +257,127 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
   const size_t smem = (size_t)(kRowThreads / 32) * 2 * C * sizeof(float);
   ln_bwd_kernel<T, PER_LANE><<<row_grid(), kRowThreads, smem, st>>>(
       static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<const T*>(gamma), mean, rstd,
-      static_cast<T*>(dx), partial, rows, C);
+      static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C);
   count_launch();
   return check_launch("ln_bwd");
 }
 
 template <typename T>
 static int ln_dispatch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
-                       float* mean, float* rstd, void* dx, float* partial, long long rows, int C, float eps,
-                       cudaStream_t st) {
+                       float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
+                       float eps, cudaStream_t st) {
   constexpr int VEC = Vec16<T>::N;
   if (C % (32 * VEC) != 0 || C / 32 > 32)
     return set_error(MSDA_ERR_UNSUPPORTED, "layer_norm: C=%d must be a multiple of %d and <= 1024", C, 32 * VEC);
   switch (C / 32) {
-    case 4: return ln_launch<T, 4>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-    case 8: return ln_launch<T, 8>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-    case 16: return ln_launch<T, 16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-    case 32: return ln_launch<T, 32>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
+    case 4: return ln_launch<T, 4>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
+    case 8: return ln_launch<T, 8>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
+    case 16: return ln_launch<T, 16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
+    case 32: return ln_launch<T, 32>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
     default: break;
   }
   return set_error(MSDA_ERR_UNSUPPORTED, "layer_norm: C=%d not supported (128, 256, 512 or 1024)", C);
 }
 
+// ---- fp16 gradient accumulator helpers -------------------------------------------------------
+// ws layout (floats): [0] ticket counter, [1] running max bits, [16] scale out.
+template <typename T>
+__global__ void __launch_bounds__(256)
+grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) {
+  constexpr int VEC = Vec16<T>::N;
+  float m = 0.f;
+  const long long nv = n / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float t[VEC];
+    Vec16IO<T>::load(g + i * VEC, t);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) m = fmaxf(m, fabsf(t[k]));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nv * VEC + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(to_f32<T>(g[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  unsigned* wsu = reinterpret_cast<unsigned*>(ws);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(wsu + 1, __float_as_uint(m));   // non-negative floats order like uints
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(wsu, 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const float amax = __uint_as_float(atomicExch(wsu + 1, 0u));
+    float s = 1.f;
+    if (amax > 0.f && isfinite(amax)) s = exp2f(floorf(log2f(4.0f / amax)));
+    ws[16] = s;
+    wsu[0] = 0u;
+  }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n) {
+  const float inv = 1.0f / __ldg(scale);             // power of two: exact
+  const long long nv = n / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float t[8];
+    Vec16<__half>::unpack(ldg128(acc + i * 8), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t[k] *= inv;
+    if constexpr (sizeof(TO) == 2) {
+      *reinterpret_cast<uint4*>(out + i * 8) = Vec16<TO>::pack(t);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[i * 8 + k] = from_f32<TO>(t[k]);
+    }
+  }
+  if (blockIdx.x == 0)
+    for (long long i = nv * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
+}
+
+int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st) {
+  const int grid = row_grid();
+  if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, ws);
+  else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, ws);
+  else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, ws);
+  count_launch();
+  return check_launch("grad_amax_scale");
+}
+
+int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
+                        cudaStream_t st) {
+  const long long need = (n / 8 + 255) / 256;
+  const int grid = (int)(need < (long long)row_grid() * 4 ? (need > 0 ? need : 1) : (long long)row_grid() * 4);
+  const __half* a = static_cast<const __half*>(acc16);
+  if (out_dtype == MSDA_F32) unscale_cast_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float*>(out), scale, n);
+  else if (out_dtype == MSDA_BF16) unscale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, static_cast<__nv_bfloat16*>(out), scale, n);
+  else unscale_cast_kernel<__half><<<grid, 256, 0, st>>>(a, static_cast<__half*>(out), scale, n);
+  count_launch();
+  return check_launch("unscale_cast");
+}
+
 int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
               long long rows, int C, float eps, int dtype, cudaStream_t st) {
-  int rc;
-  if (dtype == MSDA_F32) rc = ln_dispatch<float>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-  else if (dtype == MSDA_BF16) rc = ln_dispatch<__nv_bfloat16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-  else rc = ln_dispatch<__half>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, rows, C, eps, st);
-  if (rc || !bwd) return rc;
-  // final reduction of the per-CTA partial rows [dgamma | dbeta] into the (2, C) output strip
-  const int n = row_grid();
-  const int blocks = (2 * C + 255) / 256;
   if (dtype == MSDA_F32)
-    colsum_final_kernel<float><<<blocks, 256, 0, st>>>(partial, static_cast<float*>(dgamma_dbeta), n, 2 * C);
-  else if (dtype == MSDA_BF16)
-    colsum_final_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, static_cast<__nv_bfloat16*>(dgamma_dbeta), n, 2 * C);
-  else
-    colsum_final_kernel<__half><<<blocks, 256, 0, st>>>(partial, static_cast<__half*>(dgamma_dbeta), n, 2 * C);
+    return ln_dispatch<float>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
+  if (dtype == MSDA_BF16)
+    return ln_dispatch<__nv_bfloat16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
+  return ln_dispatch<__half>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
+}
+
+template <typename T>
+static int colsum_out(const void* x, void* out, float* ws, long long rows, int C, int out_dtype, int grid,
+                      size_t smem, cudaStream_t st) {
+  const T* xi = static_cast<const T*>(x);
+  if (out_dtype == MSDA_F32) colsum_kernel<T, float><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<float*>(out), rows, C);
+  else if (out_dtype == MSDA_BF16) colsum_kernel<T, __nv_bfloat16><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<__nv_bfloat16*>(out), rows, C);
+  else colsum_kernel<T, __half><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<__half*>(out), rows, C);
   count_launch();
-  return check_launch("ln_bwd(final)");
+  return check_launch("colsum");
 }
 
 int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype, int out_dtype,
@@ -273,16 +389,9 @@ int launch_colsum(const void* x, void* out, float* partial, long long rows, int 
   const long long need = (rows + row_lanes - 1) / row_lanes;
   const int grid = (int)(need < row_grid() ? (need > 0 ? need : 1) : row_grid());
   const size_t smem = (size_t)row_lanes * C * sizeof(float);
-  if (dtype == MSDA_F32) colsum_partial_kernel<float><<<grid, kRowThreads, smem, st>>>(static_cast<const float*>(x), partial, rows, C);
-  else if (dtype == MSDA_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, kRowThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), partial, rows, C);
-  else colsum_partial_kernel<__half><<<grid, kRowThreads, smem, st>>>(static_cast<const __half*>(x), partial, rows, C);
-  count_launch();
-  if (int rc = check_launch("colsum")) return rc;
-  if (out_dtype == MSDA_F32) colsum_final_kernel<float><<<(C + 255) / 256, 256, 0, st>>>(partial, static_cast<float*>(out), grid, C);
-  else if (out_dtype == MSDA_BF16) colsum_final_kernel<__nv_bfloat16><<<(C + 255) / 256, 256, 0, st>>>(partial, static_cast<__nv_bfloat16*>(out), grid, C);
-  else colsum_final_kernel<__half><<<(C + 255) / 256, 256, 0, st>>>(partial, static_cast<__half*>(out), grid, C);
-  count_launch();
-  return check_launch("colsum(final)");
+  if (dtype == MSDA_F32) return colsum_out<float>(x, out, partial, rows, C, out_dtype, grid, smem, st);
+  if (dtype == MSDA_BF16) return colsum_out<__nv_bfloat16>(x, out, partial, rows, C, out_dtype, grid, smem, st);
+  return colsum_out<__half>(x, out, partial, rows, C, out_dtype, grid, smem, st);
 }
 
 }  // namespace msda

@@ -85,6 +85,41 @@ def _check_value(value):
     return value.contiguous()
 
 
+_scale_ws = {}
+
+
+def _accumulator(value, g_out):
+    """grad_value accumulator for the fused backward kernels.
+
+    fp32 value: fp32 accumulator (red.global.add.v4.f32).  16-bit value: fp16 accumulator scaled by
+    a power of two derived on the device from max|g_out| (no host sync) -- half the L2 sectors per
+    update; set ``APOLLO_B200_FP32_ACCUM=1`` to force fp32.  Returns (buffer, code, scale_tensor).
+    """
+    import os
+    dev = value.device
+    if value.dtype == torch.float32 or os.environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1':
+        return torch.zeros(value.shape, dtype=torch.float32, device=dev), _lib.F32, None
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _scale_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(64, dtype=torch.float32, device=dev)
+        _scale_ws[key] = ws
+    with torch.cuda.device(dev):
+        _lib.call('grad_amax_scale', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
+                  ws.data_ptr(), _stream_ptr(value))
+    return torch.zeros(value.shape, dtype=torch.float16, device=dev), _lib.F16, ws[16:17]
+
+
+def _finish_accumulator(acc, code, scale, value):
+    if code == _lib.F32:
+        return acc.to(value.dtype)
+    out = torch.empty(value.shape, dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        _lib.call('unscale_cast', acc.data_ptr(), out.data_ptr(), scale.data_ptr(), acc.numel(),
+                  _DTYPE_CODE[value.dtype], _stream_ptr(value))
+    return out
+
+
 def _coords(value, offsets, logits):
     """Offsets / logits are consumed in fp32 or in the value dtype (no conversion pass for a
     bf16 model); anything else is brought to fp32."""
@@ -140,7 +175,7 @@ class SpatialCrossAttnFunction(Function):
         bs, HW, _, L, P, _ = offsets.shape
         D = ref_cam.shape[3]
         g_slots = g_slots.to(value.dtype).contiguous()
-        g_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        g_value, acc_code, acc_scale = _accumulator(value, g_slots)
         g_off = torch.empty_like(offsets)
         g_log = torch.empty_like(logits)
         with torch.cuda.device(value.device):
@@ -148,8 +183,10 @@ class SpatialCrossAttnFunction(Function):
                 logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
                 bs, num_cam, Nk, M, Dh, L, P, D, HW, ctx.bev_w, _DTYPE_CODE[value.dtype],
-                _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
-        return (g_value.to(value.dtype), None, None, g_off, g_log, None, None, None, None, None)
+                _DTYPE_CODE[offsets.dtype], acc_code,
+                None if acc_scale is None else acc_scale.data_ptr(), _stream_ptr(value))
+        g_value = _finish_accumulator(g_value, acc_code, acc_scale, value)
+        return (g_value, None, None, g_off, g_log, None, None, None, None, None)
 
 
 class QueueDeformAttnFunction(Function):
@@ -193,18 +230,20 @@ class QueueDeformAttnFunction(Function):
         BQ, Nk, M, Dh = value.shape
         bs, Nq, _, Q, L, P, _ = offsets.shape
         g_out = g_out.to(value.dtype).contiguous()
-        g_value = torch.zeros(value.shape, dtype=torch.float32, device=value.device)
+        g_value, acc_code, acc_scale = _accumulator(value, g_out)
         g_off = torch.empty_like(offsets)
         g_log = torch.empty_like(logits)
         with torch.cuda.device(value.device):
             _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                 logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
                 g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.bev_w, ctx.clamp,
-                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
+                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], acc_code,
+                None if acc_scale is None else acc_scale.data_ptr(), _stream_ptr(value))
+        g_value = _finish_accumulator(g_value, acc_code, acc_scale, value)
         g_ref = None
         if ctx.needs_input_grad[5]:
             # loc = ref + off / (W, H)  =>  d ref = sum over heads and points of d off * (W, H)
             wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(torch.float32)      # (L, 2)
             g_ref = (g_off.float() * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
             g_ref = g_ref.permute(0, 2, 1, 3, 4).reshape(bs * Q, Nq, L, 2)
-        return g_value.to(value.dtype), None, None, g_off, g_log, g_ref, None, None
+        return g_value, None, None, g_off, g_log, g_ref, None, None

@@ -20,11 +20,16 @@ from .multi_scale_deformable_attn_function import _DTYPE_CODE, _stream_ptr, cust
 _workspaces = {}
 
 
+_WS_HEADER = 64      # floats: ticket counter of the "last CTA finishes" reduction (kept at zero)
+
+
 def _workspace(device, floats):
-    key = (device.type, device.index)
+    """Zero-initialised scratch, one per (device, stream): [64-float header | partial rows].  The
+    kernels leave the header at zero, so the buffer is reusable without a memset."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
-    if ws is None or ws.numel() < floats:
-        ws = torch.empty(max(floats, 1 << 20), dtype=torch.float32, device=device)
+    if ws is None or ws.numel() < floats + _WS_HEADER:
+        ws = torch.zeros(max(floats + _WS_HEADER, 1 << 20), dtype=torch.float32, device=device)
         _workspaces[key] = ws
     return ws
 

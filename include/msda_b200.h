@@ -156,15 +156,20 @@ int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
             int bev_w, int value_dtype, int coord_dtype, void* stream);
 
 /*   g_slots   (bs, HW, M*Dh) value_dtype   gradient w.r.t. `slots`
- *   g_value   (bs*num_cam, Nk, M, Dh) fp32 accumulator (zero-filled by the caller)
+ *   g_value   (bs*num_cam, Nk, M, Dh) accumulator, zero-filled by the caller: fp32
+ *             (accum_dtype = MSDA_F32), or fp16 (accum_dtype = MSDA_F16, 16-bit value dtypes only)
+ *             holding gradient * (*accum_scale), a power of two from grad_amax_scale(); the fp16
+ *             form halves the L2 sectors per update (red.global.add.noftz.v4.f16x2) and is
+ *             turned into the value dtype by unscale_cast()
  *   g_offsets (bs, HW, M, L, P, 2) coord_dtype, fully written
  *   g_logits  (bs, HW, M, L*P) coord_dtype, fully written (softmax backward included)        */
 int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const void* offsets, const void* logits, const float* ref_cam,
             const uint8_t* bev_mask, const uint32_t* hit_bits, const void* g_slots,
-            float* g_value, void* g_offsets, void* g_logits,
+            void* g_value, void* g_offsets, void* g_logits,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, int coord_dtype, void* stream);
+            int bev_w, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
+            void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Fused temporal self-attention / decoder cross-attention core
@@ -188,9 +193,19 @@ int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
 
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const void* offsets, const void* logits, const float* ref, const void* g_out,
-            float* g_value, void* g_offsets, void* g_logits,
+            void* g_value, void* g_offsets, void* g_logits,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
-            float clamp, int value_dtype, int coord_dtype, void* stream);
+            float clamp, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
+            void* stream);
+
+/* Helpers of the fp16 gradient accumulator.
+ *   grad_amax_scale: ws is a zero-initialised fp32 scratch of >= 64 floats (left zeroed except
+ *     ws[16]); on return (stream order) ws[16] = 2^floor(log2(4 / max|g|)) (1 when g is all zero):
+ *     single contributions are <= 4 in fp16, 16 000 same-sign maximal updates stay finite.
+ *   unscale_cast: out[i] = (out_dtype)(acc_f16[i] / *scale).                                   */
+int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream);
+int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section
@@ -200,8 +215,11 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *
  *   x, y, dy, dx  (rows, C) dtype;  gamma, beta (C,) dtype;  mean, rstd (rows,) fp32
  *   dgamma_dbeta  (2, C) dtype out: row 0 = d gamma, row 1 = d beta
- *   partial       fp32 scratch of rowops_workspace_rows() * 2 * C floats (ln_bwd) or
- *                 rowops_workspace_rows() * C floats (colsum)
+ *   partial       fp32 scratch of 64 + rowops_workspace_rows() * 2 * C floats (ln_bwd) or
+ *                 64 + rowops_workspace_rows() * C floats (colsum); its first 64 floats are a
+ *                 ticket counter that must be ZERO on entry and is left at zero (the last CTA
+ *                 to finish folds the per-CTA partial rows into the output: one launch, no
+ *                 atomics on the data); one scratch buffer per stream
  *   C must be 128, 256, 512 or 1024 for LayerNorm; a multiple of 16 bytes per row for colsum.
  * ------------------------------------------------------------------------------- */
 int rowops_workspace_rows(void);

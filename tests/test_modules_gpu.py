@@ -338,6 +338,36 @@ def test_fused_bf16_within_tolerance():
     assert rel_err(out, ref) <= 1e-2
 
 
+@pytest.mark.parametrize('accum', ['fp16', 'fp32'])
+def test_fused_bf16_backward_accumulators(accum, monkeypatch):
+    """bf16 fused backward on identical (bf16-rounded) inputs: the scaled fp16 grad_value
+    accumulator and the fp32 one both stay within bf16 resolution of the fp32 oracle gradient,
+    also for tiny upstream gradients (the scale is derived on the device from max|g_out|)."""
+    from apollo_vision_net_b200.fused_ops import QueueDeformAttnFunction
+    from oracle.msda_oracle import msda_torch
+    monkeypatch.setenv('APOLLO_B200_FP32_ACCUM', '1' if accum == 'fp32' else '0')
+    g = torch.Generator().manual_seed(31)
+    bs, H, W, M, Dh, L, P, Nq = 1, 24, 40, 8, 32, 1, 4, 3000
+    value = torch.randn(bs, H * W, M, Dh, generator=g).bfloat16()
+    offsets = torch.randn(bs, Nq, M, 1, L, P, 2, generator=g) * 3
+    logits = torch.randn(bs, Nq, M, 1, L * P, generator=g)
+    ref = torch.rand(bs, Nq, L, 2, generator=g)
+    shapes = torch.tensor([[H, W]])
+    starts = torch.tensor([0])
+    for gscale in (1.0, 1e-6):
+        g_out = (torch.randn(bs, Nq, M * Dh, generator=g) * gscale).bfloat16()
+        v1 = value.float().requires_grad_(True)
+        loc = ref[:, :, None, :, None, :] + offsets[:, :, :, 0] / torch.tensor([W, H]).view(1, 1, 1, 1, 1, 2)
+        att = logits[:, :, :, 0].softmax(-1).view(bs, Nq, M, L, P)
+        msda_torch(v1, shapes, loc, att).backward(g_out.float())
+        v2 = value.to(DEV).requires_grad_(True)
+        out = QueueDeformAttnFunction.apply(v2, shapes.to(DEV), starts.to(DEV), offsets.to(DEV),
+                                            logits.to(DEV), ref.to(DEV), None, 0)
+        out.backward(g_out.to(DEV))
+        assert torch.isfinite(v2.grad).all()
+        assert rel_err(v2.grad, v1.grad) <= 1e-2, (accum, gscale)
+
+
 # ------------------------------------------------------------------ row-wise companions ----
 @pytest.mark.parametrize('dtype,C', [(torch.float32, 256), (torch.bfloat16, 256), (torch.float32, 512),
                                      (torch.bfloat16, 512)])

@@ -37,6 +37,7 @@ def main():
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--which', default='sca,tsa')
+    ap.add_argument('--accum', default='auto', help="'auto' (fp16 for 16-bit values) or 'fp32'")
     ap.add_argument('--coord', default='same', help="'same' = offsets/logits in the value dtype, 'fp32'")
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -68,7 +69,10 @@ def main():
         logits = torch.randn(1, HW, M, L * P, generator=g, device=dev).to(cdtype)
         slots = torch.empty(1, HW, C, device=dev, dtype=dtype)
         gs = torch.randn(1, HW, C, generator=g, device=dev).to(dtype)
-        gv = torch.zeros(6, Nk, M, Dh, device=dev)
+        half_acc = dtype != torch.float32 and args.accum == 'auto'
+        gv = torch.zeros(6, Nk, M, Dh, device=dev, dtype=torch.float16 if half_acc else torch.float32)
+        sws = torch.zeros(64, device=dev)
+        acode = 1 if half_acc else 0
         goff = torch.empty_like(offsets)
         glog = torch.empty_like(logits)
         code = _DTYPE_CODE[dtype]
@@ -79,10 +83,12 @@ def main():
                       geo.hit_bits.data_ptr(), slots.data_ptr(), None, 1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, st)
 
         def bwd():
+            if half_acc:
+                _lib.call('grad_amax_scale', gs.data_ptr(), gs.numel(), code, sws.data_ptr(), st)
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
-                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, st)
+                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, acode, sws[16:].data_ptr() if half_acc else None, st)
         res['sca_fwd_us'] = round(timeit(fwd, flush, args.iters), 1)
         res['sca_bwd_us'] = round(timeit(bwd, flush, args.iters), 1)
         res['sca_samples'] = pairs * M * L * P
@@ -96,7 +102,10 @@ def main():
         ref = torch.stack([ref2d + 0.004, ref2d], 1).reshape(2, HW, 1, 2).contiguous()
         out = torch.empty(1, HW, C, device=dev, dtype=dtype)
         go = torch.randn(1, HW, C, generator=g, device=dev).to(dtype)
-        gv = torch.zeros(Q, HW, M, Dh, device=dev)
+        gv = torch.zeros(Q, HW, M, Dh, device=dev, dtype=torch.float16 if (dtype != torch.float32 and args.accum == 'auto') else torch.float32)
+        half_acc = gv.dtype == torch.float16
+        sws = torch.zeros(64, device=dev)
+        acode = 1 if half_acc else 0
         goff = torch.empty_like(offsets)
         glog = torch.empty_like(logits)
         tshape = torch.tensor([[H, W]], device=dev)
@@ -108,9 +117,12 @@ def main():
                       logits.data_ptr(), ref.data_ptr(), out.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, st)
 
         def tbwd():
+            if half_acc:
+                _lib.call('grad_amax_scale', go.data_ptr(), go.numel(), code, sws.data_ptr(), st)
             _lib.call('tsa_bwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(), goff.data_ptr(),
-                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, st)
+                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, acode,
+                      sws[16:].data_ptr() if half_acc else None, st)
         res['tsa_fwd_us'] = round(timeit(tfwd, flush, args.iters), 1)
         res['tsa_bwd_us'] = round(timeit(tbwd, flush, args.iters), 1)
     res.update(bev=args.bev, dtype=args.dtype, pairs=pairs)
