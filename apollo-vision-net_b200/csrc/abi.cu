@@ -237,8 +237,8 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
   if (bs <= 0 || num_cam <= 0 || num_cam > 32 || HW <= 0 || D <= 0)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_point_sampling: invalid sizes bs=%d cams=%d HW=%d D=%d",
                      bs, num_cam, HW, D);
-  if (!ref_3d || !lidar2img || !pc_range_host || !ref_cam || !bev_mask || !hit_bits || !hit_index ||
-      !hit_count)
+  if (!ref_3d || !lidar2img || !pc_range_host || !ref_cam || !bev_mask || !hit_bits ||
+      ((hit_index == nullptr) != (hit_count == nullptr)))
     return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_point_sampling: NULL pointer");
   return launch_point_sampling(ref_3d, lidar2img, pc_range_host, img_h, img_w, bs, num_cam, HW, D,
                                ref_cam, bev_mask, hit_bits, hit_index, hit_count,

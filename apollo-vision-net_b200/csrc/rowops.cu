@@ -29,9 +29,11 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Final stage of the column reductions, run by the LAST CTA to finish (ticket counter in the
-// workspace header, reset for the next launch): out[c] = sum over the gridDim.x partial rows.
-constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the partial rows
+// Final stage of the column reductions.  Every CTA adds its partial sums into an fp32 strip in
+// the workspace with reductions at L2 (the strip is all zero on entry); the LAST CTA to finish
+// (ticket counter in the workspace header) converts the strip into the output and zeroes strip and
+// counter again, so the workspace is reusable without a memset.  One launch, no serial tail.
+constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the strip
 
 template <typename TO>
 __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __restrict__ out, int ncols) {
@@ -47,18 +49,10 @@ __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __r
   __syncthreads();
   if (!last) return;
   __threadfence();
-  const float* partial = ws + kWsHeaderFloats;
+  float* strip = ws + kWsHeaderFloats;
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int r = 0;
-    for (; r + 3 < (int)gridDim.x; r += 4) {
-      s0 += __ldcg(partial + (size_t)(r + 0) * ncols + c);
-      s1 += __ldcg(partial + (size_t)(r + 1) * ncols + c);
-      s2 += __ldcg(partial + (size_t)(r + 2) * ncols + c);
-      s3 += __ldcg(partial + (size_t)(r + 3) * ncols + c);
-    }
-    for (; r < (int)gridDim.x; ++r) s0 += __ldcg(partial + (size_t)r * ncols + c);
-    out[c] = from_f32<TO>((s0 + s1) + (s2 + s3));
+    out[c] = from_f32<TO>(__ldcg(strip + c));
+    strip[c] = 0.f;
   }
 }
 
@@ -182,7 +176,7 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kRowThreads / 32; ++w) s += sm[(size_t)w * 2 * C + c];
-    ws[kWsHeaderFloats + (size_t)blockIdx.x * 2 * C + c] = s;
+    atomicAdd(ws + kWsHeaderFloats + c, s);
   }
   finalize_columns<T>(ws, dgamma_dbeta, 2 * C);
 }
@@ -226,7 +220,7 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ ws, TO* __restrict__ 
   for (int c = threadIdx.x; c < C; c += kRowThreads) {
     float s = 0.f;
     for (int w = 0; w < row_lanes; ++w) s += sm[(size_t)w * C + c];
-    ws[kWsHeaderFloats + (size_t)blockIdx.x * C + c] = s;
+    atomicAdd(ws + kWsHeaderFloats + c, s);
   }
   finalize_columns<TO>(ws, out, C);
 }

@@ -46,8 +46,10 @@ class BevGeometry:
                            self.D)
 
 
-def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w):
-    """ref_3d (bs, D, HW, 3) fp32 CUDA; lidar2img (bs, num_cam, 4, 4) -> :class:`BevGeometry`."""
+def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w, with_lists=True):
+    """ref_3d (bs, D, HW, 3) fp32 CUDA; lidar2img (bs, num_cam, 4, 4) -> :class:`BevGeometry`.
+    ``with_lists=False`` skips the ordered per-camera hit lists (``hit_index`` / ``hit_count``
+    are then None); the fused spatial cross-attention only needs the bit field."""
     _require_cuda(ref_3d=ref_3d)
     dev = ref_3d.device
     ref_3d = ref_3d.to(torch.float32).contiguous()
@@ -58,13 +60,14 @@ def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w):
     ref_cam = torch.empty((num_cam, bs, HW, D, 2), dtype=torch.float32, device=dev)
     mask = torch.empty((num_cam, bs, HW, D), dtype=torch.uint8, device=dev)
     hit_bits = torch.empty((bs, HW), dtype=torch.int32, device=dev)
-    hit_index = torch.empty((num_cam, HW), dtype=torch.int32, device=dev)
-    hit_count = torch.empty((num_cam,), dtype=torch.int32, device=dev)
+    hit_index = torch.empty((num_cam, HW), dtype=torch.int32, device=dev) if with_lists else None
+    hit_count = torch.empty((num_cam,), dtype=torch.int32, device=dev) if with_lists else None
     pc = (ctypes.c_double * 6)(*[float(x) for x in pc_range])
     with torch.cuda.device(dev):
         _lib.call('bev_point_sampling', ref_3d.data_ptr(), l2i.data_ptr(), ctypes.cast(pc, ctypes.c_void_p), float(img_h),
             float(img_w), bs, num_cam, HW, D, ref_cam.data_ptr(), mask.data_ptr(),
-            hit_bits.data_ptr(), hit_index.data_ptr(), hit_count.data_ptr(), _stream_ptr(ref_3d))
+            hit_bits.data_ptr(), hit_index.data_ptr() if with_lists else None,
+            hit_count.data_ptr() if with_lists else None, _stream_ptr(ref_3d))
     return BevGeometry(ref_cam, mask, hit_bits, hit_index, hit_count, D)
 
 

@@ -195,7 +195,7 @@ class BEVFormerEncoder(BaseModule):
         return l2i, h, w
 
     def point_sampling(self, reference_points, pc_range, img_metas=None, lidar2img=None,
-                       img_shape=None, return_geometry=False):
+                       img_shape=None, return_geometry=False, with_lists=True):
         """reference_points (bs, D, HW, 3) -> (reference_points_cam (num_cam, bs, HW, D, 2),
         bev_mask (num_cam, bs, HW, D) bool), reference :89-241; ``return_geometry`` also hands
         back the device-side hit bit field and compacted hit lists."""
@@ -203,7 +203,7 @@ class BEVFormerEncoder(BaseModule):
             lidar2img, h, w = self._meta_geometry(img_metas)
         else:
             h, w = int(img_shape[0]), int(img_shape[1])
-        geo = bev_point_sampling(reference_points, pc_range, lidar2img, h, w)
+        geo = bev_point_sampling(reference_points, pc_range, lidar2img, h, w, with_lists=with_lists)
         if return_geometry:
             return geo
         return geo.reference_points_cam, geo.bev_mask
@@ -239,7 +239,7 @@ class BEVFormerEncoder(BaseModule):
         ref_2d = ref_2d_base.clone()
 
         geo = self.point_sampling(ref_3d, self.pc_range, img_metas, lidar2img, img_shape,
-                                  return_geometry=True)
+                                  return_geometry=True, with_lists=False)
 
         # "bug kept for reproducing the paper": shift_ref_2d aliases ref_2d (reference :309-311)
         shift_ref_2d = ref_2d

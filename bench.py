@@ -262,13 +262,17 @@ def run_b200(args):
     peak, peak_src = measured_peak()
     Nk = sum(h * w for h, w in levels)
     L, P, M, Dh = len(levels), SCA_POINTS, HEADS, C // HEADS
-    ev = 2                                                           # bf16 value / grads
-    sca_fwd_bytes = (6 * Nk * C * ev + HW * M * L * P * 2 * 4 + HW * M * L * P * 4
-                     + 6 * HW * PILLAR * 2 * 4 + HW * 4 + HW * C * ev)
-    sca_bwd_bytes = (sca_fwd_bytes + 2 * 6 * Nk * C * 4 + HW * M * L * P * 2 * 4 + HW * M * L * P * 4)
+    ev = 2                       # bf16 value / outputs / upstream gradients
+    ec = 2                       # offsets / logits and their gradients arrive in the model dtype (bf16)
+    ea = 4 if os.environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1' else 2   # grad_value accumulator
+    # compulsory traffic, every operand once: value + offsets + logits + ref_cam +
+    # hit bits + out; backward adds g_out (= |out|), 2 x accumulator (zero-fill + final), g_offsets, g_logits
+    sca_fwd_bytes = (6 * Nk * C * ev + HW * M * L * P * 3 * ec + 6 * HW * PILLAR * 2 * 4 + HW * 4
+                     + HW * C * ev)
+    sca_bwd_bytes = sca_fwd_bytes + 2 * 6 * Nk * C * ea + HW * M * L * P * 3 * ec
     tsa_s = 2 * 1 * TSA_POINTS
-    tsa_fwd_bytes = 2 * HW * C * ev + HW * M * tsa_s * 3 * 4 + 2 * HW * 2 * 4 + HW * C * ev
-    tsa_bwd_bytes = tsa_fwd_bytes + 2 * 2 * HW * C * 4 + HW * M * tsa_s * 3 * 4
+    tsa_fwd_bytes = 2 * HW * C * ev + HW * M * tsa_s * 3 * ec + 2 * HW * 2 * 4 + HW * C * ev
+    tsa_bwd_bytes = tsa_fwd_bytes + 2 * 2 * HW * C * ea + HW * M * tsa_s * 3 * ec
     algo = dict(sca_fwd=sca_fwd_bytes, sca_bwd=sca_bwd_bytes, tsa_fwd=tsa_fwd_bytes,
                 tsa_bwd=tsa_bwd_bytes)
     kernels = {}

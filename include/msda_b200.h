@@ -124,7 +124,8 @@ int msda_fwd_bwd_host(const void* value_host, const int64_t* shapes_host, const 
  *   hit_index  (num_cam, HW) int32 out: ascending query indices seen by camera i in
  *              batch element 0 (the reference's quirk, :137); entries past the count
  *              are -1
- *   hit_count  (num_cam,) int32 out
+ *   hit_count  (num_cam,) int32 out   (hit_index and hit_count may both be NULL: the fused
+ *              kernels only read hit_bits, the ordered lists are for callers that want them)
  * ------------------------------------------------------------------------------- */
 int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double* pc_range_host,
                        float img_h, float img_w, int bs, int num_cam, int HW, int D,
@@ -215,11 +216,10 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
  *
  *   x, y, dy, dx  (rows, C) dtype;  gamma, beta (C,) dtype;  mean, rstd (rows,) fp32
  *   dgamma_dbeta  (2, C) dtype out: row 0 = d gamma, row 1 = d beta
- *   partial       fp32 scratch of 64 + rowops_workspace_rows() * 2 * C floats (ln_bwd) or
- *                 64 + rowops_workspace_rows() * C floats (colsum); its first 64 floats are a
- *                 ticket counter that must be ZERO on entry and is left at zero (the last CTA
- *                 to finish folds the per-CTA partial rows into the output: one launch, no
- *                 atomics on the data); one scratch buffer per stream
+ *   partial       fp32 scratch of 64 + 2 * C floats, ALL ZERO on entry and left all zero: a ticket
+ *                 counter plus an fp32 strip that every CTA reduces its partial sums into; the
+ *                 last CTA to finish converts the strip into the output (one launch); one
+ *                 scratch buffer per stream
  *   C must be 128, 256, 512 or 1024 for LayerNorm; a multiple of 16 bytes per row for colsum.
  * ------------------------------------------------------------------------------- */
 int rowops_workspace_rows(void);
