@@ -64,7 +64,8 @@ def build(force=False, verbose=False):
 
     def compile_one(args):
         src, obj = args
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get('MSDA_NVCC_FLAGS', '').split() + [
+            '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -31,6 +31,14 @@
 namespace msda {
 
 constexpr int kFusedThreads = 256;
+#ifndef FUSED_BWD_UNROLL
+#define FUSED_BWD_UNROLL 2
+#endif
+#ifndef FUSED_BWD_MINBLOCKS
+#define FUSED_BWD_MINBLOCKS 3
+#endif
+#define FUSED_PRAGMA(x) _Pragma(#x)
+#define FUSED_UNROLL(n) FUSED_PRAGMA(unroll n)
 enum { MODE_SCA = 0, MODE_TSA = 1 };
 
 template <int TPH>
@@ -339,8 +347,8 @@ fused_fwd_kernel(const FusedArgs a) {
   }
 }
 
-template <typename T, typename CT, int TPH, int MODE>
-__global__ void __launch_bounds__(kFusedThreads)
+template <typename T, typename CT, int TPH, int MODE, bool ACC_HALF>
+__global__ void __launch_bounds__(kFusedThreads, FUSED_BWD_MINBLOCKS)
 fused_bwd_kernel(const FusedArgs a) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int V2 = VEC / 2;
@@ -409,14 +417,13 @@ fused_bwd_kernel(const FusedArgs a) {
       // fp16 accumulator (16-bit value dtypes): one 16-byte red.v4.f16x2 carries the lane's 8
       // channels in their natural order, scaled by a power of two chosen from max|g_out|
       __half* ghead16 = static_cast<__half*>(a.g_value) + head_off + chunk * VEC;
-      const bool acc_half = (VEC == 8) && a.acc_half;
-      const float acc_scale = acc_half ? __ldg(a.acc_scale) : 1.f;
+      const float acc_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
 
       float2 g[V2], gs[V2];
       {
         const T* grow_ptr = static_cast<const T*>(a.g_out) + grow * a.Dh;
         Vec16<T>::unpack2(ldg128(grow_ptr + chunk * VEC), g);
-        if (VEC == 4) {
+        if (VEC == 4 || ACC_HALF) {
 #pragma unroll
           for (int i = 0; i < V2; ++i) gs[i] = g[i];
         } else {
@@ -439,6 +446,12 @@ fused_bwd_kernel(const FusedArgs a) {
         }
       }
 
+      __half2 gh[4];
+      if (ACC_HALF) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gh[k] = __floats2half2_rn(g[k % V2].x * acc_scale, g[k % V2].y * acc_scale);
+      }
+
       // One sample against one value map: scatters grad_value, accumulates the row's location /
       // weight gradients in the shared row (one writer per (row, sample)).
       auto sample = [&](size_t boff, int H, int W, float lx, float ly, float w, int s, bool mine) {
@@ -452,13 +465,13 @@ fused_bwd_kernel(const FusedArgs a) {
         auto scatter = [&](int off, float cw) {
           const float aw = w * cw;
           if (aw == 0.f || (a.debug & 1)) return;        // invalid corner, or a zero contribution
-          if (VEC == 8 && acc_half) {
-            const float2 aw2 = splat2(aw * acc_scale);
+          if (ACC_HALF) {
+            // gh = fp16(g * scale) per row; one HMUL2 per channel pair, one 16-byte reduction
+            const __half2 aw2 = __float2half2_rn(aw);
             uint32_t h[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 pk = fmul2(aw2, g[k % V2]);
-              const __half2 hk = __floats2half2_rn(pk.x, pk.y);
+              const __half2 hk = __hmul2(aw2, gh[k]);
               h[k] = *reinterpret_cast<const uint32_t*>(&hk);
             }
             red_add_f16x8(ghead16 + boff + off, h[0], h[1], h[2], h[3]);
@@ -528,7 +541,7 @@ fused_bwd_kernel(const FusedArgs a) {
             const int H = lv.t.h[l], W = lv.t.w[l];
             const size_t loff = coff + (size_t)lv.t.start[l] * pix_stride;
             int z = 0;
-#pragma unroll 2
+FUSED_UNROLL(FUSED_BWD_UNROLL)
             for (int p = 0; p < a.P; ++p) {
               const int s = l * a.P + p;
               const float2 r = __ldg(rc + z);
@@ -546,7 +559,7 @@ fused_bwd_kernel(const FusedArgs a) {
             const size_t loff = boff + (size_t)lv.t.start[l] * pix_stride;
             const float2 r = __ldg(reinterpret_cast<const float2*>(
                 a.ref + ((((size_t)b * a.groups + j) * a.Nq + q) * a.L + l) * 2));
-#pragma unroll 2
+FUSED_UNROLL(FUSED_BWD_UNROLL)
             for (int p = 0; p < a.P; ++p) {
               const int s = (j * a.L + l) * a.P + p;
               const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
@@ -657,7 +670,10 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float);
   if (smem > 200 * 1024)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: %d samples per row need %zu bytes of shared memory", what, S, smem);
-  auto kfn = bwd ? fused_bwd_kernel<T, CT, TPH, MODE> : fused_fwd_kernel<T, CT, TPH, MODE>;
+  constexpr bool kHalfOk = sizeof(T) == 2;
+  auto kfn = !bwd ? fused_fwd_kernel<T, CT, TPH, MODE>
+                  : (kHalfOk && f.acc_half ? fused_bwd_kernel<T, CT, TPH, MODE, kHalfOk>
+                                           : fused_bwd_kernel<T, CT, TPH, MODE, false>);
   cudaError_t e = cudaSuccess;
   if (smem > 48 * 1024)
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
