@@ -442,3 +442,109 @@ def test_row_sharded_encoder_matches_full_on_one_gpu():
     assert rel_err(got, full) <= 1e-5
     with pytest.raises(RuntimeError, match='prev_bev'):
         enc(bevq, feat, feat, row_shard=(0, 2), **dict(kw, prev_bev=None))
+
+
+# ------------------------------------------------------------------ more shapes / paths ----
+@pytest.mark.parametrize('C,heads,D,P', [(128, 8, 4, 8), (64, 8, 2, 4), (256, 8, 1, 4)])
+def test_sca_generic_head_dims_and_anchor_counts(C, heads, D, P):
+    """The shared SCA of the voxel / hybrid configs: Dh = 16 / 8, D = num_points_in_voxel other
+    than 4, bs = 2."""
+    from apollo_vision_net_b200.modules import SpatialCrossAttention
+    import apollo_vision_net_b200.synthetic as syn
+    levels = [(15, 25), (8, 13)]
+    cfg = dict(embed_dims=C, pc_range=syn.PC_RANGE, batch_first=True,
+               deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C, num_heads=heads,
+                                         num_points=P, num_levels=len(levels)))
+    o = OracleSpatialCrossAttention(**cfg)
+    _randomize(o, 1)
+    o.eval()
+    m = SpatialCrossAttention(**cfg)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).eval()
+    bs, H, W = 2, 18, 22
+    g = torch.Generator().manual_seed(13)
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs, jitter=4.0, seed=2)
+    r3 = G.reference_points_3d(H, W, 8.0, D, bs=bs)
+    uv, mask = G.point_sampling(r3, syn.PC_RANGE, l2i, img_shape[0], img_shape[1])
+    q = torch.randn(bs, H * W, C, generator=g)
+    feat = torch.randn(6, Nk, bs, C, generator=g)
+    go = torch.randn(bs, H * W, C, generator=g)
+    shapes, starts = torch.tensor(shapes_l), torch.tensor(starts_l)
+    q1, f1 = q.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    ref = o(q1, f1, f1, reference_points_cam=uv, bev_mask=mask, spatial_shapes=shapes,
+            level_start_index=starts)
+    ref.backward(go)
+    q2, f2 = q.to(DEV).requires_grad_(True), feat.to(DEV).requires_grad_(True)
+    out = m(q2, f2, f2, reference_points_cam=uv.to(DEV), bev_mask=mask.to(DEV),
+            spatial_shapes=shapes.to(DEV), level_start_index=starts.to(DEV), bev_h=H, bev_w=W)
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= FWD
+    assert rel_err(q2.grad, q1.grad) <= BWD
+    assert rel_err(f2.grad, f1.grad) <= BWD
+
+
+def test_decoder_box_reference_points_and_padding_mask():
+    """4-d (box) reference points and key_padding_mask: the operator path of decoder.py:301-333."""
+    from apollo_vision_net_b200.modules import CustomMSDeformableAttention
+    bs, H, W, C, Nq = 2, 12, 9, 256, 40
+    o = OracleCustomMSDeformableAttention(embed_dims=C, num_levels=1, attn_logits_clamp=2.0)
+    _randomize(o, 4)
+    o.eval()
+    m = CustomMSDeformableAttention(embed_dims=C, num_levels=1, attn_logits_clamp=2.0)
+    m.load_state_dict(o.state_dict())
+    m.to(DEV).eval()
+    g = torch.Generator().manual_seed(17)
+    q = torch.randn(Nq, bs, C, generator=g)
+    val = torch.randn(H * W, bs, C, generator=g)
+    rp = torch.rand(bs, Nq, 1, 4, generator=g) * 0.5 + 0.25
+    kpm = torch.rand(bs, H * W, generator=g) < 0.1
+    go = torch.randn(Nq, bs, C, generator=g)
+    kw = dict(spatial_shapes=torch.tensor([[H, W]]), level_start_index=torch.tensor([0]))
+    q1, v1 = q.clone().requires_grad_(True), val.clone().requires_grad_(True)
+    ref = o(q1, None, v1, reference_points=rp, key_padding_mask=kpm, **kw)
+    ref.backward(go)
+    q2, v2 = q.to(DEV).requires_grad_(True), val.to(DEV).requires_grad_(True)
+    out = m(q2, None, v2, reference_points=rp.to(DEV), key_padding_mask=kpm.to(DEV),
+            **{k: v.to(DEV) for k, v in kw.items()})
+    out.backward(go.to(DEV))
+    assert rel_err(out, ref) <= FWD
+    assert rel_err(q2.grad, q1.grad) <= BWD
+    assert rel_err(v2.grad, v1.grad) <= BWD
+
+
+def test_maptrv2_decoder_stack_runs_config4():
+    """MapTRv2Decoder (6 decoupled layers, 350 vectors x 20 points, one-to-many mask) built from
+    the reference's config fragment (bev_tiny_det_mapv2.py:33-63): runs forward + backward on the
+    fused cross-attention; checks shapes, finiteness and the refinement of the reference points."""
+    import apollo_vision_net_b200 as pkg
+    C, V, Pn, bs, H, W = 256, 350, 20, 1, 50, 50
+    dec = pkg.build_transformer_layer_sequence(dict(
+        type='MapTRv2Decoder', num_layers=6, return_intermediate=True,
+        transformerlayers=dict(
+            type='MapTRv2DecoupledDetrTransformerDecoderLayer', num_vec=V, num_pts_per_vec=Pn,
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_levels=1)],
+            feedforward_channels=512, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    _randomize(dec, 6)
+    dec.to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    query = torch.randn(V * Pn, bs, C, generator=g).to(DEV).requires_grad_(True)
+    qpos = torch.randn(V * Pn, bs, C, generator=g).to(DEV)
+    bev = torch.randn(H * W, bs, C, generator=g).to(DEV).requires_grad_(True)
+    refp = torch.rand(bs, V * Pn, 2, generator=g).to(DEV)
+    mask = torch.zeros(V, V, dtype=torch.bool, device=DEV)
+    mask[50:, :50] = True
+    mask[:50, 50:] = True                                     # one2one / one2many separation
+    reg = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(6)]).to(DEV)
+    inter, refs = dec(query, key=None, value=bev, query_pos=qpos, reference_points=refp,
+                      reg_branches=reg, spatial_shapes=torch.tensor([[H, W]], device=DEV),
+                      level_start_index=torch.tensor([0], device=DEV), self_attn_mask=mask,
+                      num_vec=V, num_pts_per_vec=Pn)
+    assert inter.shape == (6, V * Pn, bs, C) and refs.shape == (6, bs, V * Pn, 2)
+    assert torch.isfinite(inter).all() and (refs >= 0).all() and (refs <= 1).all()
+    inter[-1].float().pow(2).mean().backward()
+    assert torch.isfinite(bev.grad).all() and bev.grad.abs().sum() > 0
+    assert torch.isfinite(query.grad).all()
