@@ -84,18 +84,36 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int b = (int)(row / M / Nq);
 
   const int pix_stride = M * Dh;
-  const size_t voff = ((size_t)b * Nk * M + m) * Dh + chunk * VEC;
-  const T* vbase = value + voff;
-  float* gbase = g_value + voff;
   const CT* my_loc = STAGED ? (s_loc + (size_t)r_local * LP * 2) : (loc + row * LP * 2);
   const CT* my_att = STAGED ? (s_att + (size_t)r_local * LP) : (attn + row * LP);
 
-  float g[VEC];
+  constexpr int V2 = VEC / 2;
+  constexpr int SC = VEC / 4;
+  // Dot products use the natural channel ownership [VEC*chunk, VEC*(chunk+1)) of the 128-bit value
+  // loads; the grad_value scatter of a 16-bit value dtype uses [4c, 4c+4) and [4*TPH+4c, ...), so
+  // that the TPH lanes of a head cover 16*TPH contiguous bytes (whole sectors) per reduction.
+  float2 g[V2], gs[V2];
   {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 ug = active ? ldg128(grad_out + row * Dh + chunk * VEC) : z;
-    Vec16<T>::unpack(ug, g);
+    const T* grow_ptr = grad_out + row * Dh;
+    const uint4 ug = active ? ldg128(grow_ptr + chunk * VEC) : z;
+    Vec16<T>::unpack2(ug, g);
+    if (VEC == 4) {
+#pragma unroll
+      for (int i = 0; i < V2; ++i) gs[i] = g[i];
+    } else {
+      const T* lo = grow_ptr + 4 * chunk;
+      const T* hi = grow_ptr + 4 * TPH + 4 * chunk;
+      const bool ok = active;
+      gs[0] = ok ? make_float2(to_f32<T>(lo[0]), to_f32<T>(lo[1])) : make_float2(0.f, 0.f);
+      gs[1] = ok ? make_float2(to_f32<T>(lo[2]), to_f32<T>(lo[3])) : make_float2(0.f, 0.f);
+      gs[V2 - 2] = ok ? make_float2(to_f32<T>(hi[0]), to_f32<T>(hi[1])) : make_float2(0.f, 0.f);
+      gs[V2 - 1] = ok ? make_float2(to_f32<T>(hi[2]), to_f32<T>(hi[3])) : make_float2(0.f, 0.f);
+    }
   }
+  const size_t head_off = ((size_t)b * Nk * M + m) * Dh;
+  const T* vhead = value + head_off + chunk * VEC;
+  float* ghead = g_value + head_off + 4 * chunk;
 
   for (int l = 0; l < L; ++l) {
     const int H = lv.h[l], W = lv.w[l];
@@ -105,54 +123,54 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const int s = l * P + p;
       const float lx = to_f32<CT>(my_loc[2 * s]);
       const float ly = to_f32<CT>(my_loc[2 * s + 1]);
-      const float a = to_f32<CT>(my_att[s]);
-      const Bilinear bl = bilinear_setup(lx, ly, H, W);
-      const float hw = 1.f - bl.lw, hh = 1.f - bl.lh;
-      const long long o00 = (long long)loff + ((long long)bl.y0 * W + bl.x0) * pix_stride;
-      const long long o01 = o00 + pix_stride;
-      const long long o10 = o00 + (long long)W * pix_stride;
-      const long long o11 = o10 + pix_stride;
-      const bool c00 = active && bl.vy0 && bl.vx0, c01 = active && bl.vy0 && bl.vx1;
-      const bool c10 = active && bl.vy1 && bl.vx0, c11 = active && bl.vy1 && bl.vx1;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      const uint4 u00 = c00 ? ldg128(vbase + o00) : z;
-      const uint4 u01 = c01 ? ldg128(vbase + o01) : z;
-      const uint4 u10 = c10 ? ldg128(vbase + o10) : z;
-      const uint4 u11 = c11 ? ldg128(vbase + o11) : z;
-      const float w00 = hh * hw, w01 = hh * bl.lw, w10 = bl.lh * hw, w11 = bl.lh * bl.lw;
-
-      // grad_value: a * w_corner * grad_out, one 16-byte reduction per 4 channels
-      auto scatter = [&](bool ok, long long off, float w) {
-        if (!ok) return;
-        const float aw = a * w;
-        float* dst = gbase + off;
+      const float a = active ? to_f32<CT>(my_att[s]) : 0.f;
+      const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      const T* vb = vhead + loff;
+      float* gb = ghead + loff;
+      const uint4 u00 = ldg128(vb + c.o00);
+      const uint4 u01 = ldg128(vb + c.o01);
+      const uint4 u10 = ldg128(vb + c.o10);
+      const uint4 u11 = ldg128(vb + c.o11);
+      auto scatter = [&](int off, float cw) {
+        const float aw = a * cw;
+        if (aw == 0.f) return;                           // invalid corner, or a zero contribution
+        const float2 aw2 = splat2(aw);
+        float* dst = gb + off;
 #pragma unroll
-        for (int i = 0; i < VEC; i += 4)
-          red_add_f32x4(dst + i, aw * g[i], aw * g[i + 1], aw * g[i + 2], aw * g[i + 3]);
+        for (int k = 0; k < SC; ++k) {
+          const float2 p0 = fmul2(aw2, gs[2 * k]), p1 = fmul2(aw2, gs[2 * k + 1]);
+          red_add_f32x4(dst + k * 4 * TPH, p0.x, p0.y, p1.x, p1.y);
+        }
       };
-      scatter(c00, o00, w00);
-      scatter(c01, o01, w01);
-      scatter(c10, o10, w10);
-      scatter(c11, o11, w11);
-
-      float f[VEC];
-      float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-      Vec16<T>::unpack(u00, f);
+      scatter(c.o00, c.w00);
+      scatter(c.o01, c.w01);
+      scatter(c.o10, c.w10);
+      scatter(c.o11, c.w11);
+      float2 f[V2];
+      float2 d;
+      Vec16<T>::unpack2(u00, f);
+      d = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) d00 = fmaf(f[i], g[i], d00);
-      Vec16<T>::unpack(u01, f);
+      for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+      const float d00 = (c.valid & 1u) ? d.x + d.y : 0.f;
+      Vec16<T>::unpack2(u01, f);
+      d = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) d01 = fmaf(f[i], g[i], d01);
-      Vec16<T>::unpack(u10, f);
+      for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+      const float d01 = (c.valid & 2u) ? d.x + d.y : 0.f;
+      Vec16<T>::unpack2(u10, f);
+      d = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) d10 = fmaf(f[i], g[i], d10);
-      Vec16<T>::unpack(u11, f);
+      for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+      const float d10 = (c.valid & 4u) ? d.x + d.y : 0.f;
+      Vec16<T>::unpack2(u11, f);
+      d = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) d11 = fmaf(f[i], g[i], d11);
-
-      float ga = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
-      float gx = hh * (d01 - d00) + bl.lh * (d11 - d10);
-      float gy = hw * (d10 - d00) + bl.lw * (d11 - d01);
+      for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+      const float d11 = (c.valid & 8u) ? d.x + d.y : 0.f;
+      float ga = c.w00 * d00 + c.w01 * d01 + c.w10 * d10 + c.w11 * d11;
+      float gx = c.hh * (d01 - d00) + c.lh * (d11 - d10);
+      float gy = c.hw * (d10 - d00) + c.lw * (d11 - d01);
       ga = group_sum<TPH>(ga);
       gx = group_sum<TPH>(gx);
       gy = group_sum<TPH>(gy);

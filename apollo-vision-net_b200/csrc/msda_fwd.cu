@@ -78,9 +78,10 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const CT* my_loc = STAGED ? (s_loc + (size_t)r_local * LP * 2) : (loc + row * LP * 2);
   const CT* my_att = STAGED ? (s_att + (size_t)r_local * LP) : (attn + row * LP);
 
-  float acc[VEC];
+  constexpr int V2 = VEC / 2;
+  float2 acc2[V2];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (int i = 0; i < V2; ++i) acc2[i] = make_float2(0.f, 0.f);
 
   for (int l = 0; l < L; ++l) {
     const int H = lv.h[l], W = lv.w[l];
@@ -91,26 +92,34 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float lx = to_f32<CT>(my_loc[2 * s]);
       const float ly = to_f32<CT>(my_loc[2 * s + 1]);
       const float a = to_f32<CT>(my_att[s]);
-      const Bilinear bl = bilinear_setup(lx, ly, H, W);
-      const float hw = 1.f - bl.lw, hh = 1.f - bl.lh;
-      const T* p00 = lbase + ((long long)bl.y0 * W + bl.x0) * pix_stride;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      const uint4 u00 = (bl.vy0 && bl.vx0) ? ldg128(p00) : z;
-      const uint4 u01 = (bl.vy0 && bl.vx1) ? ldg128(p00 + pix_stride) : z;
-      const uint4 u10 = (bl.vy1 && bl.vx0) ? ldg128(p00 + (size_t)W * pix_stride) : z;
-      const uint4 u11 = (bl.vy1 && bl.vx1) ? ldg128(p00 + (size_t)(W + 1) * pix_stride) : z;
-      const float w00 = hh * hw, w01 = hh * bl.lw, w10 = bl.lh * hw, w11 = bl.lh * bl.lw;
-      float f00[VEC], f01[VEC], f10[VEC], f11[VEC];
-      Vec16<T>::unpack(u00, f00);
-      Vec16<T>::unpack(u01, f01);
-      Vec16<T>::unpack(u10, f10);
-      Vec16<T>::unpack(u11, f11);
+      // clamped corners: unpredicated 128-bit loads, weight zero for corners outside the map
+      const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      const uint4 u00 = ldg128(lbase + c.o00);
+      const uint4 u01 = ldg128(lbase + c.o01);
+      const uint4 u10 = ldg128(lbase + c.o10);
+      const uint4 u11 = ldg128(lbase + c.o11);
+      const float2 w00 = splat2(a * c.w00), w01 = splat2(a * c.w01);
+      const float2 w10 = splat2(a * c.w10), w11 = splat2(a * c.w11);
+      float2 f[V2];
+      Vec16<T>::unpack2(u00, f);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float v = w00 * f00[i] + w01 * f01[i] + w10 * f10[i] + w11 * f11[i];
-        acc[i] = fmaf(a, v, acc[i]);
-      }
+      for (int i = 0; i < V2; ++i) acc2[i] = ffma2(w00, f[i], acc2[i]);
+      Vec16<T>::unpack2(u01, f);
+#pragma unroll
+      for (int i = 0; i < V2; ++i) acc2[i] = ffma2(w01, f[i], acc2[i]);
+      Vec16<T>::unpack2(u10, f);
+#pragma unroll
+      for (int i = 0; i < V2; ++i) acc2[i] = ffma2(w10, f[i], acc2[i]);
+      Vec16<T>::unpack2(u11, f);
+#pragma unroll
+      for (int i = 0; i < V2; ++i) acc2[i] = ffma2(w11, f[i], acc2[i]);
     }
+  }
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < V2; ++i) {
+    acc[2 * i] = acc2[i].x;
+    acc[2 * i + 1] = acc2[i].y;
   }
   T* o = out + row * Dh + chunk * VEC;
   *reinterpret_cast<uint4*>(o) = Vec16<T>::pack(acc);
