@@ -224,6 +224,10 @@ fused_fwd_kernel(const FusedArgs a) {
   const int po = 2 * S + 4, pw = S + 4;                // padded row pitches (floats)
   float* s_off = reinterpret_cast<float*>(dyn_smem);   // [ROWS][po]
   float* s_w = s_off + (size_t)ROWS * po;              // [ROWS][pw]
+  // per-row exchange buffer: TPH sample records of 32 bytes (4 corner offsets + 4 weights), row
+  // pitch padded by 16 bytes so that the rows of a warp read conflict-free
+  constexpr int REC_PITCH = 8 * TPH + 4;               // in 4-byte words
+  uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_w + (size_t)ROWS * pw);
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
 
@@ -234,6 +238,8 @@ fused_fwd_kernel(const FusedArgs a) {
   const int r_slot = tid / TPH;
   float* my_off = s_off + (size_t)r_slot * po;
   float* my_w = s_w + (size_t)r_slot * pw;
+  uint32_t* my_rec = s_rec + (size_t)r_slot * REC_PITCH;
+  const unsigned gmask = (TPH >= 32) ? 0xffffffffu : (((1u << TPH) - 1u) << ((tid & 31) & ~(TPH - 1)));
   const int pix_stride = a.M * a.Dh;
   const size_t batch_stride = (size_t)a.Nk * pix_stride;
 
@@ -266,27 +272,46 @@ fused_fwd_kernel(const FusedArgs a) {
 #pragma unroll
         for (int i = 0; i < V2; ++i) acc[i] = make_float2(0.f, 0.f);
 
-        auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
-          const Corners c = corner_setup(lx, ly, H, W, pix_stride);
-          const uint4 u00 = ldg128(lbase + c.o00);
-          const uint4 u01 = ldg128(lbase + c.o01);
-          const uint4 u10 = ldg128(lbase + c.o10);
-          const uint4 u11 = ldg128(lbase + c.o11);
-          const float2 w00 = splat2(w * c.w00), w01 = splat2(w * c.w01);
-          const float2 w10 = splat2(w * c.w10), w11 = splat2(w * c.w11);
-          float2 f[V2];
-          Vec16<T>::unpack2(u00, f);
+        // Each of the row's TPH lanes sets up ONE sample of a block of TPH (corner offsets from
+        // the value-map base, weights = attention x bilinear, zero for corners outside the map),
+        // the lanes exchange the records through the row's shared buffer, and then every lane
+        // walks the block: 2 shared loads + 4 unpredicated 128-bit gathers + FFMA2 per sample.
+        auto accumulate_block = [&](const T* vbase_cam, int count) {
+          __syncwarp(gmask);          // the row's lanes only: rows of a warp may differ in trip count
 #pragma unroll
-          for (int i = 0; i < V2; ++i) acc[i] = ffma2(w00, f[i], acc[i]);
-          Vec16<T>::unpack2(u01, f);
+          for (int j = 0; j < TPH; ++j) {
+            if (j < count) {
+              const int4 o = *reinterpret_cast<const int4*>(my_rec + 8 * j);
+              const float4 wq = *reinterpret_cast<const float4*>(my_rec + 8 * j + 4);
+              const uint4 u00 = ldg128(vbase_cam + o.x);
+              const uint4 u01 = ldg128(vbase_cam + o.y);
+              const uint4 u10 = ldg128(vbase_cam + o.z);
+              const uint4 u11 = ldg128(vbase_cam + o.w);
+              const float2 w00 = splat2(wq.x), w01 = splat2(wq.y), w10 = splat2(wq.z), w11 = splat2(wq.w);
+              float2 f[V2];
+              Vec16<T>::unpack2(u00, f);
 #pragma unroll
-          for (int i = 0; i < V2; ++i) acc[i] = ffma2(w01, f[i], acc[i]);
-          Vec16<T>::unpack2(u10, f);
+              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w00, f[i], acc[i]);
+              Vec16<T>::unpack2(u01, f);
 #pragma unroll
-          for (int i = 0; i < V2; ++i) acc[i] = ffma2(w10, f[i], acc[i]);
-          Vec16<T>::unpack2(u11, f);
+              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w01, f[i], acc[i]);
+              Vec16<T>::unpack2(u10, f);
 #pragma unroll
-          for (int i = 0; i < V2; ++i) acc[i] = ffma2(w11, f[i], acc[i]);
+              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w10, f[i], acc[i]);
+              Vec16<T>::unpack2(u11, f);
+#pragma unroll
+              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w11, f[i], acc[i]);
+            }
+          }
+          __syncwarp(gmask);
+        };
+        auto write_record = [&](int l, float lx, float ly, float w) {
+          const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
+          const int base = lv.t.start[l] * pix_stride;
+          *reinterpret_cast<int4*>(my_rec + 8 * chunk) =
+              make_int4(base + c.o00, base + c.o01, base + c.o10, base + c.o11);
+          *reinterpret_cast<float4*>(my_rec + 8 * chunk + 4) =
+              make_float4(w * c.w00, w * c.w01, w * c.w10, w * c.w11);
         };
 
         if (MODE == MODE_SCA) {
@@ -296,21 +321,43 @@ fused_fwd_kernel(const FusedArgs a) {
             const float2* rc = reinterpret_cast<const float2*>(
                 a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
             const T* vcam = vhead + ((size_t)b * a.groups + cam) * batch_stride;
-            for (int l = 0; l < a.L; ++l) {
-              const int H = lv.t.h[l], W = lv.t.w[l];
-              const T* lbase = vcam + (size_t)lv.t.start[l] * pix_stride;
-              int z = 0;                                             // point index p = k*D + z (quirk 5)
-#pragma unroll 4
-              for (int p = 0; p < a.P; ++p) {
-                const int s = l * a.P + p;
+            for (int s0 = 0; s0 < LP; s0 += TPH) {
+              const int s = s0 + chunk;
+              if (s < LP) {
+                const int l = s / a.P;
+                const int z = (s - l * a.P) % a.D;                   // point index p = k*D + z (quirk 5)
                 const float2 r = __ldg(rc + z);
-                z = (z + 1 == a.D) ? 0 : z + 1;
                 const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-                sample(lbase, H, W, r.x + o.x, r.y + o.y, my_w[s]);
+                write_record(l, r.x + o.x, r.y + o.y, my_w[s]);
               }
+              accumulate_block(vcam, min(TPH, LP - s0));
             }
           }
         } else {
+          // short rows (4-8 samples per queue entry): every lane sets up its own samples, the
+          // exchange would cost more than it saves
+          auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
+            const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+            const uint4 u00 = ldg128(lbase + c.o00);
+            const uint4 u01 = ldg128(lbase + c.o01);
+            const uint4 u10 = ldg128(lbase + c.o10);
+            const uint4 u11 = ldg128(lbase + c.o11);
+            const float2 w00 = splat2(w * c.w00), w01 = splat2(w * c.w01);
+            const float2 w10 = splat2(w * c.w10), w11 = splat2(w * c.w11);
+            float2 f[V2];
+            Vec16<T>::unpack2(u00, f);
+#pragma unroll
+            for (int i = 0; i < V2; ++i) acc[i] = ffma2(w00, f[i], acc[i]);
+            Vec16<T>::unpack2(u01, f);
+#pragma unroll
+            for (int i = 0; i < V2; ++i) acc[i] = ffma2(w01, f[i], acc[i]);
+            Vec16<T>::unpack2(u10, f);
+#pragma unroll
+            for (int i = 0; i < V2; ++i) acc[i] = ffma2(w10, f[i], acc[i]);
+            Vec16<T>::unpack2(u11, f);
+#pragma unroll
+            for (int i = 0; i < V2; ++i) acc[i] = ffma2(w11, f[i], acc[i]);
+          };
           for (int j = 0; j < a.groups; ++j) {
             const T* vb = vhead + ((size_t)b * a.groups + j) * batch_stride;
             for (int l = 0; l < a.L; ++l) {
@@ -667,7 +714,8 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   a.vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.g_offsets) | reinterpret_cast<uintptr_t>(f.g_logits)) % 16 == 0);
   if ((reinterpret_cast<uintptr_t>(f.offsets) % 16) != 0 || (reinterpret_cast<uintptr_t>(f.logits) % 16) != 0)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets / logits must be 16-byte aligned", what);
-  const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float);
+  const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float) +
+                      (bwd ? 0 : (size_t)ROWS * (8 * TPH + 4) * sizeof(uint32_t));
   if (smem > 200 * 1024)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: %d samples per row need %zu bytes of shared memory", what, S, smem);
   constexpr bool kHalfOk = sizeof(T) == 2;
