@@ -90,7 +90,7 @@ def host_inputs(bev_h, bev_w, levels, seed, dtype, pin):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed regions run."""
     FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
@@ -102,7 +102,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                 '--format=csv,noheader,nounits', '-lms', '100'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -225,6 +225,8 @@ def run_b200(args):
     # Per-kernel durations for the roofline object: the same step run eagerly (a replayed graph
     # cannot carry timing events), K steps, CUDA events on the launching stream around each of our
     # launches, L2 flushed every step exactly as in the graph-replay timed region below.
+    clocks = ClockSampler(local)
+    clocks.__enter__()                             # sampled over every timed region below
     timer = _lib.KernelTimer()
     launches0 = _lib.launch_count()
     _lib.set_timer(timer)
@@ -330,14 +332,14 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step_device()
-    with ClockSampler(local) as clocks:
-        ms = timed(step_device, args.steps)
+    ms = timed(step_device, args.steps)
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     torch.cuda.synchronize()
     pipe['primed'] = False                         # the timed region starts with an empty pipeline
     pipe['left'] = args.steps                      # ... and issues exactly `steps` H2D copies
     ms_e2e = timed(step_e2e, args.steps)
+    clocks.__exit__(None, None, None)
 
     ms_per_step = ms / args.steps
     value = world * points_per_step * args.steps / (ms / 1e3)
@@ -417,6 +419,80 @@ def run_b200(args):
             'clocks': clocks.summary(),
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ BEV row sharding ------
+def run_rowshard(args):
+    """BASELINE configs[4]: encoder FORWARD at a 400x400 BEV with the BEV query rows sharded over the
+    ranks (value maps replicated, one NCCL all-gather of the rows at encoder exit).  Strong
+    scaling: the frame is fixed, N ranks split its rows.  Not the contract line (that is the
+    default workload); run it with --workload rowshard."""
+    import torch.distributed as dist
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    from apollo_vision_net_b200 import _lib
+    from apollo_vision_net_b200.parallel import all_gather_bev_rows
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    pkg.build()
+    dtype = torch.bfloat16
+    bev = args.bev if args.bev != 200 else 400
+    levels = syn.LEVELS_BASE
+    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE))
+    randomize(enc, 0)
+    enc.to(dev).to(dtype).eval()
+    l2i, img_shape = syn.camera_rig(1.0, bs=1)
+    l2i_dev = torch.as_tensor(l2i).to(dev)
+    host = host_inputs(bev, bev, levels, seed=1, dtype=dtype, pin=False)   # same frame on every rank
+    d = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        flush.zero_()
+        with torch.no_grad():
+            out = enc(d['bev_query'], d['feat'], d['feat'], bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
+                      spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
+                      shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape,
+                      row_shard=(rank, world) if world > 1 else None)
+            if world > 1:
+                out = all_gather_bev_rows(out, bev, bev)
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    s.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'BEVFormer encoder forward frames/s, BEV-query-row sharded', 'value': args.steps / (float(ms) / 1e3),
+            'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': float(ms) / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'BEVFormer-base encoder forward, {bev}x{bev} BEV, 6 cams, 4 levels, '
+                                   f'{args.layers} layers, rows sharded over {world} rank(s), value maps '
+                                   'replicated, one all-gather at exit (BASELINE configs[4])'},
+            'gpu_launches': _lib.launch_count() - launches0}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -504,12 +580,16 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--bev', type=int, default=200)
     ap.add_argument('--layers', type=int, default=6)
+    ap.add_argument('--workload', default='encoder', choices=['encoder', 'rowshard'],
+                    help="'encoder' (default, the contract line) or 'rowshard' (400x400 forward, strong scaling)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         args.steps = min(args.steps, 3)
         run_reference(args)
+    elif args.workload == 'rowshard':
+        run_rowshard(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_b200(args)
