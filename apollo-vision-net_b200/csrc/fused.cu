@@ -410,6 +410,8 @@ fused_bwd_kernel(const FusedArgs a) {
   float* s_w = s_off + (size_t)ROWS * po;              // [ROWS][pw] softmax weights
   float* s_go = s_w + (size_t)ROWS * pw;               // [ROWS][po] grad wrt raw offsets
   float* s_ga = s_go + (size_t)ROWS * po;              // [ROWS][pw] grad wrt weights -> logits
+  constexpr int REC_PITCH = 8 * TPH + 4;               // per-row exchange buffer, in 4-byte words
+  uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_ga + (size_t)ROWS * pw);
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
 
@@ -422,6 +424,7 @@ fused_bwd_kernel(const FusedArgs a) {
   float* my_w = s_w + (size_t)r_slot * pw;
   float* my_go = s_go + (size_t)r_slot * po;
   float* my_ga = s_ga + (size_t)r_slot * pw;
+  uint32_t* my_rec = s_rec + (size_t)r_slot * REC_PITCH;
   const int pix_stride = a.M * a.Dh;
   const size_t batch_stride = (size_t)a.Nk * pix_stride;
 
@@ -499,16 +502,19 @@ fused_bwd_kernel(const FusedArgs a) {
         for (int k = 0; k < 4; ++k) gh[k] = __floats2half2_rn(g[k % V2].x * acc_scale, g[k % V2].y * acc_scale);
       }
 
-      // One sample against one value map: scatters grad_value, accumulates the row's location /
-      // weight gradients in the shared row (one writer per (row, sample)).
-      auto sample = [&](size_t boff, int H, int W, float lx, float ly, float w, int s, bool mine) {
-        const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      // Core of one sample against one value map, from its corner set-up: gathers the four
+      // corners, scatters grad_value, returns this lane's partial (d out / d weight, d/dx, d/dy).
+      auto core = [&](size_t boff, int o00, int o01, int o10, int o11, float lw, float lh,
+                      unsigned valid, float w, float& ga, float& gx, float& gy) {
+        const float hw = 1.f - lw, hh = 1.f - lh;
+        const float w00 = (valid & 1u) ? hh * hw : 0.f, w01 = (valid & 2u) ? hh * lw : 0.f;
+        const float w10 = (valid & 4u) ? lh * hw : 0.f, w11 = (valid & 8u) ? lh * lw : 0.f;
         const T* vb = vhead + boff;
         float* gb = ghead + boff;
-        const uint4 u00 = ldg128(vb + c.o00);
-        const uint4 u01 = ldg128(vb + c.o01);
-        const uint4 u10 = ldg128(vb + c.o10);
-        const uint4 u11 = ldg128(vb + c.o11);
+        const uint4 u00 = ldg128(vb + o00);
+        const uint4 u01 = ldg128(vb + o01);
+        const uint4 u10 = ldg128(vb + o10);
+        const uint4 u11 = ldg128(vb + o11);
         auto scatter = [&](int off, float cw) {
           const float aw = w * cw;
           if (aw == 0.f || (a.debug & 1)) return;        // invalid corner, or a zero contribution
@@ -532,50 +538,43 @@ fused_bwd_kernel(const FusedArgs a) {
             red_add_f32x4(dst + k * 4 * TPH, p0.x, p0.y, p1.x, p1.y);
           }
         };
-        scatter(c.o00, c.w00);
-        scatter(c.o01, c.w01);
-        scatter(c.o10, c.w10);
-        scatter(c.o11, c.w11);
+        scatter(o00, w00);
+        scatter(o01, w01);
+        scatter(o10, w10);
+        scatter(o11, w11);
         float2 f[V2];
         float2 d;
         Vec16<T>::unpack2(u00, f);
         d = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d00 = (c.valid & 1u) ? d.x + d.y : 0.f;
+        const float d00 = (valid & 1u) ? d.x + d.y : 0.f;
         Vec16<T>::unpack2(u01, f);
         d = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d01 = (c.valid & 2u) ? d.x + d.y : 0.f;
+        const float d01 = (valid & 2u) ? d.x + d.y : 0.f;
         Vec16<T>::unpack2(u10, f);
         d = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d10 = (c.valid & 4u) ? d.x + d.y : 0.f;
+        const float d10 = (valid & 4u) ? d.x + d.y : 0.f;
         Vec16<T>::unpack2(u11, f);
         d = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d11 = (c.valid & 8u) ? d.x + d.y : 0.f;
-        float ga = c.w00 * d00 + c.w01 * d01 + c.w10 * d10 + c.w11 * d11;
-        float gx = c.hh * (d01 - d00) + c.lh * (d11 - d10);
-        float gy = c.hw * (d10 - d00) + c.lw * (d11 - d01);
-        ga = group_sum<TPH>(ga);
-        gx = group_sum<TPH>(gx);
-        gy = group_sum<TPH>(gy);
-        if (chunk == 0 && mine) {
-          // d loc / d offset = 1 / (W_l, H_l) cancels the (W_l, H_l) factor of d pixel / d loc
-          my_ga[s] += ga;
-          float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
-          float2 cur = *go2;
-          cur.x += w * gx;
-          cur.y += w * gy;
-          *go2 = cur;
-        }
+        const float d11 = (valid & 8u) ? d.x + d.y : 0.f;
+        ga = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+        gx = hh * (d01 - d00) + lh * (d11 - d10);
+        gy = hw * (d10 - d00) + lw * (d11 - d01);
       };
 
       if (MODE == MODE_SCA) {
+        // Blocks of TPH samples: lane c sets up sample s0 + c and publishes its record (corner
+        // offsets, fractions, validity, attention weight) in the row's exchange buffer; every lane
+        // then walks the block; after the lane sums, lane c owns the totals of sample s0 + c and
+        // adds them to the row's accumulators (d loc / d offset = 1 / (W_l, H_l) cancels the
+        // (W_l, H_l) factor of d pixel / d loc).
         uint32_t warp_hits = __reduce_or_sync(0xffffffffu, hits);
         while (warp_hits) {
           const int cam = __ffs(warp_hits) - 1;
@@ -584,18 +583,51 @@ fused_bwd_kernel(const FusedArgs a) {
           const float2* rc = reinterpret_cast<const float2*>(
               a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
           const size_t coff = ((size_t)b * a.groups + cam) * batch_stride;
-          for (int l = 0; l < a.L; ++l) {
-            const int H = lv.t.h[l], W = lv.t.w[l];
-            const size_t loff = coff + (size_t)lv.t.start[l] * pix_stride;
-            int z = 0;
-FUSED_UNROLL(FUSED_BWD_UNROLL)
-            for (int p = 0; p < a.P; ++p) {
-              const int s = l * a.P + p;
-              const float2 r = __ldg(rc + z);
-              z = (z + 1 == a.D) ? 0 : z + 1;
-              const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-              sample(loff, H, W, r.x + o.x, r.y + o.y, mine ? my_w[s] : 0.f, s, mine);
+          for (int s0 = 0; s0 < LP; s0 += TPH) {
+            const int s = s0 + chunk;
+            float my_wgt = 0.f;
+            {
+              int4 ro = make_int4(0, 0, 0, 0);
+              float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (s < LP) {
+                const int l = s / a.P;
+                const int z = (s - l * a.P) % a.D;                   // point index p = k*D + z (quirk 5)
+                const float2 r = __ldg(rc + z);
+                const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
+                const Corners c = corner_setup(r.x + o.x, r.y + o.y, lv.t.h[l], lv.t.w[l], pix_stride);
+                const int base = lv.t.start[l] * pix_stride;
+                my_wgt = mine ? my_w[s] : 0.f;
+                ro = make_int4(base + c.o00, base + c.o01, base + c.o10, base + c.o11);
+                rf = make_float4(c.lw, c.lh, __uint_as_float(c.valid), my_wgt);
+              }
+              *reinterpret_cast<int4*>(my_rec + 8 * chunk) = ro;
+              *reinterpret_cast<float4*>(my_rec + 8 * chunk + 4) = rf;
             }
+            __syncwarp();
+            float tga = 0.f, tgx = 0.f, tgy = 0.f;
+            const int count = min(TPH, LP - s0);
+FUSED_UNROLL(FUSED_BWD_UNROLL)
+            for (int j = 0; j < TPH; ++j) {
+              if (j < count) {
+                const int4 ro = *reinterpret_cast<const int4*>(my_rec + 8 * j);
+                const float4 rf = *reinterpret_cast<const float4*>(my_rec + 8 * j + 4);
+                float ga, gx, gy;
+                core(coff, ro.x, ro.y, ro.z, ro.w, rf.x, rf.y, __float_as_uint(rf.z), rf.w, ga, gx, gy);
+                ga = group_sum<TPH>(ga);
+                gx = group_sum<TPH>(gx);
+                gy = group_sum<TPH>(gy);
+                if (j == chunk) { tga = ga; tgx = gx; tgy = gy; }
+              }
+            }
+            if (s < LP && mine) {
+              my_ga[s] += tga;
+              float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
+              float2 cur = *go2;
+              cur.x += my_wgt * tgx;
+              cur.y += my_wgt * tgy;
+              *go2 = cur;
+            }
+            __syncwarp();
           }
         }
       } else {
@@ -610,7 +642,21 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
             for (int p = 0; p < a.P; ++p) {
               const int s = (j * a.L + l) * a.P + p;
               const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-              sample(loff, H, W, r.x + o.x, r.y + o.y, live ? my_w[s] : 0.f, s, live);
+              const float w = live ? my_w[s] : 0.f;
+              const Corners c = corner_setup(r.x + o.x, r.y + o.y, H, W, pix_stride);
+              float ga, gx, gy;
+              core(loff, c.o00, c.o01, c.o10, c.o11, c.lw, c.lh, c.valid, w, ga, gx, gy);
+              ga = group_sum<TPH>(ga);
+              gx = group_sum<TPH>(gx);
+              gy = group_sum<TPH>(gy);
+              if (chunk == 0 && live) {
+                my_ga[s] += ga;
+                float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
+                float2 cur = *go2;
+                cur.x += w * gx;
+                cur.y += w * gy;
+                *go2 = cur;
+              }
             }
           }
         }
@@ -715,7 +761,7 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   if ((reinterpret_cast<uintptr_t>(f.offsets) % 16) != 0 || (reinterpret_cast<uintptr_t>(f.logits) % 16) != 0)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets / logits must be 16-byte aligned", what);
   const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float) +
-                      (bwd ? 0 : (size_t)ROWS * (8 * TPH + 4) * sizeof(uint32_t));
+                      (size_t)ROWS * (8 * TPH + 4) * sizeof(uint32_t);
   if (smem > 200 * 1024)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: %d samples per row need %zu bytes of shared memory", what, S, smem);
   constexpr bool kHalfOk = sizeof(T) == 2;
