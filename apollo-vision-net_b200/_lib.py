@@ -11,7 +11,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
-LIB_PATH = os.path.join(_HERE, 'libmsda_b200.so')
+# APOLLO_B200_LIB: load another build of the same ABI (kernel experiments, tools/dev_variants.sh)
+LIB_PATH = os.environ.get('APOLLO_B200_LIB') or os.path.join(_HERE, 'libmsda_b200.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
 SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'rowops.cu']
 
@@ -32,10 +33,10 @@ _SIGNATURES = {
     'msda_fwd_host': (_c_int, [_c_vp] * 6 + [_c_int] * 9 + [_c_vp, _c_i64, _c_vp]),
     'msda_fwd_bwd_host': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_vp, _c_i64, _c_vp]),
     'bev_point_sampling': (_c_int, [_c_vp] * 3 + [_c_f, _c_f] + [_c_int] * 4 + [_c_vp] * 6),
-    'sca_fwd': (_c_int, [_c_vp] * 10 + [_c_int] * 12 + [_c_vp]),
-    'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 13 + [_c_vp, _c_vp]),
-    'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_vp]),
-    'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_int, _c_vp, _c_vp]),
+    'sca_fwd': (_c_int, [_c_vp] * 10 + [_c_int] * 12 + [_c_i64, _c_i64, _c_vp]),
+    'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 12 + [_c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
+    'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_vp]),
+    'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
     'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp]),
     'unscale_cast': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp]),
     'rowops_workspace_rows': (_c_int, []),

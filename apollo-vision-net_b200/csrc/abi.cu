@@ -78,6 +78,12 @@ static int validate_fused(const FusedProblem& f, bool bwd, bool sca, const char*
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: at most 32 cameras (got %d)", fn, f.groups);
   if ((long long)f.Nk * f.M * f.Dh >= 0x7fffffffLL)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: Nk*M*Dh must be < 2^31", fn);
+  {
+    // per-query row lengths of the offsets / logits tensors; a stride of 0 means dense
+    const long long per_q = (long long)f.M * (sca ? 1 : f.groups) * f.L * f.P;
+    if ((f.off_stride != 0 && f.off_stride < 2 * per_q) || (f.log_stride != 0 && f.log_stride < per_q))
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets / logits stride shorter than a row", fn);
+  }
   if ((long long)f.bs * f.Nq == 0) return MSDA_OK;
   if (!f.value || !f.shapes || !f.starts || !f.offsets || !f.logits || !f.ref)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: NULL input pointer", fn);
@@ -248,8 +254,10 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
 int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
             const void* logits, const float* ref_cam, const uint8_t* bev_mask,
             const uint32_t* hit_bits, void* slots, float* attn_out, int bs, int num_cam, int Nk,
-            int M, int Dh, int L, int P, int D, int HW, int bev_w, int value_dtype, int coord_dtype, void* stream) {
+            int M, int Dh, int L, int P, int D, int HW, int bev_w, int value_dtype, int coord_dtype,
+            int64_t offsets_stride, int64_t logits_stride, void* stream) {
   FusedProblem f;
+  f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.out = slots; f.attn_out = attn_out;
   f.bs = bs; f.groups = num_cam; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.D = D;
@@ -263,9 +271,10 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
             const void* logits, const float* ref_cam, const uint8_t* bev_mask,
             const uint32_t* hit_bits, const void* g_slots, void* g_value, void* g_offsets,
             void* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
-            void* stream) {
+            int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride, int64_t logits_stride,
+            int accum_dtype, const float* accum_scale, void* stream) {
   FusedProblem f;
+  f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.g_out = g_slots;
@@ -279,8 +288,10 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
             const void* logits, const float* ref, void* out, int bs, int Q, int Nk, int M, int Dh,
-            int L, int P, int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, void* stream) {
+            int L, int P, int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype,
+            int64_t offsets_stride, int64_t logits_stride, void* stream) {
   FusedProblem f;
+  f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.out = out;
   f.bs = bs; f.groups = Q; f.Nk = Nk; f.M = M; f.Dh = Dh; f.L = L; f.P = P; f.Nq = Nq;
@@ -293,9 +304,10 @@ int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, con
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,
             const void* logits, const float* ref, const void* g_out, void* g_value,
             void* g_offsets, void* g_logits, int bs, int Q, int Nk, int M, int Dh, int L, int P,
-            int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, int accum_dtype,
-            const float* accum_scale, void* stream) {
+            int Nq, int bev_w, float clamp, int value_dtype, int coord_dtype, int64_t offsets_stride,
+            int64_t logits_stride, int accum_dtype, const float* accum_scale, void* stream) {
   FusedProblem f;
+  f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref; f.g_out = g_out; f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;

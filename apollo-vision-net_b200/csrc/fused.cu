@@ -34,6 +34,9 @@ constexpr int kFusedThreads = 256;
 #ifndef FUSED_BWD_UNROLL
 #define FUSED_BWD_UNROLL 2
 #endif
+#ifndef FUSED_FWD_MINBLOCKS
+#define FUSED_FWD_MINBLOCKS 4
+#endif
 #ifndef FUSED_BWD_MINBLOCKS
 #define FUSED_BWD_MINBLOCKS 3
 #endif
@@ -86,6 +89,7 @@ struct FusedArgs {
   int tiles_per_sample;
   long long num_tiles;         // bs * tiles_per_sample
   int vec_ok;                  // rows can be written with 16-byte stores
+  long long off_stride, log_stride;   // elements between the rows of consecutive queries
   int debug;                   // MSDA_DEBUG experiment switches (0 in production)
 };
 
@@ -147,17 +151,17 @@ template <> __device__ __forceinline__ void store_coord4<__half>(__half* dst, co
 template <int TPH, typename CT>
 __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels& lv, bool live,
                                           const CT* __restrict__ g_off, const CT* __restrict__ g_log,
-                                          float* so, float* sw, int chunk, int S, int LP) {
+                                          float* so, float* sw, int chunk, int S, int LP,
+                                          const uint32_t* s_meta) {
   // offsets: lane handles samples chunk, chunk + TPH, ... (8 contiguous bytes each)
   if (live) {
-    int sl = chunk;                       // sample index modulo LP
-    while (sl >= LP) sl -= LP;
-    for (int s = chunk; s < S; s += TPH) {
-      const int l = sl / a.P;
-      const float2 o = load_coord2<CT>(g_off + 2 * s);
-      *reinterpret_cast<float2*>(so + 2 * s) = make_float2(o.x * lv.inv_w[l], o.y * lv.inv_h[l]);
-      sl += TPH;
-      while (sl >= LP) sl -= LP;
+    for (int base = 0; base < S; base += a.P) {       // one level of one segment at a time
+      const int l = (int)(s_meta[base] & 0xffffu);
+      const float iw = lv.inv_w[l], ih = lv.inv_h[l];
+      for (int s = base + chunk; s < base + a.P; s += TPH) {
+        const float2 o = load_coord2<CT>(g_off + 2 * s);
+        *reinterpret_cast<float2*>(so + 2 * s) = make_float2(o.x * iw, o.y * ih);
+      }
     }
   }
   // softmax
@@ -212,7 +216,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
 }
 
 template <typename T, typename CT, int TPH, int MODE>
-__global__ void __launch_bounds__(kFusedThreads)
+__global__ void __launch_bounds__(kFusedThreads, FUSED_FWD_MINBLOCKS)
 fused_fwd_kernel(const FusedArgs a) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int V2 = VEC / 2;
@@ -228,10 +232,17 @@ fused_fwd_kernel(const FusedArgs a) {
   // pitch padded by 16 bytes so that the rows of a warp read conflict-free
   constexpr int REC_PITCH = 8 * TPH + 4;               // in 4-byte words
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_w + (size_t)ROWS * pw);
+  // per-sample (level | anchor << 16); the anchor follows the SCA point ordering p = k*D + z
+  // (quirk 5).  Keeps the integer divisions out of the sample loops.
+  uint32_t* s_meta = s_rec + (size_t)ROWS * REC_PITCH;
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
 
   load_fused_levels(lv, a);
+  for (int i = tid; i < S; i += kFusedThreads) {
+    const int sl = i % LP, l = sl / a.P;
+    s_meta[i] = (uint32_t)l | ((uint32_t)((sl - l * a.P) % a.D) << 16);
+  }
   __syncthreads();
 
   const int chunk = tid % TPH;
@@ -239,7 +250,6 @@ fused_fwd_kernel(const FusedArgs a) {
   float* my_off = s_off + (size_t)r_slot * po;
   float* my_w = s_w + (size_t)r_slot * pw;
   uint32_t* my_rec = s_rec + (size_t)r_slot * REC_PITCH;
-  const unsigned gmask = (TPH >= 32) ? 0xffffffffu : (((1u << TPH) - 1u) << ((tid & 31) & ~(TPH - 1)));
   const int pix_stride = a.M * a.Dh;
   const size_t batch_stride = (size_t)a.Nk * pix_stride;
 
@@ -263,87 +273,34 @@ fused_fwd_kernel(const FusedArgs a) {
       const bool work = live && (MODE == MODE_TSA || hits != 0);
       const long long grow = ((long long)b * a.Nq + q) * a.M + m;
       __syncwarp();                                                   // previous row's readers are done
-      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + grow * S * 2,
-                         static_cast<const CT*>(a.logits) + grow * S, my_off, my_w, chunk, S, LP);
+      const long long qrow = (long long)b * a.Nq + q;
+      const long long off_at = qrow * a.off_stride + (long long)m * S * 2;
+      const long long log_at = qrow * a.log_stride + (long long)m * S;
+      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + off_at,
+                         static_cast<const CT*>(a.logits) + log_at, my_off, my_w, chunk, S, LP, s_meta);
 
-      if (live) {
+      {
         const T* vhead = static_cast<const T*>(a.value) + (size_t)m * a.Dh + chunk * VEC;
+        constexpr bool MIXED = sizeof(T) == 2;   // 16-bit value: FHFMA straight from the loaded words
         float2 acc[V2];
+        float accm[8];
 #pragma unroll
         for (int i = 0; i < V2; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) accm[i] = 0.f;
 
-        // Each of the row's TPH lanes sets up ONE sample of a block of TPH (corner offsets from
-        // the value-map base, weights = attention x bilinear, zero for corners outside the map),
-        // the lanes exchange the records through the row's shared buffer, and then every lane
-        // walks the block: 2 shared loads + 4 unpredicated 128-bit gathers + FFMA2 per sample.
-        auto accumulate_block = [&](const T* vbase_cam, int count) {
-          __syncwarp(gmask);          // the row's lanes only: rows of a warp may differ in trip count
-#pragma unroll
-          for (int j = 0; j < TPH; ++j) {
-            if (j < count) {
-              const int4 o = *reinterpret_cast<const int4*>(my_rec + 8 * j);
-              const float4 wq = *reinterpret_cast<const float4*>(my_rec + 8 * j + 4);
-              const uint4 u00 = ldg128(vbase_cam + o.x);
-              const uint4 u01 = ldg128(vbase_cam + o.y);
-              const uint4 u10 = ldg128(vbase_cam + o.z);
-              const uint4 u11 = ldg128(vbase_cam + o.w);
-              const float2 w00 = splat2(wq.x), w01 = splat2(wq.y), w10 = splat2(wq.z), w11 = splat2(wq.w);
-              float2 f[V2];
-              Vec16<T>::unpack2(u00, f);
-#pragma unroll
-              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w00, f[i], acc[i]);
-              Vec16<T>::unpack2(u01, f);
-#pragma unroll
-              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w01, f[i], acc[i]);
-              Vec16<T>::unpack2(u10, f);
-#pragma unroll
-              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w10, f[i], acc[i]);
-              Vec16<T>::unpack2(u11, f);
-#pragma unroll
-              for (int i = 0; i < V2; ++i) acc[i] = ffma2(w11, f[i], acc[i]);
-            }
-          }
-          __syncwarp(gmask);
-        };
-        auto write_record = [&](int l, float lx, float ly, float w) {
-          const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
-          const int base = lv.t.start[l] * pix_stride;
-          *reinterpret_cast<int4*>(my_rec + 8 * chunk) =
-              make_int4(base + c.o00, base + c.o01, base + c.o10, base + c.o11);
-          *reinterpret_cast<float4*>(my_rec + 8 * chunk + 4) =
-              make_float4(w * c.w00, w * c.w01, w * c.w10, w * c.w11);
-        };
-
-        if (MODE == MODE_SCA) {
-          while (hits) {
-            const int cam = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const float2* rc = reinterpret_cast<const float2*>(
-                a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
-            const T* vcam = vhead + ((size_t)b * a.groups + cam) * batch_stride;
-            for (int s0 = 0; s0 < LP; s0 += TPH) {
-              const int s = s0 + chunk;
-              if (s < LP) {
-                const int l = s / a.P;
-                const int z = (s - l * a.P) % a.D;                   // point index p = k*D + z (quirk 5)
-                const float2 r = __ldg(rc + z);
-                const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-                write_record(l, r.x + o.x, r.y + o.y, my_w[s]);
-              }
-              accumulate_block(vcam, min(TPH, LP - s0));
-            }
-          }
-        } else {
-          // short rows (4-8 samples per queue entry): every lane sets up its own samples, the
-          // exchange would cost more than it saves
-          auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
-            const Corners c = corner_setup(lx, ly, H, W, pix_stride);
-            const uint4 u00 = ldg128(lbase + c.o00);
-            const uint4 u01 = ldg128(lbase + c.o01);
-            const uint4 u10 = ldg128(lbase + c.o10);
-            const uint4 u11 = ldg128(lbase + c.o11);
-            const float2 w00 = splat2(w * c.w00), w01 = splat2(w * c.w01);
-            const float2 w10 = splat2(w * c.w10), w11 = splat2(w * c.w11);
+        // a * bilinear weights against the four gathered corners.  fp32 value: FFMA2 with fp32
+        // weights.  16-bit value: the weights are rounded to the value dtype (wa = w00|w01,
+        // wb = w10|w11 packed), products are exact, accumulation is fp32.
+        auto blend = [&](const uint4& u00, const uint4& u01, const uint4& u10, const uint4& u11,
+                         float w00f, float w01f, float w10f, float w11f, uint32_t wa, uint32_t wb) {
+          if constexpr (MIXED) {
+            axpy_mixed<T>(u00, lo16(wa), accm);
+            axpy_mixed<T>(u01, hi16(wa), accm);
+            axpy_mixed<T>(u10, lo16(wb), accm);
+            axpy_mixed<T>(u11, hi16(wb), accm);
+          } else {
+            const float2 w00 = splat2(w00f), w01 = splat2(w01f), w10 = splat2(w10f), w11 = splat2(w11f);
             float2 f[V2];
             Vec16<T>::unpack2(u00, f);
 #pragma unroll
@@ -357,6 +314,88 @@ fused_fwd_kernel(const FusedArgs a) {
             Vec16<T>::unpack2(u11, f);
 #pragma unroll
             for (int i = 0; i < V2; ++i) acc[i] = ffma2(w11, f[i], acc[i]);
+          }
+        };
+
+        // Each of the row's TPH lanes sets up ONE sample of a block of TPH (corner BYTE offsets
+        // from the camera's value slab, weights = attention x bilinear, zero for corners outside
+        // the map), the lanes exchange the records through the row's shared buffer, and then
+        // every lane walks the block: 2 shared loads + 4 unpredicated 128-bit gathers per sample.
+        auto accumulate_block = [&](const T* vbase_cam, int count, bool mine) {
+          const char* vb = reinterpret_cast<const char*>(vbase_cam);
+          __syncwarp();               // the camera loop is warp-uniform (rows not hit idle through it)
+#pragma unroll
+          for (int j = 0; j < TPH; ++j) {
+            if (j < count && mine) {
+              const uint4 o = *reinterpret_cast<const uint4*>(my_rec + 8 * j);
+              const uint4 u00 = ldg128(vb + o.x);
+              const uint4 u01 = ldg128(vb + o.y);
+              const uint4 u10 = ldg128(vb + o.z);
+              const uint4 u11 = ldg128(vb + o.w);
+              if constexpr (MIXED) {
+                const uint2 wq = *reinterpret_cast<const uint2*>(my_rec + 8 * j + 4);
+                blend(u00, u01, u10, u11, 0.f, 0.f, 0.f, 0.f, wq.x, wq.y);
+              } else {
+                const float4 wq = *reinterpret_cast<const float4*>(my_rec + 8 * j + 4);
+                blend(u00, u01, u10, u11, wq.x, wq.y, wq.z, wq.w, 0u, 0u);
+              }
+            }
+          }
+          __syncwarp();
+        };
+        auto write_record = [&](int l, float lx, float ly, float w) {
+          const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
+          const int base = lv.t.start[l] * pix_stride;
+          constexpr unsigned ES = sizeof(T);
+          *reinterpret_cast<uint4*>(my_rec + 8 * chunk) =
+              make_uint4((unsigned)(base + c.o00) * ES, (unsigned)(base + c.o01) * ES,
+                         (unsigned)(base + c.o10) * ES, (unsigned)(base + c.o11) * ES);
+          if constexpr (MIXED) {
+            *reinterpret_cast<uint2*>(my_rec + 8 * chunk + 4) =
+                make_uint2(Vec16<T>::pack2(w * c.w00, w * c.w01), Vec16<T>::pack2(w * c.w10, w * c.w11));
+          } else {
+            *reinterpret_cast<float4*>(my_rec + 8 * chunk + 4) =
+                make_float4(w * c.w00, w * c.w01, w * c.w10, w * c.w11);
+          }
+        };
+
+        if (MODE == MODE_SCA) {
+          // every lane of the warp walks the union of the warp's cameras (with 8 heads per warp
+          // that is the query's own list); rows the camera does not hit skip records and gathers
+          uint32_t warp_hits = __reduce_or_sync(0xffffffffu, hits);
+          while (warp_hits) {
+            const int cam = __ffs(warp_hits) - 1;
+            warp_hits &= warp_hits - 1;
+            const bool mine = (hits >> cam) & 1u;
+            const float2* rc = reinterpret_cast<const float2*>(
+                a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
+            const T* vcam = vhead + ((size_t)b * a.groups + cam) * batch_stride;
+            for (int s0 = 0; s0 < LP; s0 += TPH) {
+              const int s = s0 + chunk;
+              if (s < LP && mine) {
+                const uint32_t meta = s_meta[s];
+                const float2 r = __ldg(rc + (meta >> 16));
+                const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
+                write_record((int)(meta & 0xffffu), r.x + o.x, r.y + o.y, my_w[s]);
+              }
+              accumulate_block(vcam, min(TPH, LP - s0), mine);
+            }
+          }
+        } else if (live) {
+          // short rows (4-8 samples per queue entry): every lane sets up its own samples, the
+          // exchange would cost more than it saves
+          auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
+            const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+            const uint4 u00 = ldg128(lbase + c.o00);
+            const uint4 u01 = ldg128(lbase + c.o01);
+            const uint4 u10 = ldg128(lbase + c.o10);
+            const uint4 u11 = ldg128(lbase + c.o11);
+            if constexpr (MIXED) {
+              blend(u00, u01, u10, u11, 0.f, 0.f, 0.f, 0.f, Vec16<T>::pack2(w * c.w00, w * c.w01),
+                    Vec16<T>::pack2(w * c.w10, w * c.w11));
+            } else {
+              blend(u00, u01, u10, u11, w * c.w00, w * c.w01, w * c.w10, w * c.w11, 0u, 0u);
+            }
           };
           for (int j = 0; j < a.groups; ++j) {
             const T* vb = vhead + ((size_t)b * a.groups + j) * batch_stride;
@@ -377,8 +416,8 @@ fused_fwd_kernel(const FusedArgs a) {
         float out[VEC];
 #pragma unroll
         for (int i = 0; i < V2; ++i) {
-          out[2 * i] = acc[i].x;
-          out[2 * i + 1] = acc[i].y;
+          out[2 * i] = MIXED ? accm[(2 * i) % 8] : acc[i].x;
+          out[2 * i + 1] = MIXED ? accm[(2 * i + 1) % 8] : acc[i].y;
         }
         if (scale == 2.f) {
 #pragma unroll
@@ -387,8 +426,10 @@ fused_fwd_kernel(const FusedArgs a) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i) out[i] = out[i] / scale;
         }
-        T* o = static_cast<T*>(a.out) + grow * a.Dh + chunk * VEC;
-        *reinterpret_cast<uint4*>(o) = Vec16<T>::pack(out);
+        if (live) {
+          T* o = static_cast<T*>(a.out) + grow * a.Dh + chunk * VEC;
+          *reinterpret_cast<uint4*>(o) = Vec16<T>::pack(out);
+        }
       }
     }
   }
@@ -410,12 +451,22 @@ fused_bwd_kernel(const FusedArgs a) {
   float* s_w = s_off + (size_t)ROWS * po;              // [ROWS][pw] softmax weights
   float* s_go = s_w + (size_t)ROWS * pw;               // [ROWS][po] grad wrt raw offsets
   float* s_ga = s_go + (size_t)ROWS * po;              // [ROWS][pw] grad wrt weights -> logits
-  constexpr int REC_PITCH = 8 * TPH + 4;               // per-row exchange buffer, in 4-byte words
+  // per-row exchange buffer of TPH sample records, in 4-byte words: 4 corner byte offsets (the
+  // validity bits ride in the low 4 bits of the first, the offsets are multiples of 16), lw, lh
+  // and the scatter weights attention x bilinear -- two packed fp16 pairs for the fp16 accumulator,
+  // four floats otherwise
+  constexpr int REC_WORDS = ACC_HALF ? 8 : 12;
+  constexpr int REC_PITCH = REC_WORDS * TPH + 4;
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_ga + (size_t)ROWS * pw);
+  uint32_t* s_meta = s_rec + (size_t)ROWS * REC_PITCH;   // per-sample level | anchor << 16
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
 
   load_fused_levels(lv, a);
+  for (int i = tid; i < S; i += kFusedThreads) {
+    const int sl = i % LP, l = sl / a.P;
+    s_meta[i] = (uint32_t)l | ((uint32_t)((sl - l * a.P) % a.D) << 16);
+  }
   __syncthreads();
 
   const int chunk = tid % TPH;
@@ -450,8 +501,11 @@ fused_bwd_kernel(const FusedArgs a) {
       const bool work = live && (MODE == MODE_TSA || hits != 0);
       const long long grow = ((long long)b * a.Nq + q) * a.M + m;
       __syncwarp();
-      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + grow * S * 2,
-                         static_cast<const CT*>(a.logits) + grow * S, my_off, my_w, chunk, S, LP);
+      const long long qrow = (long long)b * a.Nq + q;
+      const long long off_at = qrow * a.off_stride + (long long)m * S * 2;
+      const long long log_at = qrow * a.log_stride + (long long)m * S;
+      stage_row<TPH, CT>(a, lv, work, static_cast<const CT*>(a.offsets) + off_at,
+                         static_cast<const CT*>(a.logits) + log_at, my_off, my_w, chunk, S, LP, s_meta);
       // clear the row's gradient accumulators
       for (int i = chunk; i < 2 * S; i += TPH) my_go[i] = 0.f;
       for (int i = chunk; i < S; i += TPH) my_ga[i] = 0.f;
@@ -469,10 +523,17 @@ fused_bwd_kernel(const FusedArgs a) {
       __half* ghead16 = static_cast<__half*>(a.g_value) + head_off + chunk * VEC;
       const float acc_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
 
+      // 16-bit value: the dot products take g_out straight from its packed words (FHFMA, exact
+      // products) and the 1 / count factor is applied to the per-sample totals instead
+      constexpr bool MIXED = sizeof(T) == 2;
+      constexpr unsigned ES = sizeof(T);
+      const float dscale = !MIXED ? 1.f : (scale == 2.f ? 0.5f : 1.f / scale);
       float2 g[V2], gs[V2];
+      uint4 gp;
       {
         const T* grow_ptr = static_cast<const T*>(a.g_out) + grow * a.Dh;
-        Vec16<T>::unpack2(ldg128(grow_ptr + chunk * VEC), g);
+        gp = ldg128(grow_ptr + chunk * VEC);
+        Vec16<T>::unpack2(gp, g);
         if (VEC == 4 || ACC_HALF) {
 #pragma unroll
           for (int i = 0; i < V2; ++i) gs[i] = g[i];
@@ -502,71 +563,111 @@ fused_bwd_kernel(const FusedArgs a) {
         for (int k = 0; k < 4; ++k) gh[k] = __floats2half2_rn(g[k % V2].x * acc_scale, g[k % V2].y * acc_scale);
       }
 
-      // Core of one sample against one value map, from its corner set-up: gathers the four
-      // corners, scatters grad_value, returns this lane's partial (d out / d weight, d/dx, d/dy).
-      auto core = [&](size_t boff, int o00, int o01, int o10, int o11, float lw, float lh,
-                      unsigned valid, float w, float& ga, float& gx, float& gy) {
-        const float hw = 1.f - lw, hh = 1.f - lh;
-        const float w00 = (valid & 1u) ? hh * hw : 0.f, w01 = (valid & 2u) ? hh * lw : 0.f;
-        const float w10 = (valid & 4u) ? lh * hw : 0.f, w11 = (valid & 8u) ? lh * lw : 0.f;
-        const T* vb = vhead + boff;
-        float* gb = ghead + boff;
+      // Core of one sample against one value map, from its record: gathers the four corners,
+      // scatters grad_value, returns this lane's partial (d out / d weight, d/dx, d/dy).  o00v =
+      // byte offset of corner 00 | validity bits; aw* = attention x bilinear weight per corner
+      // (zero for invalid corners and for rows without work), as packed fp16 pairs (awa = 00|01,
+      // awb = 10|11) for the fp16 accumulator or as floats.
+      auto core = [&](size_t boff, unsigned o00v, unsigned o01, unsigned o10, unsigned o11, float lw,
+                      float lh, uint32_t awa, uint32_t awb, float aw00, float aw01, float aw10,
+                      float aw11, float& ga, float& gx, float& gy) {
+        const unsigned o00 = o00v & ~15u;
+        const char* vb = reinterpret_cast<const char*>(vhead + boff);
         const uint4 u00 = ldg128(vb + o00);
         const uint4 u01 = ldg128(vb + o01);
         const uint4 u10 = ldg128(vb + o10);
         const uint4 u11 = ldg128(vb + o11);
-        auto scatter = [&](int off, float cw) {
-          const float aw = w * cw;
-          if (aw == 0.f || (a.debug & 1)) return;        // invalid corner, or a zero contribution
-          if (ACC_HALF) {
-            // gh = fp16(g * scale) per row; one HMUL2 per channel pair, one 16-byte reduction
-            const __half2 aw2 = __float2half2_rn(aw);
+        if constexpr (ACC_HALF) {
+          // gh = fp16(g * scale) per row; one HMUL2 per channel pair, one predicated 16-byte
+          // reduction per corner (skipped where the weight is zero)
+          char* gb = reinterpret_cast<char*>(ghead16 + boff);
+          auto scatter = [&](unsigned off, __half2 aw2, uint32_t on) {
             uint32_t h[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const __half2 hk = __hmul2(aw2, gh[k]);
               h[k] = *reinterpret_cast<const uint32_t*>(&hk);
             }
-            red_add_f16x8(ghead16 + boff + off, h[0], h[1], h[2], h[3]);
-            return;
-          }
-          const float2 aw2 = splat2(aw);
-          float* dst = gb + off;
+            red_add_f16x8_if(reinterpret_cast<__half*>(gb + off), h[0], h[1], h[2], h[3], on);
+          };
+          const __half2 pa = *reinterpret_cast<const __half2*>(&awa);
+          const __half2 pb = *reinterpret_cast<const __half2*>(&awb);
+          const uint32_t live_mask = (a.debug & 1) ? 0u : 0x7fffu;
+          scatter(o00, __low2half2(pa), awa & live_mask);
+          scatter(o01, __high2half2(pa), (awa >> 16) & live_mask);
+          scatter(o10, __low2half2(pb), awb & live_mask);
+          scatter(o11, __high2half2(pb), (awb >> 16) & live_mask);
+        } else {
+          char* gb = reinterpret_cast<char*>(ghead + boff);
+          auto scatter = [&](unsigned off, float aw) {
+            const float2 aw2 = splat2(aw);
+            float* dst = reinterpret_cast<float*>(gb + (size_t)off * (sizeof(float) / ES));
+            const uint32_t on = (aw != 0.f && !(a.debug & 1)) ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < SC; ++k) {
-            const float2 p0 = fmul2(aw2, gs[2 * k]), p1 = fmul2(aw2, gs[2 * k + 1]);
-            red_add_f32x4(dst + k * 4 * TPH, p0.x, p0.y, p1.x, p1.y);
-          }
-        };
-        scatter(o00, w00);
-        scatter(o01, w01);
-        scatter(o10, w10);
-        scatter(o11, w11);
-        float2 f[V2];
-        float2 d;
-        Vec16<T>::unpack2(u00, f);
-        d = make_float2(0.f, 0.f);
+            for (int k = 0; k < SC; ++k) {
+              const float2 p0 = fmul2(aw2, gs[2 * k]), p1 = fmul2(aw2, gs[2 * k + 1]);
+              red_add_f32x4_if(dst + k * 4 * TPH, p0.x, p0.y, p1.x, p1.y, on);
+            }
+          };
+          scatter(o00, aw00);
+          scatter(o01, aw01);
+          scatter(o10, aw10);
+          scatter(o11, aw11);
+        }
+        float d00, d01, d10, d11;
+        if constexpr (MIXED) {
+          d00 = dot_mixed<T>(u00, gp);
+          d01 = dot_mixed<T>(u01, gp);
+          d10 = dot_mixed<T>(u10, gp);
+          d11 = dot_mixed<T>(u11, gp);
+        } else {
+          float2 f[V2];
+          float2 d;
+          Vec16<T>::unpack2(u00, f);
+          d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d00 = (valid & 1u) ? d.x + d.y : 0.f;
-        Vec16<T>::unpack2(u01, f);
-        d = make_float2(0.f, 0.f);
+          for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+          d00 = d.x + d.y;
+          Vec16<T>::unpack2(u01, f);
+          d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d01 = (valid & 2u) ? d.x + d.y : 0.f;
-        Vec16<T>::unpack2(u10, f);
-        d = make_float2(0.f, 0.f);
+          for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+          d01 = d.x + d.y;
+          Vec16<T>::unpack2(u10, f);
+          d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d10 = (valid & 4u) ? d.x + d.y : 0.f;
-        Vec16<T>::unpack2(u11, f);
-        d = make_float2(0.f, 0.f);
+          for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+          d10 = d.x + d.y;
+          Vec16<T>::unpack2(u11, f);
+          d = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
-        const float d11 = (valid & 8u) ? d.x + d.y : 0.f;
-        ga = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+          for (int i = 0; i < V2; ++i) d = ffma2(f[i], g[i], d);
+          d11 = d.x + d.y;
+        }
+        // corners outside the map were gathered from a clamped (in-bounds) address: drop them
+        d00 = (o00v & 1u) ? d00 : 0.f;
+        d01 = (o00v & 2u) ? d01 : 0.f;
+        d10 = (o00v & 4u) ? d10 : 0.f;
+        d11 = (o00v & 8u) ? d11 : 0.f;
+        const float hw = 1.f - lw, hh = 1.f - lh;
+        ga = hh * (hw * d00 + lw * d01) + lh * (hw * d10 + lw * d11);
         gx = hh * (d01 - d00) + lh * (d11 - d10);
         gy = hw * (d10 - d00) + lw * (d11 - d01);
+      };
+      // record fields after the offsets, from a corner set-up and the sample's attention weight
+      auto scatter_weights = [&](const Corners& c, float w, uint32_t (&rw)[REC_WORDS - 4]) {
+        rw[0] = __float_as_uint(c.lw);
+        rw[1] = __float_as_uint(c.lh);
+        if constexpr (ACC_HALF) {
+          const __half2 pa = __floats2half2_rn(w * c.w00, w * c.w01);
+          const __half2 pb = __floats2half2_rn(w * c.w10, w * c.w11);
+          rw[2] = *reinterpret_cast<const uint32_t*>(&pa);
+          rw[3] = *reinterpret_cast<const uint32_t*>(&pb);
+        } else {
+          rw[2] = 0u; rw[3] = 0u;
+          rw[4] = __float_as_uint(w * c.w00); rw[5] = __float_as_uint(w * c.w01);
+          rw[6] = __float_as_uint(w * c.w10); rw[7] = __float_as_uint(w * c.w11);
+        }
       };
 
       if (MODE == MODE_SCA) {
@@ -587,21 +688,27 @@ fused_bwd_kernel(const FusedArgs a) {
             const int s = s0 + chunk;
             float my_wgt = 0.f;
             {
-              int4 ro = make_int4(0, 0, 0, 0);
-              float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+              uint4 ro = make_uint4(0u, 0u, 0u, 0u);
+              uint32_t rw[REC_WORDS - 4];
+#pragma unroll
+              for (int i = 0; i < REC_WORDS - 4; ++i) rw[i] = 0u;
               if (s < LP) {
-                const int l = s / a.P;
-                const int z = (s - l * a.P) % a.D;                   // point index p = k*D + z (quirk 5)
-                const float2 r = __ldg(rc + z);
+                const uint32_t meta = s_meta[s];
+                const int l = (int)(meta & 0xffffu);
+                const float2 r = __ldg(rc + (meta >> 16));
                 const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
                 const Corners c = corner_setup(r.x + o.x, r.y + o.y, lv.t.h[l], lv.t.w[l], pix_stride);
                 const int base = lv.t.start[l] * pix_stride;
                 my_wgt = mine ? my_w[s] : 0.f;
-                ro = make_int4(base + c.o00, base + c.o01, base + c.o10, base + c.o11);
-                rf = make_float4(c.lw, c.lh, __uint_as_float(c.valid), my_wgt);
+                ro = make_uint4(((unsigned)(base + c.o00) * ES) | c.valid, (unsigned)(base + c.o01) * ES,
+                                (unsigned)(base + c.o10) * ES, (unsigned)(base + c.o11) * ES);
+                scatter_weights(c, my_wgt, rw);
               }
-              *reinterpret_cast<int4*>(my_rec + 8 * chunk) = ro;
-              *reinterpret_cast<float4*>(my_rec + 8 * chunk + 4) = rf;
+              uint32_t* rec = my_rec + REC_WORDS * chunk;
+              *reinterpret_cast<uint4*>(rec) = ro;
+              *reinterpret_cast<uint4*>(rec + 4) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+              if constexpr (!ACC_HALF)
+                *reinterpret_cast<uint4*>(rec + 8) = make_uint4(rw[4], rw[5], rw[6], rw[7]);
             }
             __syncwarp();
             float tga = 0.f, tgx = 0.f, tgy = 0.f;
@@ -609,10 +716,14 @@ fused_bwd_kernel(const FusedArgs a) {
 FUSED_UNROLL(FUSED_BWD_UNROLL)
             for (int j = 0; j < TPH; ++j) {
               if (j < count) {
-                const int4 ro = *reinterpret_cast<const int4*>(my_rec + 8 * j);
-                const float4 rf = *reinterpret_cast<const float4*>(my_rec + 8 * j + 4);
+                const uint32_t* rec = my_rec + REC_WORDS * j;
+                const uint4 ro = *reinterpret_cast<const uint4*>(rec);
+                const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
+                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
                 float ga, gx, gy;
-                core(coff, ro.x, ro.y, ro.z, ro.w, rf.x, rf.y, __float_as_uint(rf.z), rf.w, ga, gx, gy);
+                core(coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
+                     ra.x, ra.y, ra.z, ra.w, ga, gx, gy);
                 ga = group_sum<TPH>(ga);
                 gx = group_sum<TPH>(gx);
                 gy = group_sum<TPH>(gy);
@@ -620,11 +731,12 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
               }
             }
             if (s < LP && mine) {
-              my_ga[s] += tga;
+              my_ga[s] += tga * dscale;
               float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
               float2 cur = *go2;
-              cur.x += my_wgt * tgx;
-              cur.y += my_wgt * tgy;
+              const float ws = my_wgt * dscale;
+              cur.x += ws * tgx;
+              cur.y += ws * tgy;
               *go2 = cur;
             }
             __syncwarp();
@@ -644,17 +756,26 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
               const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
               const float w = live ? my_w[s] : 0.f;
               const Corners c = corner_setup(r.x + o.x, r.y + o.y, H, W, pix_stride);
+              uint32_t rw[REC_WORDS - 4];
+              scatter_weights(c, w, rw);
               float ga, gx, gy;
-              core(loff, c.o00, c.o01, c.o10, c.o11, c.lw, c.lh, c.valid, w, ga, gx, gy);
+              if constexpr (ACC_HALF)
+                core(loff, ((unsigned)c.o00 * ES) | c.valid, (unsigned)c.o01 * ES, (unsigned)c.o10 * ES,
+                     (unsigned)c.o11 * ES, c.lw, c.lh, rw[2], rw[3], 0.f, 0.f, 0.f, 0.f, ga, gx, gy);
+              else
+                core(loff, ((unsigned)c.o00 * ES) | c.valid, (unsigned)c.o01 * ES, (unsigned)c.o10 * ES,
+                     (unsigned)c.o11 * ES, c.lw, c.lh, 0u, 0u, w * c.w00, w * c.w01, w * c.w10,
+                     w * c.w11, ga, gx, gy);
               ga = group_sum<TPH>(ga);
               gx = group_sum<TPH>(gx);
               gy = group_sum<TPH>(gy);
               if (chunk == 0 && live) {
-                my_ga[s] += ga;
+                my_ga[s] += ga * dscale;
                 float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
                 float2 cur = *go2;
-                cur.x += w * gx;
-                cur.y += w * gy;
+                const float ws = w * dscale;
+                cur.x += ws * gx;
+                cur.y += ws * gy;
                 *go2 = cur;
               }
             }
@@ -668,7 +789,7 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
       {
         const int nseg = S / LP;
         const bool use_clamp = a.clamp >= 0.f;
-        const CT* raw = static_cast<const CT*>(a.logits) + grow * S;
+        const CT* raw = static_cast<const CT*>(a.logits) + log_at;
         if (LP % TPH == 0) {
           for (int sg = 0; sg < nseg; ++sg) {
             float dot = 0.f;
@@ -704,8 +825,8 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
 
       // gradient rows back to global memory
       if (live) {
-        CT* dst_o = static_cast<CT*>(a.g_offsets) + grow * S * 2;
-        CT* dst_l = static_cast<CT*>(a.g_logits) + grow * S;
+        CT* dst_o = static_cast<CT*>(a.g_offsets) + off_at;
+        CT* dst_l = static_cast<CT*>(a.g_logits) + log_at;
         if (a.vec_ok) {
           for (int c = chunk; c < (2 * S) / 4; c += TPH) store_coord4<CT>(dst_o + 4 * c, my_go + 4 * c);
           for (int c = chunk; c < S / 4; c += TPH) store_coord4<CT>(dst_l + 4 * c, my_ga + 4 * c);
@@ -757,11 +878,17 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   }
   a.num_tiles = (long long)f.bs * a.tiles_per_sample;
   if (a.num_tiles <= 0) return MSDA_OK;
-  a.vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.g_offsets) | reinterpret_cast<uintptr_t>(f.g_logits)) % 16 == 0);
+  a.off_stride = f.off_stride ? f.off_stride : (long long)f.M * S * 2;
+  a.log_stride = f.log_stride ? f.log_stride : (long long)f.M * S;
+  if (a.off_stride % 2 != 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: the offsets stride must be even", what);
+  a.vec_ok = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(f.g_offsets) | reinterpret_cast<uintptr_t>(f.g_logits)) % 16 == 0) &&
+             ((a.off_stride * sizeof(CT)) % 16 == 0) && ((a.log_stride * sizeof(CT)) % 16 == 0);
   if ((reinterpret_cast<uintptr_t>(f.offsets) % 16) != 0 || (reinterpret_cast<uintptr_t>(f.logits) % 16) != 0)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: offsets / logits must be 16-byte aligned", what);
   const size_t smem = (size_t)ROWS * ((2 * S + 4) + (S + 4)) * (bwd ? 2 : 1) * sizeof(float) +
-                      (size_t)ROWS * (8 * TPH + 4) * sizeof(uint32_t);
+                      (size_t)ROWS * ((bwd && !(sizeof(T) == 2 && f.acc_half) ? 12 : 8) * TPH + 4) * sizeof(uint32_t) +
+                      (size_t)S * sizeof(uint32_t);
   if (smem > 200 * 1024)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: %d samples per row need %zu bytes of shared memory", what, S, smem);
   constexpr bool kHalfOk = sizeof(T) == 2;
@@ -792,11 +919,15 @@ static int dispatch_tph(const FusedProblem& f, bool bwd, cudaStream_t st, const 
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: head_dim %d must be a multiple of %d for this dtype "
                      "(use the op-boundary msda_fwd/msda_bwd, which has a generic path)", what, f.Dh, VEC);
   switch (f.Dh / VEC) {
+#ifndef FUSED_DEV_ONLY               // development builds compile the base-config instance only
     case 1: return launch_fused<T, CT, 1, MODE>(f, bwd, st, what);
     case 2: return launch_fused<T, CT, 2, MODE>(f, bwd, st, what);
+#endif
     case 4: return launch_fused<T, CT, 4, MODE>(f, bwd, st, what);
+#ifndef FUSED_DEV_ONLY
     case 8: return launch_fused<T, CT, 8, MODE>(f, bwd, st, what);
     case 16: return launch_fused<T, CT, 16, MODE>(f, bwd, st, what);
+#endif
     default: break;
   }
   return set_error(MSDA_ERR_UNSUPPORTED, "%s: head_dim %d not supported by the fused kernels", what, f.Dh);
@@ -811,6 +942,10 @@ static int dispatch_dtype(const FusedProblem& f, bool bwd, cudaStream_t st, cons
   if (f.coord_dtype != MSDA_F32 && f.coord_dtype != f.value_dtype)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: offsets / logits must be fp32 or the value dtype", what);
   const bool c32 = f.coord_dtype == MSDA_F32;
+#ifdef FUSED_DEV_ONLY
+  if (f.value_dtype == MSDA_BF16 && !c32) return dispatch_tph<__nv_bfloat16, __nv_bfloat16, MODE>(f, bwd, st, what);
+  return set_error(MSDA_ERR_UNSUPPORTED, "%s: development build (bf16 / bf16 only)", what);
+#else
   switch (f.value_dtype) {
     case MSDA_F32: return dispatch_tph<float, float, MODE>(f, bwd, st, what);
     case MSDA_BF16: return c32 ? dispatch_tph<__nv_bfloat16, float, MODE>(f, bwd, st, what)
@@ -818,6 +953,7 @@ static int dispatch_dtype(const FusedProblem& f, bool bwd, cudaStream_t st, cons
     default: return c32 ? dispatch_tph<__half, float, MODE>(f, bwd, st, what)
                         : dispatch_tph<__half, __half, MODE>(f, bwd, st, what);
   }
+#endif
 }
 
 int launch_sca_fwd(const FusedProblem& f, cudaStream_t st) { return dispatch_dtype<MODE_SCA>(f, false, st, "sca_fwd"); }

@@ -127,6 +127,41 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
+// Mixed-precision FMA of sm_100 (SASS FHFMA): fp32 accumulator += a * b with a, b in the 16-bit
+// value dtype.  The product of two bf16 / fp16 numbers is exact in fp32, so nothing is lost
+// against unpack + FFMA; the operands are taken straight from the halves of the loaded words.
+template <typename T> __device__ __forceinline__ float fma_mixed(uint16_t a, uint16_t b, float c);
+template <> __device__ __forceinline__ float fma_mixed<__nv_bfloat16>(uint16_t a, uint16_t b, float c) {
+  float d;
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+template <> __device__ __forceinline__ float fma_mixed<__half>(uint16_t a, uint16_t b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint16_t lo16(uint32_t w) { return (uint16_t)(w & 0xffffu); }
+__device__ __forceinline__ uint16_t hi16(uint32_t w) { return (uint16_t)(w >> 16); }
+
+// acc[0..7] += (8 channels of u) * w, w in the value dtype
+template <typename T>
+__device__ __forceinline__ void axpy_mixed(const uint4& u, uint16_t w, float (&acc)[8]) {
+  acc[0] = fma_mixed<T>(lo16(u.x), w, acc[0]); acc[1] = fma_mixed<T>(hi16(u.x), w, acc[1]);
+  acc[2] = fma_mixed<T>(lo16(u.y), w, acc[2]); acc[3] = fma_mixed<T>(hi16(u.y), w, acc[3]);
+  acc[4] = fma_mixed<T>(lo16(u.z), w, acc[4]); acc[5] = fma_mixed<T>(hi16(u.z), w, acc[5]);
+  acc[6] = fma_mixed<T>(lo16(u.w), w, acc[6]); acc[7] = fma_mixed<T>(hi16(u.w), w, acc[7]);
+}
+// sum over the 8 channels of u * g (two chains of four)
+template <typename T>
+__device__ __forceinline__ float dot_mixed(const uint4& u, const uint4& g) {
+  float a = fma_mixed<T>(lo16(u.x), lo16(g.x), 0.f), b = fma_mixed<T>(hi16(u.x), hi16(g.x), 0.f);
+  a = fma_mixed<T>(lo16(u.y), lo16(g.y), a); b = fma_mixed<T>(hi16(u.y), hi16(g.y), b);
+  a = fma_mixed<T>(lo16(u.z), lo16(g.z), a); b = fma_mixed<T>(hi16(u.z), hi16(g.z), b);
+  a = fma_mixed<T>(lo16(u.w), lo16(g.w), a); b = fma_mixed<T>(hi16(u.w), hi16(g.w), b);
+  return a + b;
+}
+
 // 128-bit read-only global load (value maps are re-read many times: keep them in L1/L2).
 __device__ __forceinline__ uint4 ldg128(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
@@ -141,6 +176,18 @@ __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, flo
 __device__ __forceinline__ void red_add_f16x8(__half* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};"
                :: "l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// predicated forms: the reduction is issued only where `on` is non-zero (no branch)
+__device__ __forceinline__ void red_add_f32x4_if(float* addr, float a, float b, float c, float d, uint32_t on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+               "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+               :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(on) : "memory");
+}
+__device__ __forceinline__ void red_add_f16x8_if(__half* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                                 uint32_t on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+               "@p red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};\n\t}"
+               :: "l"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(on) : "memory");
 }
 __device__ __forceinline__ void red_add_f32x2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(addr), "f"(a), "f"(b) : "memory");

@@ -45,6 +45,9 @@ struct FusedProblem {
   float clamp = -1.f;
   int value_dtype = MSDA_F32;
   int coord_dtype = MSDA_F32;
+  // elements between the offset / logit rows of consecutive queries (0 = dense); the gradient
+  // buffers have the layout of their inputs
+  long long off_stride = 0, log_stride = 0;
 };
 
 int set_error(int code, const char* fmt, ...);

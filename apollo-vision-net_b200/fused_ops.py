@@ -123,12 +123,62 @@ def _finish_accumulator(acc, code, scale, value):
     return out
 
 
-def _coords(value, offsets, logits):
-    """Offsets / logits are consumed in fp32 or in the value dtype (no conversion pass for a
-    bf16 model); anything else is brought to fp32."""
-    dt = offsets.dtype if (offsets.dtype == logits.dtype and
-                           offsets.dtype in (torch.float32, value.dtype)) else torch.float32
-    return offsets.to(dt).contiguous(), logits.to(dt).contiguous()
+class _Coords:
+    """Offsets / logits as the kernels take them: base pointers, per-query row strides (elements)
+    and dtype.  They are consumed in fp32 or in the value dtype (no conversion pass for a bf16
+    model); anything else is brought to fp32.
+
+    Two calling conventions: separate tensors (the outputs of the ``sampling_offsets`` and
+    ``attention_weights`` Linear layers), or -- ``logits is None`` -- ONE tensor ``(bs, Nq, 3*n)``
+    whose columns ``[0, 2n)`` are the offsets and ``[2n, 3n)`` the logits of a query, i.e. the
+    output of a single GEMM over the concatenated weights; the
+    gradient then comes back as one tensor of the same layout.
+    """
+
+    def __init__(self, value, offsets, logits, tail_off, tail_log):
+        self.merged = logits is None
+        if self.merged:
+            dt = offsets.dtype if offsets.dtype in (torch.float32, value.dtype) else torch.float32
+            buf = offsets.to(dt).contiguous()
+            bs, nq, width = buf.shape
+            n = width // 3
+            assert width == 3 * n and 2 * n == _prod(tail_off) and n == _prod(tail_log), \
+                (buf.shape, tail_off, tail_log)
+            self.keep = (buf,)
+            self.off_ptr, self.log_ptr = buf.data_ptr(), buf.data_ptr() + 2 * n * buf.element_size()
+            self.off_stride = self.log_stride = width
+            self.n = n
+        else:
+            dt = offsets.dtype if (offsets.dtype == logits.dtype and
+                                   offsets.dtype in (torch.float32, value.dtype)) else torch.float32
+            o, lg = offsets.to(dt).contiguous(), logits.to(dt).contiguous()
+            assert tuple(o.shape[2:]) == tuple(tail_off) and tuple(lg.shape[2:]) == tuple(tail_log), \
+                (o.shape, lg.shape, tail_off, tail_log)
+            self.keep = (o, lg)
+            self.off_ptr, self.log_ptr = o.data_ptr(), lg.data_ptr()
+            self.off_stride, self.log_stride = _prod(tail_off), _prod(tail_log)
+        self.dtype = dt
+        self.code = _DTYPE_CODE[dt]
+
+    @staticmethod
+    def grads(saved, merged):
+        """Gradient buffers with the layout of the inputs: (tensors to return, off_ptr, log_ptr)."""
+        if merged:
+            buf, = saved
+            g = torch.empty(buf.shape, dtype=buf.dtype, device=buf.device)
+            n = buf.shape[-1] // 3
+            return (g, None), g.data_ptr(), g.data_ptr() + 2 * n * g.element_size()
+        o, lg = saved
+        g_off = torch.empty(o.shape, dtype=o.dtype, device=o.device)
+        g_log = torch.empty(lg.shape, dtype=lg.dtype, device=lg.device)
+        return (g_off, g_log), g_off.data_ptr(), g_log.data_ptr()
+
+
+def _prod(xs):
+    n = 1
+    for x in xs:
+        n *= int(x)
+    return n
 
 
 class SpatialCrossAttnFunction(Function):
@@ -146,24 +196,28 @@ class SpatialCrossAttnFunction(Function):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref_cam=ref_cam,
                       mask=mask_u8, hit_bits=hit_bits)
         value = _check_value(value)
-        offsets, logits = _coords(value, offsets, logits)
         shapes = spatial_shapes.to(torch.int64).contiguous()
         starts = level_start_index.to(torch.int64).contiguous()
         ref_cam = ref_cam.to(torch.float32).contiguous()
         mask_u8 = mask_u8.contiguous()
         hit_bits = hit_bits.contiguous()
         Bc, Nk, M, Dh = value.shape
-        bs, HW, M2, L, P, _ = offsets.shape
+        bs, HW = offsets.shape[:2]
+        L = shapes.shape[0]
         D = ref_cam.shape[3]
-        assert Bc == bs * num_cam and M2 == M and logits.shape == (bs, HW, M, L * P)
+        P = (offsets.shape[-1] // (3 * M * L)) if logits is None else offsets.shape[4]
+        co = _Coords(value, offsets, logits, (M, L, P, 2), (M, L * P))
+        assert Bc == bs * num_cam
         assert ref_cam.shape == (num_cam, bs, HW, D, 2) and hit_bits.shape == (bs, HW)
         slots = torch.empty((bs, HW, M * Dh), dtype=value.dtype, device=value.device)
         with torch.cuda.device(value.device):
-            _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
-                logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
+            _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), co.off_ptr,
+                co.log_ptr, ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
                 slots.data_ptr(), None, bs, num_cam, Nk, M, Dh, L, P, D, HW, int(bev_w or 0),
-                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], _stream_ptr(value))
-        ctx.save_for_backward(value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits)
+                _DTYPE_CODE[value.dtype], co.code, co.off_stride, co.log_stride, _stream_ptr(value))
+        ctx.save_for_backward(value, shapes, starts, ref_cam, mask_u8, hit_bits, *co.keep)
+        ctx.merged, ctx.dims = co.merged, (bs, HW, M, Dh, L, P, D, Nk)
+        ctx.coord = (co.code, co.off_stride, co.log_stride)
         ctx.num_cam = num_cam
         ctx.bev_w = int(bev_w or 0)
         return slots
@@ -172,21 +226,21 @@ class SpatialCrossAttnFunction(Function):
     @once_differentiable
     @custom_bwd
     def backward(ctx, g_slots):
-        value, shapes, starts, offsets, logits, ref_cam, mask_u8, hit_bits = ctx.saved_tensors
+        value, shapes, starts, ref_cam, mask_u8, hit_bits, *coords = ctx.saved_tensors
         num_cam = ctx.num_cam
-        Bc, Nk, M, Dh = value.shape
-        bs, HW, _, L, P, _ = offsets.shape
-        D = ref_cam.shape[3]
+        bs, HW, M, Dh, L, P, D, Nk = ctx.dims
+        code, so, sl = ctx.coord
+        off_ptr = coords[0].data_ptr()
+        log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_slots = g_slots.to(value.dtype).contiguous()
         g_value, acc_code, acc_scale = _accumulator(value, g_slots)
-        g_off = torch.empty_like(offsets)
-        g_log = torch.empty_like(logits)
+        (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
-            _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
-                logits.data_ptr(), ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
-                g_slots.data_ptr(), g_value.data_ptr(), g_off.data_ptr(), g_log.data_ptr(),
+            _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,
+                log_ptr, ref_cam.data_ptr(), mask_u8.data_ptr(), hit_bits.data_ptr(),
+                g_slots.data_ptr(), g_value.data_ptr(), g_off_ptr, g_log_ptr,
                 bs, num_cam, Nk, M, Dh, L, P, D, HW, ctx.bev_w, _DTYPE_CODE[value.dtype],
-                _DTYPE_CODE[offsets.dtype], acc_code,
+                code, so, sl, acc_code,
                 None if acc_scale is None else acc_scale.data_ptr(), _stream_ptr(value))
         g_value = _finish_accumulator(g_value, acc_code, acc_scale, value)
         return (g_value, None, None, g_off, g_log, None, None, None, None, None)
@@ -205,22 +259,27 @@ class QueueDeformAttnFunction(Function):
                 bev_w=0):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref=ref)
         value = _check_value(value)
-        offsets, logits = _coords(value, offsets, logits)
         ref = ref.to(torch.float32).contiguous()
         shapes = spatial_shapes.to(torch.int64).contiguous()
         starts = level_start_index.to(torch.int64).contiguous()
         BQ, Nk, M, Dh = value.shape
-        bs, Nq, M2, Q, L, P, _ = offsets.shape
-        assert BQ == bs * Q and M2 == M and logits.shape == (bs, Nq, M, Q, L * P)
+        bs, Nq = offsets.shape[:2]
+        L = shapes.shape[0]
+        Q = BQ // bs
+        P = (offsets.shape[-1] // (3 * M * Q * L)) if logits is None else offsets.shape[5]
+        co = _Coords(value, offsets, logits, (M, Q, L, P, 2), (M, Q, L * P))
+        assert BQ == bs * Q
         assert ref.shape == (bs * Q, Nq, L, 2), (ref.shape, (bs * Q, Nq, L, 2))
         clamp = -1.0 if clamp is None else float(clamp)
         out = torch.empty((bs, Nq, M * Dh), dtype=value.dtype, device=value.device)
         with torch.cuda.device(value.device):
-            _lib.call('tsa_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
-                logits.data_ptr(), ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
-                int(bev_w or 0), clamp, _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype],
-                _stream_ptr(value))
-        ctx.save_for_backward(value, shapes, starts, offsets, logits, ref)
+            _lib.call('tsa_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), co.off_ptr,
+                co.log_ptr, ref.data_ptr(), out.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq,
+                int(bev_w or 0), clamp, _DTYPE_CODE[value.dtype], co.code, co.off_stride,
+                co.log_stride, _stream_ptr(value))
+        ctx.save_for_backward(value, shapes, starts, ref, *co.keep)
+        ctx.merged, ctx.dims = co.merged, (bs, Nq, M, Dh, Q, L, P, Nk)
+        ctx.coord = (co.code, co.off_stride, co.log_stride)
         ctx.clamp = clamp
         ctx.bev_w = int(bev_w or 0)
         return out
@@ -229,24 +288,27 @@ class QueueDeformAttnFunction(Function):
     @once_differentiable
     @custom_bwd
     def backward(ctx, g_out):
-        value, shapes, starts, offsets, logits, ref = ctx.saved_tensors
-        BQ, Nk, M, Dh = value.shape
-        bs, Nq, _, Q, L, P, _ = offsets.shape
+        value, shapes, starts, ref, *coords = ctx.saved_tensors
+        bs, Nq, M, Dh, Q, L, P, Nk = ctx.dims
+        code, so, sl = ctx.coord
+        off_ptr = coords[0].data_ptr()
+        log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_out = g_out.to(value.dtype).contiguous()
         g_value, acc_code, acc_scale = _accumulator(value, g_out)
-        g_off = torch.empty_like(offsets)
-        g_log = torch.empty_like(logits)
+        (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
-            _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
-                logits.data_ptr(), ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
-                g_off.data_ptr(), g_log.data_ptr(), bs, Q, Nk, M, Dh, L, P, Nq, ctx.bev_w, ctx.clamp,
-                _DTYPE_CODE[value.dtype], _DTYPE_CODE[offsets.dtype], acc_code,
+            _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,
+                log_ptr, ref.data_ptr(), g_out.data_ptr(), g_value.data_ptr(),
+                g_off_ptr, g_log_ptr, bs, Q, Nk, M, Dh, L, P, Nq, ctx.bev_w, ctx.clamp,
+                _DTYPE_CODE[value.dtype], code, so, sl, acc_code,
                 None if acc_scale is None else acc_scale.data_ptr(), _stream_ptr(value))
         g_value = _finish_accumulator(g_value, acc_code, acc_scale, value)
         g_ref = None
         if ctx.needs_input_grad[5]:
             # loc = ref + off / (W, H)  =>  d ref = sum over heads and points of d off * (W, H)
             wh = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(torch.float32)      # (L, 2)
-            g_ref = (g_off.float() * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
+            go = g_off[..., :2 * (so // 3)] if ctx.merged else g_off
+            go = go.reshape(bs, Nq, M, Q, L, P, 2)
+            g_ref = (go.float() * wh.view(1, 1, 1, 1, L, 1, 2)).sum(dim=(2, 5))            # (bs, Nq, Q, L, 2)
             g_ref = g_ref.permute(0, 2, 1, 3, 4).reshape(bs * Q, Nq, L, 2)
         return g_value, None, None, g_off, g_log, g_ref, None, None

@@ -54,17 +54,18 @@ class CustomMSDeformableAttention(DeformAttnBase):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, M, -1)
-        offsets = self.sampling_offsets(query).view(bs, num_query, M, L, P, 2)
-        logits = self.attention_weights(query).view(bs, num_query, M, L * P)
+        coords = self.project_coords(query)             # offsets | logits of a query, one GEMM
+        n = M * L * P
 
         if reference_points.shape[-1] == 2:
             if reference_points.shape[2] != L:          # a single reference broadcast over levels
                 reference_points = reference_points.expand(-1, -1, L, -1)
-            output = QueueDeformAttnFunction.apply(
-                value, spatial_shapes, level_start_index,
-                offsets.view(bs, num_query, M, 1, L, P, 2), logits.view(bs, num_query, M, 1, L * P),
-                reference_points, self.attn_logits_clamp, 0)
+            output = QueueDeformAttnFunction.apply(value, spatial_shapes, level_start_index,
+                                                   coords, None, reference_points,
+                                                   self.attn_logits_clamp, 0)
         elif reference_points.shape[-1] == 4:
+            offsets = coords[..., :2 * n].reshape(bs, num_query, M, L, P, 2)
+            logits = coords[..., 2 * n:].reshape(bs, num_query, M, L * P)
             if self.attn_logits_clamp is not None:
                 c = float(self.attn_logits_clamp)
                 logits = logits.clamp(min=-c, max=c)

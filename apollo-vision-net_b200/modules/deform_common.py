@@ -9,7 +9,7 @@ import torch.nn as nn
 from ..multi_scale_deformable_attn_function import (MultiScaleDeformableAttnFunction_fp16,
                                                     MultiScaleDeformableAttnFunction_fp32)
 from ..registry import BaseModule, constant_init, xavier_init
-from ..rowops import Linear
+from ..rowops import Linear, linear
 
 
 def _is_power_of_2(n):
@@ -71,6 +71,18 @@ class DeformAttnBase(BaseModule):
         xavier_init(self.value_proj, distribution='uniform', bias=0.)
         xavier_init(self.output_proj, distribution='uniform', bias=0.)
         self._is_init = True
+
+
+    def project_coords(self, query):
+        """``sampling_offsets(query)`` and ``attention_weights(query)`` as ONE GEMM over the
+        concatenated weights: returns (..., 3n) with the raw offsets
+        of a query in columns [0, 2n) and its raw attention logits in [2n, 3n).  The parameters stay
+        the reference's two Linear layers (checkpoint layout unchanged); the fused kernels read both
+        column blocks in place and return one gradient tensor of the same layout, so the backward
+        is one dX GEMM, one dW GEMM and one bias reduction instead of two of each."""
+        w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+        b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+        return linear(query, w, b)
 
 
 def msda_apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,

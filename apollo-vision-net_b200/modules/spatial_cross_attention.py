@@ -144,9 +144,9 @@ class SpatialCrossAttention(BaseModule):
             mask_u8 = mask_b.contiguous().view(torch.uint8)
         num_cams, l, bs_v, _ = value.shape
         value = value.permute(2, 0, 1, 3).reshape(bs * self.num_cams, l, self.embed_dims)
-        v, off, logits = da.project(query, value)
-        v = v.view(bs * self.num_cams, l, da.num_heads, -1)
-        slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, off, logits,
+        v = da.value_proj(value).view(bs * self.num_cams, l, da.num_heads, -1)
+        coords = da.project_coords(query)          # offsets | logits of a query, one GEMM
+        slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, coords, None,
                                                reference_points_cam, mask_u8, hit_bits,
                                                self.num_cams, self._grid_w(bev_h, bev_w, num_query))
         slots = self.output_proj(slots.to(query.dtype))

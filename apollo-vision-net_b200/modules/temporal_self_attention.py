@@ -60,17 +60,19 @@ class TemporalSelfAttention(DeformAttnBase):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.reshape(bs * Q, num_value, M, -1)
-        offsets = self.sampling_offsets(query).view(bs, num_query, M, Q, L, P, 2)
-        logits = self.attention_weights(query).view(bs, num_query, M, Q, L * P)
+        coords = self.project_coords(query)             # offsets | logits of a query, one GEMM
+        n = M * Q * L * P
 
         grid_w = int(bev_w) if (bev_h and bev_w and int(bev_h) * int(bev_w) == num_query) else 0
         if reference_points.shape[-1] == 2:
             if reference_points.shape[2] != L:          # a single reference broadcast over levels
                 reference_points = reference_points.expand(-1, -1, L, -1)
             output = QueueDeformAttnFunction.apply(value, spatial_shapes, level_start_index,
-                                                   offsets, logits, reference_points,
+                                                   coords, None, reference_points,
                                                    self.attn_logits_clamp, grid_w)
         elif reference_points.shape[-1] == 4:
+            offsets = coords[..., :2 * n].reshape(bs, num_query, M, Q, L, P, 2)
+            logits = coords[..., 2 * n:].reshape(bs, num_query, M, Q, L * P)
             # box-shaped references (:246-250): rare path, run on the op boundary
             if self.attn_logits_clamp is not None:
                 c = float(self.attn_logits_clamp)

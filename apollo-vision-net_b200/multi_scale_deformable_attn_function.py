@@ -42,6 +42,8 @@ def _stream_ptr(t):
 
 def _require_cuda(**tensors):
     for name, t in tensors.items():
+        if t is None:                  # optional argument not given
+            continue
         if not isinstance(t, torch.Tensor):
             raise TypeError(f'{name} must be a torch.Tensor, got {type(t)}')
         if not t.is_cuda:

@@ -146,10 +146,15 @@ class LinearFunction(Function):
         return dx, dw, db
 
 
+def linear(x, weight, bias=None):
+    """``F.linear`` whose backward computes the bias gradient with the column-sum kernel."""
+    if x.is_cuda and torch.is_grad_enabled() and x.dtype == weight.dtype and x.dtype in _DTYPE_CODE:
+        return LinearFunction.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
 class Linear(nn.Linear):
     """``torch.nn.Linear`` whose backward computes the bias gradient with the column-sum kernel."""
 
     def forward(self, x):
-        if x.is_cuda and torch.is_grad_enabled() and x.dtype == self.weight.dtype and x.dtype in _DTYPE_CODE:
-            return LinearFunction.apply(x, self.weight, self.bias)
-        return F.linear(x, self.weight, self.bias)
+        return linear(x, self.weight, self.bias)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -149,12 +149,18 @@ int bev_point_sampling(const float* ref_3d, const float* lidar2img, const double
  *   bev_w    > 0: the HW queries are a row-major (HW / bev_w) x bev_w grid (2-D work tiles); 0: unknown
  *   slots    (bs, HW, M*Dh)           value_dtype out: sum over hit cameras / count
  *   attn_out (bs, HW, M, L*P)         fp32 out (softmax result, saved for backward) or NULL
+ *   offsets_stride, logits_stride     elements between the rows of consecutive queries; 0 = dense
+ *            (M*L*P*2 and M*L*P).  Non-zero strides let both tensors be column blocks of ONE
+ *            Linear output -- sampling_offsets and attention_weights computed by a single GEMM
+ *            over the concatenated weights.  The offsets stride
+ *            must be even; g_offsets / g_logits of the backward use the same strides.
  * ------------------------------------------------------------------------------- */
 int sca_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const void* offsets, const void* logits, const float* ref_cam,
             const uint8_t* bev_mask, const uint32_t* hit_bits, void* slots, float* attn_out,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, int coord_dtype, void* stream);
+            int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride,
+            int64_t logits_stride, void* stream);
 
 /*   g_slots   (bs, HW, M*Dh) value_dtype   gradient w.r.t. `slots`
  *   g_value   (bs*num_cam, Nk, M, Dh) accumulator, zero-filled by the caller: fp32
@@ -169,8 +175,8 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const uint8_t* bev_mask, const uint32_t* hit_bits, const void* g_slots,
             void* g_value, void* g_offsets, void* g_logits,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
-            int bev_w, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
-            void* stream);
+            int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride,
+            int64_t logits_stride, int accum_dtype, const float* accum_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Fused temporal self-attention / decoder cross-attention core
@@ -190,14 +196,15 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const void* offsets, const void* logits, const float* ref, void* out,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
-            float clamp, int value_dtype, int coord_dtype, void* stream);
+            float clamp, int value_dtype, int coord_dtype, int64_t offsets_stride,
+            int64_t logits_stride, void* stream);
 
 int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             const void* offsets, const void* logits, const float* ref, const void* g_out,
             void* g_value, void* g_offsets, void* g_logits,
             int bs, int Q, int Nk, int M, int Dh, int L, int P, int Nq, int bev_w,
-            float clamp, int value_dtype, int coord_dtype, int accum_dtype, const float* accum_scale,
-            void* stream);
+            float clamp, int value_dtype, int coord_dtype, int64_t offsets_stride,
+            int64_t logits_stride, int accum_dtype, const float* accum_scale, void* stream);
 
 /* Helpers of the fp16 gradient accumulator.
  *   grad_amax_scale: ws is a zero-initialised fp32 scratch of >= 64 floats (left zeroed except

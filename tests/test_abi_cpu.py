@@ -10,7 +10,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     import apollo_vision_net_b200 as pkg
     pkg.build()
     lib = pkg._lib.lib()
-    assert lib.msda_abi_version() == 1
+    assert lib.msda_abi_version() == 2
     syms = pkg._lib.header_symbols()
     assert {'msda_fwd', 'msda_bwd', 'bev_point_sampling', 'sca_fwd', 'sca_bwd', 'tsa_fwd',
             'tsa_bwd', 'msda_fwd_host', 'msda_fwd_bwd_host'} <= set(syms)

@@ -8,7 +8,7 @@ from oracle import geometry_oracle as G
 from oracle.modules_oracle import (OracleBEVFormerEncoder, OracleCustomMSDeformableAttention,
                                    OracleSpatialCrossAttention, OracleTemporalSelfAttention)
 from tests import golden_util as gu
-from tests.util import rel_err
+from tests.util import rel_l2, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -309,8 +309,12 @@ def test_encoder_tiny_config1_vs_oracle():
             # (it jumps when a sample crosses a pixel boundary), so rounding-level differences in
             # the upstream layers flip a few samples and move the offset-path gradients at the
             # 1e-3 .. 1e-2 level -- in the fp32 oracle just as much as here (see its own error
-            # against the fp64 run).  The single-layer tests above hold the 1e-4 bar.
-            check(n, p.grad, og[n].grad, tg[n].grad, 2e-2)
+            # against the fp64 run).  The single-layer tests above hold the 1e-4 bar.  A flipped
+            # sample moves single entries (max norm), hardly the gradient as a whole (2-norm):
+            # the 2-norm carries the tight bound, the max norm a loose one.
+            e2, y2 = rel_l2(p.grad, tg[n].grad), rel_l2(og[n].grad, tg[n].grad)
+            assert e2 <= max(5e-3, 5.0 * y2), f'{n}: l2 err {e2:.3e} (fp32 oracle: {y2:.3e})'
+            check(n, p.grad, og[n].grad, tg[n].grad, 5e-2)
 
 
 def test_fused_bf16_within_tolerance():
@@ -548,3 +552,79 @@ def test_maptrv2_decoder_stack_runs_config4():
     inter[-1].float().pow(2).mean().backward()
     assert torch.isfinite(bev.grad).all() and bev.grad.abs().sum() > 0
     assert torch.isfinite(query.grad).all()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_merged_projection_layout_matches_separate_tensors(dtype):
+    """The fused Functions take offsets and logits either as two tensors or as the column blocks
+    of ONE (bs, Nq, 3n) tensor (single GEMM over the concatenated weights, SURVEY.md section 8f
+    rank 1): same forward bit for bit, same gradients, and the merged gradient comes back in the
+    merged layout."""
+    import apollo_vision_net_b200.fused_ops as fo
+    import apollo_vision_net_b200.synthetic as syn
+    from oracle import geometry_oracle as G
+    g = torch.Generator().manual_seed(4)
+    # spatial cross-attention
+    bs, H, W, M, Dh, P, D = 2, 11, 13, 8, 32, 8, 4
+    levels = [(29, 50), (15, 25)]
+    L = len(levels)
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    shapes, starts = torch.tensor(shapes_l).to(DEV), torch.tensor(starts_l).to(DEV)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs, jitter=4.0, seed=2)
+    r3 = G.reference_points_3d(H, W, 8.0, D, bs=bs)
+    geo = fo.bev_point_sampling(r3.to(DEV), syn.PC_RANGE, l2i, img_shape[0], img_shape[1])
+    n = M * L * P
+    value = torch.randn(bs * 6, Nk, M, Dh, generator=g).to(dtype).to(DEV)
+    merged = torch.randn(bs, H * W, 3 * n, generator=g)
+    merged[..., :2 * n] *= 5.0
+    merged = merged.to(dtype).to(DEV)
+    go = torch.randn(bs, H * W, M * Dh, generator=g).to(dtype).to(DEV)
+
+    def run_sca(as_merged):
+        v = value.clone().requires_grad_(True)
+        mg = merged.clone().requires_grad_(True)
+        if as_merged:
+            out = fo.SpatialCrossAttnFunction.apply(v, shapes, starts, mg, None,
+                                                    geo.reference_points_cam, geo.mask_u8,
+                                                    geo.hit_bits, 6, W)
+        else:
+            out = fo.SpatialCrossAttnFunction.apply(
+                v, shapes, starts, mg[..., :2 * n].reshape(bs, H * W, M, L, P, 2),
+                mg[..., 2 * n:].reshape(bs, H * W, M, L * P), geo.reference_points_cam,
+                geo.mask_u8, geo.hit_bits, 6, W)
+        out.backward(go)
+        return out.detach(), v.grad, mg.grad
+
+    a, b = run_sca(True), run_sca(False)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert torch.equal(a[0], b[0])
+    assert a[2].shape == merged.shape
+    assert rel_err(a[1], b[1]) <= tol and rel_err(a[2], b[2]) <= tol
+
+    # temporal self-attention layout (queue of 2) with reference-point gradients
+    Q, Pt, Hb, Wb = 2, 4, 9, 7
+    Nq = Hb * Wb
+    tshape, tstart = torch.tensor([[Hb, Wb]]).to(DEV), torch.tensor([0]).to(DEV)
+    nt = M * Q * Pt
+    tv = torch.randn(Q, Nq, M, Dh, generator=g).to(dtype).to(DEV)
+    tm = (torch.randn(1, Nq, 3 * nt, generator=g) * 2.0).to(dtype).to(DEV)
+    ref = torch.rand(Q, Nq, 1, 2, generator=g).to(DEV)
+    tgo = torch.randn(1, Nq, M * Dh, generator=g).to(dtype).to(DEV)
+
+    def run_tsa(as_merged):
+        v = tv.clone().requires_grad_(True)
+        mg = tm.clone().requires_grad_(True)
+        r = ref.clone().requires_grad_(True)
+        if as_merged:
+            out = fo.QueueDeformAttnFunction.apply(v, tshape, tstart, mg, None, r, 3.0, Wb)
+        else:
+            out = fo.QueueDeformAttnFunction.apply(
+                v, tshape, tstart, mg[..., :2 * nt].reshape(1, Nq, M, Q, 1, Pt, 2),
+                mg[..., 2 * nt:].reshape(1, Nq, M, Q, Pt), r, 3.0, Wb)
+        out.backward(tgo)
+        return out.detach(), v.grad, mg.grad, r.grad
+
+    a, b = run_tsa(True), run_tsa(False)
+    assert torch.equal(a[0], b[0])
+    for x, y in zip(a[1:], b[1:]):
+        assert rel_err(x, y) <= tol

@@ -26,3 +26,13 @@ def rel_err(a, b):
     if b.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2: insensitive to a handful of outliers (used where a few flipped
+    samples move single entries of a deep gradient)."""
+    a = torch.as_tensor(np.asarray(a.detach().float().cpu()), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b.detach().float().cpu()), dtype=torch.float64)
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

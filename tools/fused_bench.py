@@ -80,7 +80,7 @@ def main():
         def fwd():
             _lib.call('sca_fwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
-                      geo.hit_bits.data_ptr(), slots.data_ptr(), None, 1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, st)
+                      geo.hit_bits.data_ptr(), slots.data_ptr(), None, 1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, 0, 0, st)
 
         def bwd():
             if half_acc:
@@ -88,7 +88,7 @@ def main():
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
-                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, acode, sws[16:].data_ptr() if half_acc else None, st)
+                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, 0, 0, acode, sws[16:].data_ptr() if half_acc else None, st)
         res['sca_fwd_us'] = round(timeit(fwd, flush, args.iters), 1)
         res['sca_bwd_us'] = round(timeit(bwd, flush, args.iters), 1)
         res['sca_samples'] = pairs * M * L * P
@@ -114,14 +114,14 @@ def main():
 
         def tfwd():
             _lib.call('tsa_fwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
-                      logits.data_ptr(), ref.data_ptr(), out.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, st)
+                      logits.data_ptr(), ref.data_ptr(), out.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, 0, 0, st)
 
         def tbwd():
             if half_acc:
                 _lib.call('grad_amax_scale', go.data_ptr(), go.numel(), code, sws.data_ptr(), st)
             _lib.call('tsa_bwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(), goff.data_ptr(),
-                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, acode,
+                      glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, 0, 0, acode,
                       sws[16:].data_ptr() if half_acc else None, st)
         res['tsa_fwd_us'] = round(timeit(tfwd, flush, args.iters), 1)
         res['tsa_bwd_us'] = round(timeit(tbwd, flush, args.iters), 1)
