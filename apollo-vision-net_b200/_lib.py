@@ -43,6 +43,8 @@ _SIGNATURES = {
     'ln_fwd': (_c_int, [_c_vp] * 6 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
     'colsum': (_c_int, [_c_vp] * 3 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
+    'ln_residual_fwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
+    'ln_bwd_dxsum': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
 }
 
 _lib = None

@@ -326,7 +326,18 @@ int ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* m
   if (rows == 0) return MSDA_OK;
   if (!x || !gamma || !beta || !y || !mean || !rstd) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_fwd: NULL pointer");
   return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
-                   dtype, static_cast<cudaStream_t>(stream));
+                   dtype, nullptr, nullptr, false, static_cast<cudaStream_t>(stream));
+}
+
+int ln_residual_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* sum_out,
+                    void* y, float* mean, float* rstd, int64_t rows, int C, float eps, int dtype,
+                    void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_residual_fwd: invalid sizes");
+  if (rows == 0) return MSDA_OK;
+  if (!x || !residual || !gamma || !beta || !sum_out || !y || !mean || !rstd)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_residual_fwd: NULL pointer");
+  return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
+                   dtype, residual, sum_out, false, static_cast<cudaStream_t>(stream));
 }
 
 int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
@@ -335,7 +346,19 @@ int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, 
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma_dbeta || !partial)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd: NULL pointer");
   return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
-                   dx, dgamma_dbeta, partial, rows, C, 0.f, dtype, static_cast<cudaStream_t>(stream));
+                   dx, dgamma_dbeta, partial, rows, C, 0.f, dtype, nullptr, nullptr, false,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int ln_bwd_dxsum(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
+                 void* dx, void* dgamma_dbeta_dxsum, float* partial, int64_t rows, int C, int dtype,
+                 void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd_dxsum: invalid sizes");
+  if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma_dbeta_dxsum || !partial)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd_dxsum: NULL pointer");
+  return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
+                   dx, dgamma_dbeta_dxsum, partial, rows, C, 0.f, dtype, nullptr, nullptr, true,
+                   static_cast<cudaStream_t>(stream));
 }
 
 int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,

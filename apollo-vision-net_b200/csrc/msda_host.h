@@ -67,7 +67,8 @@ int launch_tsa_bwd(const FusedProblem& fp, cudaStream_t st);
 int rowops_partial_rows();
 int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
-              long long rows, int C, float eps, int dtype, cudaStream_t st);
+              long long rows, int C, float eps, int dtype, const void* residual, void* sum_out,
+              bool dxsum, cudaStream_t st);
 int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype,
                   int out_dtype, cudaStream_t st);
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st);

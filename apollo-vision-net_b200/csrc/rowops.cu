@@ -57,11 +57,13 @@ __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __r
 }
 
 // One warp per row; every lane keeps its slice of the row (C / 32 elements, <= 32) in registers.
+// With `residual`: normalises s = x + residual, rounded to T first (bit-identical to a separate
+// add kernel followed by LayerNorm), and writes s to `sum_out` (may alias x) for the backward.
 template <typename T, int PER_LANE>
 __global__ void __launch_bounds__(kRowThreads)
-ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta,
-              T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd,
-              long long rows, int C, float eps) {
+ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ gamma,
+              const T* __restrict__ beta, T* sum_out, T* __restrict__ y, float* __restrict__ mean,
+              float* __restrict__ rstd, long long rows, int C, float eps) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
   const int lane = threadIdx.x & 31;
@@ -78,14 +80,35 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __r
 #pragma unroll
     for (int i = 0; i < VEC; ++i) bb[v * VEC + i] = t[i];
   }
+  // the loads of a warp's next row are issued before the arithmetic of the current one
+  constexpr int NVA = NV > 0 ? NV : 1;      // (NV == 0 instances are rejected at dispatch)
+  uint4 nx[NVA], nr[NVA];
+  auto fetch = [&](long long r) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      nx[v] = *reinterpret_cast<const uint4*>(x + r * C + (v * 32 + lane) * VEC);   // x may alias sum_out
+      if (residual != nullptr) nr[v] = ldg128(residual + r * C + (v * 32 + lane) * VEC);
+    }
+  };
+  if (warp < rows) fetch(warp);
   for (long long r = warp; r < rows; r += nwarp) {
-    const T* xr = x + r * C;
+    uint4 cx[NVA], cr[NVA];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { cx[v] = nx[v]; cr[v] = nr[v]; }
+    if (r + nwarp < rows) fetch(r + nwarp);
     float f[PER_LANE];
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       float t[VEC];
-      Vec16IO<T>::load(xr + (v * 32 + lane) * VEC, t);
+      Vec16<T>::unpack(cx[v], t);
+      if (residual != nullptr) {
+        float rr[VEC];
+        Vec16<T>::unpack(cr[v], rr);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) t[i] = to_f32<T>(from_f32<T>(t[i] + rr[i]));
+        Vec16IO<T>::store(sum_out + r * C + (v * 32 + lane) * VEC, t);
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) { f[v * VEC + i] = t[i]; s += t[i]; }
     }
@@ -107,18 +130,22 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ gamma, const T* __r
 }
 
 // dx per row; per-CTA partial sums of dgamma / dbeta into `partial` (gridDim.x, 2, C) fp32.
-template <typename T, int PER_LANE>
-__global__ void __launch_bounds__(kRowThreads)
+// DXSUM: additionally the column sums of dx (as rounded to T) -- the bias gradient of a Linear
+// layer whose output (plus a residual) this LayerNorm normalised; output rows: d gamma, d beta,
+// sum of dx.
+template <typename T, int PER_LANE, bool DXSUM>
+__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? 3 : 1)
 ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
               float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
-  extern __shared__ float sm[];                       // [warps][2][C]
+  constexpr int NOUT = DXSUM ? 3 : 2;
+  extern __shared__ float sm[];                       // [warps][NOUT][C]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + wid;
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
-  float g[PER_LANE], dg[PER_LANE], db[PER_LANE];
+  float g[PER_LANE], dg[PER_LANE], db[PER_LANE], dsum[DXSUM ? PER_LANE : 1];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     float t[VEC];
@@ -128,15 +155,34 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   }
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < (DXSUM ? PER_LANE : 1); ++i) dsum[i] = 0.f;
+  constexpr int NVA = NV > 0 ? NV : 1;
+  uint4 nx[NVA], nd[NVA];
+  float nmu = 0.f, nrs = 0.f;
+  auto fetch = [&](long long r) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      nx[v] = ldg128(x + r * C + (v * 32 + lane) * VEC);
+      nd[v] = ldg128(dy + r * C + (v * 32 + lane) * VEC);
+    }
+    nmu = __ldg(mean + r);
+    nrs = __ldg(rstd + r);
+  };
+  if (warp < rows) fetch(warp);
   for (long long r = warp; r < rows; r += nwarp) {
-    const float mu = mean[r], rs = rstd[r];
+    const float mu = nmu, rs = nrs;
+    uint4 cx[NVA], cd[NVA];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { cx[v] = nx[v]; cd[v] = nd[v]; }
+    if (r + nwarp < rows) fetch(r + nwarp);
     float xh[PER_LANE], gd[PER_LANE];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       float tx[VEC], td[VEC];
-      Vec16IO<T>::load(x + r * C + (v * 32 + lane) * VEC, tx);
-      Vec16IO<T>::load(dy + r * C + (v * 32 + lane) * VEC, td);
+      Vec16<T>::unpack(cx[v], tx);
+      Vec16<T>::unpack(cd[v], td);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int k = v * VEC + i;
@@ -157,12 +203,13 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
       for (int i = 0; i < VEC; ++i) {
         const int k = v * VEC + i;
         t[i] = rs * (gd[k] - s1 - xh[k] * s2);
+        if (DXSUM) dsum[k] += to_f32<T>(from_f32<T>(t[i]));      // what a column sum of dx would read
       }
       Vec16IO<T>::store(dx + r * C + (v * 32 + lane) * VEC, t);
     }
   }
   // CTA reduction of the per-warp partials, then one row of partials per CTA
-  float* mine = sm + (size_t)wid * 2 * C;
+  float* mine = sm + (size_t)wid * NOUT * C;
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -170,15 +217,16 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
       const int c = (v * 32 + lane) * VEC + i;
       mine[c] = dg[v * VEC + i];
       mine[C + c] = db[v * VEC + i];
+      if (DXSUM) mine[2 * C + c] = dsum[v * VEC + i];
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += kRowThreads) {
+  for (int c = threadIdx.x; c < NOUT * C; c += kRowThreads) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < kRowThreads / 32; ++w) s += sm[(size_t)w * 2 * C + c];
+    for (int w = 0; w < kRowThreads / 32; ++w) s += sm[(size_t)w * NOUT * C + c];
     atomicAdd(ws + kWsHeaderFloats + c, s);
   }
-  finalize_columns<T>(ws, dgamma_dbeta, 2 * C);
+  finalize_columns<T>(ws, dgamma_dbeta, NOUT * C);
 }
 
 // Column sums of a (rows, C) matrix: stage 1, per-CTA partials (gridDim.x, C) fp32.  A thread
@@ -234,22 +282,28 @@ static int row_grid() {
 
 int rowops_partial_rows() { return row_grid(); }
 
+// Forward: `residual` / `sum_out` optional (both or neither).  Backward: `dxsum` selects the
+// three-row output (d gamma, d beta, column sums of dx).
 template <typename T, int PER_LANE>
 static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
                      float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
-                     float eps, cudaStream_t st) {
+                     float eps, const void* residual, void* sum_out, bool dxsum, cudaStream_t st) {
   const long long need = (rows + kRowThreads / 32 - 1) / (kRowThreads / 32);
   const int grid = (int)(need < row_grid() ? need : row_grid());
   if (grid <= 0) return MSDA_OK;
   if (!bwd) {
     ln_fwd_kernel<T, PER_LANE><<<grid, kRowThreads, 0, st>>>(
-        static_cast<const T*>(x), static_cast<const T*>(gamma), static_cast<const T*>(beta),
-        static_cast<T*>(y), mean, rstd, rows, C, eps);
+        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(gamma),
+        static_cast<const T*>(beta), static_cast<T*>(sum_out), static_cast<T*>(y), mean, rstd, rows, C, eps);
     count_launch();
     return check_launch("ln_fwd");
   }
-  const size_t smem = (size_t)(kRowThreads / 32) * 2 * C * sizeof(float);
-  ln_bwd_kernel<T, PER_LANE><<<row_grid(), kRowThreads, smem, st>>>(
+  const size_t smem = (size_t)(kRowThreads / 32) * (dxsum ? 3 : 2) * C * sizeof(float);
+  auto kfn = dxsum ? ln_bwd_kernel<T, PER_LANE, true> : ln_bwd_kernel<T, PER_LANE, false>;
+  if (smem + 1024 > 48 * 1024 &&        // (+ the kernel's static shared memory)
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return set_error(MSDA_ERR_CUDA, "ln_bwd: cannot reserve %zu bytes of shared memory", smem);
+  kfn<<<row_grid(), kRowThreads, smem, st>>>(
       static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<const T*>(gamma), mean, rstd,
       static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C);
   count_launch();
@@ -259,17 +313,20 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
 template <typename T>
 static int ln_dispatch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
                        float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
-                       float eps, cudaStream_t st) {
+                       float eps, const void* residual, void* sum_out, bool dxsum, cudaStream_t st) {
   constexpr int VEC = Vec16<T>::N;
   if (C % (32 * VEC) != 0 || C / 32 > 32)
     return set_error(MSDA_ERR_UNSUPPORTED, "layer_norm: C=%d must be a multiple of %d and <= 1024", C, 32 * VEC);
+#define LN_CASE(n) case n: return ln_launch<T, n>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, \
+                                                  rows, C, eps, residual, sum_out, dxsum, st)
   switch (C / 32) {
-    case 4: return ln_launch<T, 4>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
-    case 8: return ln_launch<T, 8>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
-    case 16: return ln_launch<T, 16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
-    case 32: return ln_launch<T, 32>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, rows, C, eps, st);
+    LN_CASE(4);
+    LN_CASE(8);
+    LN_CASE(16);
+    LN_CASE(32);
     default: break;
   }
+#undef LN_CASE
   return set_error(MSDA_ERR_UNSUPPORTED, "layer_norm: C=%d not supported (128, 256, 512 or 1024)", C);
 }
 
@@ -355,12 +412,16 @@ int launch_unscale_cast(const void* acc16, void* out, const float* scale, long l
 
 int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
-              long long rows, int C, float eps, int dtype, cudaStream_t st) {
+              long long rows, int C, float eps, int dtype, const void* residual, void* sum_out,
+              bool dxsum, cudaStream_t st) {
   if (dtype == MSDA_F32)
-    return ln_dispatch<float>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
+    return ln_dispatch<float>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps,
+                              residual, sum_out, dxsum, st);
   if (dtype == MSDA_BF16)
-    return ln_dispatch<__nv_bfloat16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
-  return ln_dispatch<__half>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps, st);
+    return ln_dispatch<__nv_bfloat16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C,
+                                      eps, residual, sum_out, dxsum, st);
+  return ln_dispatch<__half>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps,
+                             residual, sum_out, dxsum, st);
 }
 
 template <typename T>

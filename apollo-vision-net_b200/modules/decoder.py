@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from ..fused_ops import QueueDeformAttnFunction
 from ..registry import ATTENTION
-from .deform_common import DeformAttnBase, msda_apply
+from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
 def inverse_sigmoid(x, eps=1e-5):
@@ -34,7 +34,7 @@ class CustomMSDeformableAttention(DeformAttnBase):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, flag='decoder', **kwargs):
+                level_start_index=None, flag='decoder', post_norm=None, **kwargs):
         if 'residual' in kwargs and identity is None:      # mmcv's deprecated_api_warning alias
             identity = kwargs.pop('residual')
         if value is None:
@@ -78,7 +78,4 @@ class CustomMSDeformableAttention(DeformAttnBase):
             raise ValueError('Last dim of reference_points must be 2 or 4, '
                              f'but get {reference_points.shape[-1]} instead.')
 
-        output = self.output_proj(output.to(query.dtype))
-        if not self.batch_first:
-            output = output.permute(1, 0, 2)
-        return self.dropout(output) + identity
+        return finish_block(self, output.to(query.dtype), identity, post_norm)

@@ -9,7 +9,7 @@ import torch.nn as nn
 from ..multi_scale_deformable_attn_function import (MultiScaleDeformableAttnFunction_fp16,
                                                     MultiScaleDeformableAttnFunction_fp32)
 from ..registry import BaseModule, constant_init, xavier_init
-from ..rowops import Linear, linear
+from ..rowops import Linear, linear, linear_add_layernorm
 
 
 def _is_power_of_2(n):
@@ -83,6 +83,23 @@ class DeformAttnBase(BaseModule):
         w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
         b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
         return linear(query, w, b)
+
+
+def finish_block(mod, output, identity, post_norm=None):
+    """Tail of an attention block: ``dropout(output_proj(output)) + identity`` (reference
+    temporal_self_attention.py:285-289, spatial_cross_attention.py:171-173, decoder.py:353-358),
+    optionally followed by the layer's next LayerNorm (``post_norm``).  With the norm given and the
+    dropout inactive the projection, the residual add and the norm run as one fused autograd node
+    (:func:`rowops.linear_add_layernorm`); the result is then already normalised."""
+    batch_first = getattr(mod, 'batch_first', True)
+    drop = mod.dropout
+    if post_norm is not None and batch_first and not (mod.training and drop.p > 0):
+        return linear_add_layernorm(output, mod.output_proj, identity, post_norm)
+    output = mod.output_proj(output)
+    if not batch_first:
+        output = output.permute(1, 0, 2)
+    out = drop(output) + identity
+    return out if post_norm is None else post_norm(out)
 
 
 def msda_apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..fused_ops import BevGeometry, bev_point_sampling
-from ..rowops import LayerNorm, Linear
+from ..rowops import LayerNorm, Linear, linear_add_layernorm
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
                         build_transformer_layer)
 
@@ -45,11 +45,18 @@ class FFN(BaseModule):
         self.layers = nn.Sequential(*layers)
         self.add_identity = add_identity
 
-    def forward(self, x, identity=None):
+    def forward(self, x, identity=None, post_norm=None):
+        """``post_norm``: the layer's next LayerNorm; with it, two fcs and inactive dropout the last
+        Linear, the identity add and the norm run as one fused node (result already normalised)."""
+        res = x if identity is None else identity
+        last_drop = self.layers[-1]
+        if (post_norm is not None and self.add_identity and len(self.layers) == 3 and
+                not (self.training and last_drop.p > 0)):
+            return linear_add_layernorm(self.layers[0](x), self.layers[1], res, post_norm)
         out = self.layers(x)
-        if not self.add_identity:
-            return out
-        return (x if identity is None else identity) + out
+        if self.add_identity:
+            out = res + out
+        return out if post_norm is None else post_norm(out)
 
 
 @TRANSFORMER_LAYER.register_module()
@@ -102,13 +109,26 @@ class BEVFormerLayer(BaseModule):
         if tsa_shapes is None:
             tsa_shapes = (torch.tensor([[bev_h, bev_w]], device=query.device),
                           torch.tensor([0], device=query.device))
-        for op in self.operation_order:
+        # post-norm layers hand the LayerNorm that follows a block to the block, which fuses it
+        # with its output projection and residual add; the 'norm' step is then skipped
+        order = self.operation_order
+        fused_norm = False
+        for i, op in enumerate(order):
+            post = None
+            if op != 'norm' and not self.pre_norm and i + 1 < len(order) and order[i + 1] == 'norm':
+                post = self.norms[norm_index]
+            if op == 'norm' and fused_norm:
+                fused_norm = False
+                norm_index += 1
+                continue
+            fused_norm = post is not None
             if op == 'self_attn':
                 query = self.attentions[attn_index](
                     query, prev_bev, prev_bev, identity if self.pre_norm else None,
                     query_pos=bev_pos, key_pos=bev_pos, key_padding_mask=query_key_padding_mask,
                     reference_points=ref_2d, spatial_shapes=tsa_shapes[0],
-                    level_start_index=tsa_shapes[1], bev_h=bev_h, bev_w=bev_w, **kwargs)
+                    level_start_index=tsa_shapes[1], bev_h=bev_h, bev_w=bev_w, post_norm=post,
+                    **kwargs)
                 attn_index += 1
                 identity = query
             elif op == 'norm':
@@ -120,11 +140,13 @@ class BEVFormerLayer(BaseModule):
                     key_pos=key_pos, reference_points=ref_3d,
                     reference_points_cam=reference_points_cam, mask=mask,
                     key_padding_mask=key_padding_mask, spatial_shapes=spatial_shapes,
-                    level_start_index=level_start_index, bev_h=bev_h, bev_w=bev_w, **kwargs)
+                    level_start_index=level_start_index, bev_h=bev_h, bev_w=bev_w, post_norm=post,
+                    **kwargs)
                 attn_index += 1
                 identity = query
             elif op == 'ffn':
-                query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
+                query = self.ffns[ffn_index](query, identity if self.pre_norm else None,
+                                             post_norm=post)
                 ffn_index += 1
         return query
 

@@ -19,8 +19,8 @@ import torch.nn as nn
 
 from ..fused_ops import SpatialCrossAttnFunction, hit_bits_from_mask
 from ..registry import ATTENTION, BaseModule, build_attention, xavier_init
-from ..rowops import Linear
-from .deform_common import DeformAttnBase, msda_apply
+from ..rowops import Linear, linear_add_layernorm
+from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
 @ATTENTION.register_module()
@@ -116,7 +116,7 @@ class SpatialCrossAttention(BaseModule):
     def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
                 reference_points=None, spatial_shapes=None, reference_points_cam=None,
                 bev_mask=None, level_start_index=None, flag='encoder', bev_geometry=None,
-                bev_h=None, bev_w=None, **kwargs):
+                bev_h=None, bev_w=None, post_norm=None, **kwargs):
         """query (bs, HW, C); key = value (num_cam, Nk, bs, C); reference_points_cam
         (num_cam, bs, HW, D, 2); bev_mask (num_cam, bs, HW, D) -> (bs, HW, C).
 
@@ -149,5 +149,8 @@ class SpatialCrossAttention(BaseModule):
         slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, coords, None,
                                                reference_points_cam, mask_u8, hit_bits,
                                                self.num_cams, self._grid_w(bev_h, bev_w, num_query))
-        slots = self.output_proj(slots.to(query.dtype))
-        return self.dropout(slots) + inp_residual
+        # (the residual is added without a permute whatever batch_first says, reference :171-173)
+        if post_norm is not None and not (self.training and self.dropout.p > 0):
+            return linear_add_layernorm(slots.to(query.dtype), self.output_proj, inp_residual, post_norm)
+        out = self.dropout(self.output_proj(slots.to(query.dtype))) + inp_residual
+        return out if post_norm is None else post_norm(out)

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from ..fused_ops import QueueDeformAttnFunction
 from ..registry import ATTENTION
-from .deform_common import DeformAttnBase, msda_apply
+from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
 @ATTENTION.register_module()
@@ -33,7 +33,7 @@ class TemporalSelfAttention(DeformAttnBase):
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
                 level_start_index=None, flag='decoder', bev_h=None, bev_w=None, row_slice=None,
-                **kwargs):
+                post_norm=None, **kwargs):
         """query (bs, HW, C) [batch_first]; value (bs*2, HW, C) = stack([prev_bev, bev], 1) or
         None (first frame); reference_points (bs*2, HW, L, 2) -> (bs, HW, C)."""
         if value is None:
@@ -88,7 +88,4 @@ class TemporalSelfAttention(DeformAttnBase):
             raise ValueError('Last dim of reference_points must be 2 or 4, '
                              f'but get {reference_points.shape[-1]} instead.')
 
-        output = self.output_proj(output.to(query.dtype))
-        if not self.batch_first:
-            output = output.permute(1, 0, 2)
-        return self.dropout(output) + identity
+        return finish_block(self, output.to(query.dtype), identity, post_norm)

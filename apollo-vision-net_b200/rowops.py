@@ -89,6 +89,70 @@ class LayerNorm(nn.LayerNorm):
         return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
 
 
+class LinearAddLayerNormFunction(Function):
+    """y = LayerNorm(x W^T + b + residual): the post-norm tail of an attention / FFN block as one
+    autograd node.  Forward: cuBLAS GEMM, then one kernel for the residual add and the
+    normalisation (the sum overwrites the GEMM output and is what the backward re-reads).
+    Backward: one kernel for d sum, d gamma, d beta AND the bias gradient (column sums of d sum),
+    then the two GEMMs; d residual is d sum itself."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, x, weight, bias, residual, gamma, beta, eps):
+        C = weight.shape[0]
+        x2 = x.reshape(-1, x.shape[-1])
+        rows = x2.shape[0]
+        res2 = residual.reshape(rows, C).contiguous()
+        lin = torch.empty((rows, C), dtype=x.dtype, device=x.device)
+        torch.addmm(bias, x2, weight.t(), out=lin)
+        y = torch.empty_like(lin)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        g, b = gamma.contiguous(), beta.contiguous()
+        with torch.cuda.device(x.device):
+            _lib.call('ln_residual_fwd', lin.data_ptr(), res2.data_ptr(), g.data_ptr(), b.data_ptr(),
+                      lin.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
+                      float(eps), _DTYPE_CODE[x.dtype], _stream_ptr(x))
+        ctx.save_for_backward(x2, weight, lin, g, mean, rstd)
+        ctx.shapes = (x.shape, residual.shape)
+        return y.view(residual.shape)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, dy):
+        x2, weight, s, g, mean, rstd = ctx.saved_tensors
+        rows, C = s.shape
+        dy2 = dy.reshape(rows, C).to(s.dtype).contiguous()
+        ds = torch.empty_like(s)
+        out3 = torch.empty((3, C), dtype=s.dtype, device=s.device)
+        nrows = _lib.lib().rowops_workspace_rows()
+        ws = _workspace(s.device, nrows * 3 * C)
+        with torch.cuda.device(s.device):
+            _lib.call('ln_bwd_dxsum', s.data_ptr(), dy2.data_ptr(), g.data_ptr(), mean.data_ptr(),
+                      rstd.data_ptr(), ds.data_ptr(), out3.data_ptr(), ws.data_ptr(), rows, C,
+                      _DTYPE_CODE[s.dtype], _stream_ptr(s))
+        x_shape, res_shape = ctx.shapes
+        dx = (ds @ weight).view(x_shape) if ctx.needs_input_grad[0] else None
+        dw = ds.t() @ x2 if ctx.needs_input_grad[1] else None
+        return dx, dw, out3[2], ds.view(res_shape), out3[0], out3[1], None
+
+
+def linear_add_layernorm(x, linear_mod, residual, norm):
+    """``norm(linear_mod(x) + residual)`` through :class:`LinearAddLayerNormFunction` when the
+    tensors qualify (CUDA, one dtype, supported width, affine LayerNorm over the last dim with a
+    bias-carrying Linear); the plain composition otherwise."""
+    w, b = linear_mod.weight, linear_mod.bias
+    ok = (isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1 and b is not None and
+          x.is_cuda and x.dtype == w.dtype == residual.dtype and
+          residual.shape[-1] == w.shape[0] and residual.numel() == x.numel() // x.shape[-1] * w.shape[0] and
+          norm.weight is not None and norm.bias is not None and
+          _ln_supported(residual, norm.weight, norm.bias))
+    if not ok:
+        return norm(linear_mod(x) + residual)
+    return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps)
+
+
 def column_sum(x2, out_dtype=None):
     """Sum over the rows of a (rows, C) CUDA matrix (fp32 accumulation)."""
     rows, C = x2.shape

@@ -234,6 +234,20 @@ int ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* m
            int64_t rows, int C, float eps, int dtype, void* stream);
 int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
            void* dx, void* dgamma_dbeta, float* partial, int64_t rows, int C, int dtype, void* stream);
+/* Post-norm block "y = LayerNorm(linear_out + residual)" of a transformer layer
+ * (custom_base_transformer_layer.py:142-161 applied after spatial_cross_attention.py:173 /
+ * temporal_self_attention.py:289 / the FFN's identity add) in one pass each way:
+ *   ln_residual_fwd: s = (dtype)(x + residual) is written to sum_out (may alias x) and
+ *     normalised; bit-identical to an add kernel followed by ln_fwd.
+ *   ln_bwd_dxsum: ln_bwd that also returns the column sums of dx -- the bias gradient of the Linear
+ *     layer that produced x -- as a third row: dgamma_dbeta_dxsum is (3, C), partial holds
+ *     64 + 3 * C floats.                                                                       */
+int ln_residual_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
+                    void* sum_out, void* y, float* mean, float* rstd, int64_t rows, int C, float eps,
+                    int dtype, void* stream);
+int ln_bwd_dxsum(const void* x, const void* dy, const void* gamma, const float* mean,
+                 const float* rstd, void* dx, void* dgamma_dbeta_dxsum, float* partial, int64_t rows,
+                 int C, int dtype, void* stream);
 int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,
            void* stream);
 

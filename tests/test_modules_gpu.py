@@ -628,3 +628,41 @@ def test_merged_projection_layout_matches_separate_tensors(dtype):
     assert torch.equal(a[0], b[0])
     for x, y in zip(a[1:], b[1:]):
         assert rel_err(x, y) <= tol
+
+
+@pytest.mark.parametrize('dtype,rows,Cin,C', [(torch.float32, 1000, 256, 256), (torch.bfloat16, 4099, 512, 256),
+                                              (torch.float16, 77, 256, 512), (torch.float32, 1, 128, 128)])
+def test_linear_add_layernorm_matches_composition(dtype, rows, Cin, C):
+    """The fused post-norm tail y = LN(x W^T + b + residual) against the same three steps run
+    separately (Linear, add, LayerNorm kernels): identical forward, gradients within rounding,
+    and against plain torch in fp32."""
+    import apollo_vision_net_b200.rowops as ro
+    g = torch.Generator().manual_seed(31)
+    lin = ro.Linear(Cin, C).to(DEV).to(dtype)
+    norm = ro.LayerNorm(C).to(DEV).to(dtype)
+    with torch.no_grad():
+        norm.weight.copy_((torch.rand(C, generator=g) + 0.5).to(dtype))
+        norm.bias.copy_(torch.randn(C, generator=g).to(dtype))
+    x = torch.randn(2, rows, Cin, generator=g).to(dtype).to(DEV)
+    res = torch.randn(2, rows, C, generator=g).to(dtype).to(DEV)
+    go = torch.randn(2, rows, C, generator=g).to(dtype).to(DEV)
+
+    def run(fused):
+        for p in list(lin.parameters()) + list(norm.parameters()):
+            p.grad = None
+        x1, r1 = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        y = ro.linear_add_layernorm(x1, lin, r1, norm) if fused else norm(lin(x1) + r1)
+        y.backward(go)
+        return [y.detach(), x1.grad, r1.grad, lin.weight.grad, lin.bias.grad, norm.weight.grad,
+                norm.bias.grad]
+
+    a, b = run(True), run(False)
+    assert torch.equal(a[0], b[0])
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for u, v in zip(a[1:], b[1:]):
+        assert u.shape == v.shape and rel_err(u, v) <= tol
+    if dtype == torch.float32:
+        x1, r1 = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        y = torch.nn.functional.layer_norm(torch.nn.functional.linear(x1, lin.weight, lin.bias) + r1,
+                                           (C,), norm.weight, norm.bias, norm.eps)
+        assert rel_err(a[0], y) <= 1e-5
