@@ -1,0 +1,89 @@
+// What does the value layout / lane mapping buy for the bilinear gather and the grad_value scatter?
+//   map A: 4 lanes per (query, head) row, every lane touches all four corners (4 x 16 B)      [current]
+//   map B: 8 lanes per row, lane half h touches corners (x0+h, y0) and (x0+h, y0+1) (2 x 16 B)
+//   layout P: pixel-major [Nk][M][32] bf16 (x-neighbours 512 B apart)                        [current]
+//   layout H: head-major  [M][Nk][32] bf16 (x-neighbours contiguous: one 128 B line when x0 is even)
+// Locality model: a warp's rows are the 8 heads of one BEV query; samples fall within +-8 px of the
+// query's projection; consecutive queries project 1 px apart.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gather_bench gather_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+constexpr int H = 116, W = 200, M = 8, NK = H * W, SAMPLES = 32;
+
+__device__ __forceinline__ uint32_t hash(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x;
+}
+__device__ __forceinline__ size_t addr(int layout, int x, int y, int m) {   // byte offset of (pixel, head)
+  const size_t k = (size_t)y * W + x;
+  return layout == 0 ? (k * M + m) * 64 : ((size_t)m * NK + k) * 64;
+}
+
+template <int MAP, bool RED>
+__global__ void __launch_bounds__(256) k(char* base, uint32_t* out, int nq, int layout) {
+  constexpr int LPR = MAP == 0 ? 4 : 8;                  // lanes per row
+  const int tid = blockIdx.x * 256 + threadIdx.x;
+  const int row = tid / LPR, lr = tid % LPR;
+  const int chunk = lr % 4, half = lr / 4;
+  const int q = row / M, m = row % M;
+  if (q >= nq) return;
+  const int cx = 8 + (q % 180), cy = 8 + (q / 180) % 96;
+  uint32_t acc = 0;
+#pragma unroll 2
+  for (int s = 0; s < SAMPLES; ++s) {
+    const uint32_t r = hash(row * 977u + s);
+    const int x0 = cx + (int)(r & 15) - 8, y0 = cy + (int)((r >> 4) & 15) - 8;
+    if (MAP == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        char* p = base + addr(layout, x0 + (c & 1), y0 + (c >> 1), m) + chunk * 16;
+        if (RED) asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%1,%1,%1};" :: "l"(p), "r"(0x3c003c00u) : "memory");
+        else { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        char* p = base + addr(layout, x0 + half, y0 + c, m) + chunk * 16;
+        if (RED) asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%1,%1,%1};" :: "l"(p), "r"(0x3c003c00u) : "memory");
+        else { uint4 v = __ldg(reinterpret_cast<const uint4*>(p)); acc ^= v.x ^ v.y ^ v.z ^ v.w; }
+      }
+    }
+  }
+  if (!RED) out[tid] = acc;
+}
+
+template <int MAP, bool RED> float run(char* base, uint32_t* out, int nq, int layout) {
+  const int LPR = MAP == 0 ? 4 : 8;
+  const int blocks = (nq * M * LPR + 255) / 256;
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e9f;
+  for (int it = 0; it < 4; ++it) {
+    cudaMemsetAsync(out, 0, 64u << 20);                  // also evicts part of L2 between runs
+    cudaEventRecord(a);
+    k<MAP, RED><<<blocks, 256>>>(base, out, nq, layout);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); if (it > 0 && ms < best) best = ms;
+  }
+  return best * 1e3f;
+}
+
+int main() {
+  const int nq = 45179;                                   // (camera, query) pairs of the base config
+  char* base; uint32_t* out;
+  cudaMalloc(&base, (size_t)NK * M * 64 + 4096); cudaMemset(base, 0, (size_t)NK * M * 64);
+  cudaMalloc(&out, 64u << 20);
+  printf("corner accesses: %.1f M\n", nq * 8.0 * SAMPLES * 4 / 1e6);
+  printf("gather  A/P (current)  %7.1f us\n", run<0, false>(base, out, nq, 0));
+  printf("gather  B/P            %7.1f us\n", run<1, false>(base, out, nq, 0));
+  printf("gather  A/H            %7.1f us\n", run<0, false>(base, out, nq, 1));
+  printf("gather  B/H (proposed) %7.1f us\n", run<1, false>(base, out, nq, 1));
+  printf("scatter A/P (current)  %7.1f us\n", run<0, true>(base, out, nq, 0));
+  printf("scatter B/P            %7.1f us\n", run<1, true>(base, out, nq, 0));
+  printf("scatter A/H            %7.1f us\n", run<0, true>(base, out, nq, 1));
+  printf("scatter B/H (proposed) %7.1f us\n", run<1, true>(base, out, nq, 1));
+  cudaError_t e = cudaDeviceSynchronize();
+  printf("status: %s\n", cudaGetErrorString(e));
+  return 0;
+}
