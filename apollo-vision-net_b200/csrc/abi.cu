@@ -272,10 +272,16 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
             const uint32_t* hit_bits, const void* g_slots, void* g_value, void* g_offsets,
             void* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
             int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride, int64_t logits_stride,
-            int accum_dtype, const float* accum_scale, void* stream) {
+            int accum_dtype, const float* accum_scale, void* g_value_tail, int tail_copies, int tail_pixels,
+            void* stream) {
   FusedProblem f;
   f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
+  if (g_value_tail && tail_copies > 0) {
+    if (!f.acc_half || tail_pixels <= 0 || tail_pixels > Nk || tail_copies > 64)
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "sca_bwd: tail replicas need the fp16 accumulator and 0 < tail_pixels <= Nk");
+    f.g_tail = g_value_tail; f.tail_copies = tail_copies; f.tail_px = tail_pixels;
+  }
   f.value = value; f.shapes = shapes; f.starts = starts; f.offsets = offsets; f.logits = logits;
   f.ref = ref_cam; f.bev_mask = bev_mask; f.hit_bits = hit_bits; f.g_out = g_slots;
   f.g_value = g_value; f.g_offsets = g_offsets; f.g_logits = g_logits;
@@ -373,11 +379,17 @@ int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream
   return launch_grad_scale(g, n, dtype, ws, static_cast<cudaStream_t>(stream));
 }
 
-int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype, void* stream) {
+int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
+                 const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems, void* stream) {
   if (n < 0 || (n > 0 && (!acc_f16 || !out || !scale)))
     return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: bad argument");
+  if (tail && tail_copies > 0 &&
+      (map_elems <= 0 || tail_elems <= 0 || tail_elems > map_elems || n % map_elems != 0 || map_elems % 8 != 0 ||
+       tail_elems % 8 != 0))
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: inconsistent tail replica sizes");
   if (n == 0) return MSDA_OK;
-  return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, static_cast<cudaStream_t>(stream));
+  return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, tail, tail_copies, map_elems, tail_elems,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

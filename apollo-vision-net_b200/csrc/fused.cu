@@ -77,6 +77,12 @@ struct FusedArgs {
   void* g_value;               // fp32 accumulator, or fp16 (scaled by *acc_scale) when acc_half
   const float* acc_scale;
   int acc_half;
+  // fp16 accumulator only: the LAST `tail_px` pixels of every value map (the coarse pyramid levels,
+  // whose slots receive hundreds of updates each) have `tail_copies` extra zero-filled replicas
+  // (tail_copies, batch, tail_px, M, Dh); a CTA adds into replica blockIdx % (tail_copies + 1)
+  // (0 = the main buffer), which divides the number of roundings a slot's running sum sees.
+  void* g_tail;
+  int tail_copies, tail_px;
   void* g_offsets;             // CT
   void* g_logits;
   int bs, groups, Nk, M, Dh, L, P, D, Nq;
@@ -145,6 +151,15 @@ template <> __device__ __forceinline__ void store_coord4<__half>(__half* dst, co
   *reinterpret_cast<uint2*>(dst) = make_uint2(Vec16<__half>::pack2(v.x, v.y), Vec16<__half>::pack2(v.z, v.w));
 }
 
+// a / b given y = RN(1 / b): one Newton step on the quotient (Markstein) -- the correctly rounded
+// fp32 quotient for the small integer divisors (map widths / heights) used here, i.e. bit-identical
+// to the reference's `sampling_offsets / offset_normalizer`, at 3 FMA-pipe instructions.
+__device__ __forceinline__ float div_by(float a, float b, float y) {
+  const float q = a * y;
+  const float r = fmaf(-q, b, a);
+  return fmaf(r, y, q);
+}
+
 // Stage one row, executed by the row's TPH lanes (all lanes of the warp take part in the
 // shuffles; `live` gates the memory traffic).  raw offsets -> off / (W_l, H_l) in `so`;
 // raw logits -> softmax per LP-long segment in `sw`.
@@ -158,9 +173,10 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
     for (int base = 0; base < S; base += a.P) {       // one level of one segment at a time
       const int l = (int)(s_meta[base] & 0xffffu);
       const float iw = lv.inv_w[l], ih = lv.inv_h[l];
+      const float wf = (float)lv.t.w[l], hf = (float)lv.t.h[l];
       for (int s = base + chunk; s < base + a.P; s += TPH) {
         const float2 o = load_coord2<CT>(g_off + 2 * s);
-        *reinterpret_cast<float2*>(so + 2 * s) = make_float2(o.x * iw, o.y * ih);
+        *reinterpret_cast<float2*>(so + 2 * s) = make_float2(div_by(o.x, wf, iw), div_by(o.y, hf, ih));
       }
     }
   }
@@ -442,6 +458,7 @@ fused_bwd_kernel(const FusedArgs a) {
   constexpr int V2 = VEC / 2;
   constexpr int ROWS = kFusedThreads / TPH;
   constexpr int SC = VEC / 4;                          // scatter instructions per corner
+  constexpr unsigned ES_ACC = sizeof(T);               // byte offsets of the records are in units of T
   __shared__ FusedLevels lv;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int LP = a.L * a.P;
@@ -522,6 +539,13 @@ fused_bwd_kernel(const FusedArgs a) {
       // channels in their natural order, scaled by a power of two chosen from max|g_out|
       __half* ghead16 = static_cast<__half*>(a.g_value) + head_off + chunk * VEC;
       const float acc_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
+      // replica of the accumulator's coarse tail this CTA adds into (see FusedArgs::g_tail)
+      const int replica = (ACC_HALF && a.tail_copies > 0) ? (int)(blockIdx.x % (unsigned)(a.tail_copies + 1)) : 0;
+      const unsigned tail_from = replica > 0 ? (unsigned)(a.Nk - a.tail_px) * (unsigned)pix_stride * ES_ACC
+                                             : 0xffffffffu;      // byte offset inside a value map
+      const size_t tail_map = (size_t)a.tail_px * pix_stride;    // elements per map in a replica
+      __half* tail16 = static_cast<__half*>(a.g_tail) + head_off + chunk * VEC;
+      char* acc_tail = nullptr;     // set per value map: replica base minus tail_from (SCA only)
 
       // 16-bit value: the dot products take g_out straight from its packed words (FHFMA, exact
       // products) and the 1 / count factor is applied to the per-sample totals instead
@@ -579,8 +603,10 @@ fused_bwd_kernel(const FusedArgs a) {
         const uint4 u11 = ldg128(vb + o11);
         if constexpr (ACC_HALF) {
           // gh = fp16(g * scale) per row; one HMUL2 per channel pair, one predicated 16-byte
-          // reduction per corner (skipped where the weight is zero)
+          // reduction per corner (skipped where the weight is zero); corners in the coarse tail
+          // of the map go to this CTA's replica
           char* gb = reinterpret_cast<char*>(ghead16 + boff);
+          char* gt = acc_tail != nullptr ? acc_tail : gb;
           auto scatter = [&](unsigned off, __half2 aw2, uint32_t on) {
             uint32_t h[4];
 #pragma unroll
@@ -588,7 +614,8 @@ fused_bwd_kernel(const FusedArgs a) {
               const __half2 hk = __hmul2(aw2, gh[k]);
               h[k] = *reinterpret_cast<const uint32_t*>(&hk);
             }
-            red_add_f16x8_if(reinterpret_cast<__half*>(gb + off), h[0], h[1], h[2], h[3], on);
+            char* dst = (off >= tail_from ? gt : gb) + off;
+            red_add_f16x8_if(reinterpret_cast<__half*>(dst), h[0], h[1], h[2], h[3], on);
           };
           const __half2 pa = *reinterpret_cast<const __half2*>(&awa);
           const __half2 pb = *reinterpret_cast<const __half2*>(&awb);
@@ -684,6 +711,10 @@ fused_bwd_kernel(const FusedArgs a) {
           const float2* rc = reinterpret_cast<const float2*>(
               a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
           const size_t coff = ((size_t)b * a.groups + cam) * batch_stride;
+          if (replica > 0)
+            acc_tail = reinterpret_cast<char*>(
+                           tail16 + ((size_t)(replica - 1) * a.bs * a.groups + (size_t)b * a.groups + cam) * tail_map) -
+                       tail_from;
           for (int s0 = 0; s0 < LP; s0 += TPH) {
             const int s = s0 + chunk;
             float my_wgt = 0.f;
@@ -857,6 +888,7 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   a.logits = f.logits; a.ref = f.ref; a.hit_bits = f.hit_bits;
   a.out = f.out; a.g_out = f.g_out; a.g_value = f.g_value; a.g_offsets = f.g_offsets;
   a.g_logits = f.g_logits; a.acc_scale = f.acc_scale; a.acc_half = f.acc_half;
+  a.g_tail = f.g_tail; a.tail_copies = f.g_tail ? f.tail_copies : 0; a.tail_px = f.tail_px;
   a.bs = f.bs; a.groups = f.groups; a.Nk = f.Nk; a.M = f.M; a.Dh = f.Dh; a.L = f.L; a.P = f.P;
   a.D = f.D; a.Nq = f.Nq; a.clamp = f.clamp;
   if (f.M > ROWS)

@@ -38,6 +38,8 @@ struct FusedProblem {
   void* g_value = nullptr;             // fp32, or fp16 scaled by *acc_scale when acc_half
   const float* acc_scale = nullptr;
   int acc_half = 0;
+  void* g_tail = nullptr;              // replicas of the fp16 accumulator's coarse tail (see fused.cu)
+  int tail_copies = 0, tail_px = 0;
   void* g_offsets = nullptr;           // coord_dtype
   void* g_logits = nullptr;
   int bs = 0, groups = 0;              // groups = num_cam (SCA) or Q (TSA)
@@ -73,6 +75,7 @@ int launch_colsum(const void* x, void* out, float* partial, long long rows, int 
                   int out_dtype, cudaStream_t st);
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st);
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
+                        const void* tail, int copies, long long map_elems, long long tail_elems,
                         cudaStream_t st);
 
 }  // namespace msda

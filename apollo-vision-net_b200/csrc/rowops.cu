@@ -368,25 +368,44 @@ grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) 
   }
 }
 
+// out = acc / scale in the output dtype.  With tail replicas (see FusedArgs::g_tail): the last
+// `tail_elems` elements of every `map_elems`-long value map also sum `copies` replica maps.
 template <typename TO>
 __global__ void __launch_bounds__(256)
-unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n) {
+unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n,
+                    const __half* __restrict__ tail, int copies, long long map_elems, long long tail_elems) {
   const float inv = 1.0f / __ldg(scale);             // power of two: exact
-  const long long nv = n / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-    float t[8];
-    Vec16<__half>::unpack(ldg128(acc + i * 8), t);
+  // grid: x over the 16-byte chunks of a value map, y over the maps (one map of n elements
+  // when there are no tail replicas)
+  const long long maps = n / map_elems;
+  const long long chunks = map_elems / 8, tail_first = (map_elems - tail_elems) / 8;
+  for (long long map = blockIdx.y; map < maps; map += gridDim.y) {
+    const __half* a = acc + map * map_elems;
+    TO* o = out + map * map_elems;
+    const __half* t = copies > 0 ? tail + map * tail_elems - tail_first * 8 : nullptr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+      float v[8];
+      Vec16<__half>::unpack(ldg128(a + i * 8), v);
+      if (copies > 0 && i >= tail_first) {
+        for (int c = 0; c < copies; ++c) {
+          float u[8];
+          Vec16<__half>::unpack(ldg128(t + (long long)c * maps * tail_elems + i * 8), u);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] *= inv;
-    if constexpr (sizeof(TO) == 2) {
-      *reinterpret_cast<uint4*>(out + i * 8) = Vec16<TO>::pack(t);
-    } else {
+          for (int k = 0; k < 8; ++k) v[k] += u[k];
+        }
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) out[i * 8 + k] = from_f32<TO>(t[k]);
+      for (int k = 0; k < 8; ++k) v[k] *= inv;
+      if constexpr (sizeof(TO) == 2) {
+        *reinterpret_cast<uint4*>(o + i * 8) = Vec16<TO>::pack(v);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[i * 8 + k] = from_f32<TO>(v[k]);
+      }
     }
   }
-  if (blockIdx.x == 0)
-    for (long long i = nv * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
+  if (blockIdx.x == 0 && blockIdx.y == 0)             // (only without replicas: map_elems need not divide by 8)
+    for (long long i = maps * chunks * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
 }
 
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st) {
@@ -399,13 +418,23 @@ int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStre
 }
 
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
+                        const void* tail, int copies, long long map_elems, long long tail_elems,
                         cudaStream_t st) {
-  const long long need = (n / 8 + 255) / 256;
-  const int grid = (int)(need < (long long)row_grid() * 4 ? (need > 0 ? need : 1) : (long long)row_grid() * 4);
   const __half* a = static_cast<const __half*>(acc16);
-  if (out_dtype == MSDA_F32) unscale_cast_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float*>(out), scale, n);
-  else if (out_dtype == MSDA_BF16) unscale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, static_cast<__nv_bfloat16*>(out), scale, n);
-  else unscale_cast_kernel<__half><<<grid, 256, 0, st>>>(a, static_cast<__half*>(out), scale, n);
+  const __half* t = static_cast<const __half*>(tail);
+  if (!t || copies <= 0) { t = nullptr; copies = 0; map_elems = n; tail_elems = 0; }
+  const long long maps = n / map_elems;
+  const long long need = (map_elems / 8 + 255) / 256;
+  long long gx = (long long)row_grid() * 4 / maps;
+  if (gx < 1) gx = 1;
+  if (gx > need) gx = need > 0 ? need : 1;
+  const dim3 grid((unsigned)gx, (unsigned)(maps < 65535 ? maps : 65535));
+  if (out_dtype == MSDA_F32)
+    unscale_cast_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float*>(out), scale, n, t, copies, map_elems, tail_elems);
+  else if (out_dtype == MSDA_BF16)
+    unscale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, static_cast<__nv_bfloat16*>(out), scale, n, t, copies, map_elems, tail_elems);
+  else
+    unscale_cast_kernel<__half><<<grid, 256, 0, st>>>(a, static_cast<__half*>(out), scale, n, t, copies, map_elems, tail_elems);
   count_launch();
   return check_launch("unscale_cast");
 }

@@ -91,17 +91,25 @@ def _check_value(value):
 _scale_ws = {}
 
 
-def _accumulator(value, g_out):
+# fp16 accumulator: replicas of the coarse tail of every value map (see sca_bwd in msda_b200.h).
+# The coarse pyramid levels sit at the end of the pixel axis and hold ~1/16 of the pixels but half of
+# the samples; 8-way replication cuts the rounding noise of their slots by ~sqrt(8).
+_TAIL_FRACTION = 16
+_TAIL_COPIES = 7
+
+
+def _accumulator(value, g_out, num_levels=1):
     """grad_value accumulator for the fused backward kernels.
 
     fp32 value: fp32 accumulator (red.global.add.v4.f32).  16-bit value: fp16 accumulator scaled by
     a power of two derived on the device from max|g_out| (no host sync) -- half the L2 sectors per
-    update; set ``APOLLO_B200_FP32_ACCUM=1`` to force fp32.  Returns (buffer, code, scale_tensor).
+    update; set ``APOLLO_B200_FP32_ACCUM=1`` to force fp32.  Multi-level value maps additionally get
+    replicas of their coarse tail.  Returns (buffer, code, scale_tensor, tail, tail_pixels).
     """
     import os
     dev = value.device
     if value.dtype == torch.float32 or os.environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1':
-        return torch.zeros(value.shape, dtype=torch.float32, device=dev), _lib.F32, None
+        return torch.zeros(value.shape, dtype=torch.float32, device=dev), _lib.F32, None, None, 0
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _scale_ws.get(key)
     if ws is None:
@@ -110,16 +118,25 @@ def _accumulator(value, g_out):
     with torch.cuda.device(dev):
         _lib.call('grad_amax_scale', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
                   ws.data_ptr(), _stream_ptr(value))
-    return torch.zeros(value.shape, dtype=torch.float16, device=dev), _lib.F16, ws[16:17]
+    maps, Nk, M, Dh = value.shape
+    tail, tail_px = None, 0
+    if num_levels > 1 and Nk >= 4 * _TAIL_FRACTION and (M * Dh) % 8 == 0 and \
+            os.environ.get('APOLLO_B200_TAIL_REPLICAS', '1') != '0':
+        tail_px = Nk // _TAIL_FRACTION
+        tail = torch.zeros((_TAIL_COPIES, maps, tail_px, M, Dh), dtype=torch.float16, device=dev)
+    return torch.zeros(value.shape, dtype=torch.float16, device=dev), _lib.F16, ws[16:17], tail, tail_px
 
 
-def _finish_accumulator(acc, code, scale, value):
+def _finish_accumulator(acc, code, scale, value, tail=None, tail_px=0):
     if code == _lib.F32:
         return acc.to(value.dtype)
     out = torch.empty(value.shape, dtype=value.dtype, device=value.device)
+    maps, Nk, M, Dh = value.shape
     with torch.cuda.device(value.device):
         _lib.call('unscale_cast', acc.data_ptr(), out.data_ptr(), scale.data_ptr(), acc.numel(),
-                  _DTYPE_CODE[value.dtype], _stream_ptr(value))
+                  _DTYPE_CODE[value.dtype], None if tail is None else tail.data_ptr(),
+                  0 if tail is None else tail.shape[0], Nk * M * Dh, tail_px * M * Dh,
+                  _stream_ptr(value))
     return out
 
 
@@ -233,7 +250,7 @@ class SpatialCrossAttnFunction(Function):
         off_ptr = coords[0].data_ptr()
         log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_slots = g_slots.to(value.dtype).contiguous()
-        g_value, acc_code, acc_scale = _accumulator(value, g_slots)
+        g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,
@@ -241,8 +258,10 @@ class SpatialCrossAttnFunction(Function):
                 g_slots.data_ptr(), g_value.data_ptr(), g_off_ptr, g_log_ptr,
                 bs, num_cam, Nk, M, Dh, L, P, D, HW, ctx.bev_w, _DTYPE_CODE[value.dtype],
                 code, so, sl, acc_code,
-                None if acc_scale is None else acc_scale.data_ptr(), _stream_ptr(value))
-        g_value = _finish_accumulator(g_value, acc_code, acc_scale, value)
+                None if acc_scale is None else acc_scale.data_ptr(),
+                None if tail is None else tail.data_ptr(), 0 if tail is None else tail.shape[0],
+                tail_px, _stream_ptr(value))
+        g_value = _finish_accumulator(g_value, acc_code, acc_scale, value, tail, tail_px)
         return (g_value, None, None, g_off, g_log, None, None, None, None, None)
 
 
@@ -294,7 +313,7 @@ class QueueDeformAttnFunction(Function):
         off_ptr = coords[0].data_ptr()
         log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_out = g_out.to(value.dtype).contiguous()
-        g_value, acc_code, acc_scale = _accumulator(value, g_out)
+        g_value, acc_code, acc_scale, _, _ = _accumulator(value, g_out)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,

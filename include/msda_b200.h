@@ -176,7 +176,14 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             void* g_value, void* g_offsets, void* g_logits,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
             int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride,
-            int64_t logits_stride, int accum_dtype, const float* accum_scale, void* stream);
+            int64_t logits_stride, int accum_dtype, const float* accum_scale,
+            void* g_value_tail, int tail_copies, int tail_pixels, void* stream);
+/*   g_value_tail (optional, fp16 accumulator only): (tail_copies, bs*num_cam, tail_pixels, M, Dh) fp16,
+ *             zero-filled: replicas of the LAST tail_pixels pixels of every value map -- the coarse
+ *             pyramid levels, whose slots receive hundreds of updates each.  A CTA adds into replica
+ *             blockIdx % (tail_copies + 1) (0 = g_value itself), which divides the number of fp16
+ *             roundings a slot's running sum sees; unscale_cast() adds the replicas back.  NULL / 0:
+ *             everything goes to g_value.                                                          */
 
 /* ---------------------------------------------------------------------------------
  * Fused temporal self-attention / decoder cross-attention core
@@ -210,9 +217,12 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *   grad_amax_scale: ws is a zero-initialised fp32 scratch of >= 64 floats (left zeroed except
  *     ws[16]); on return (stream order) ws[16] = 2^floor(log2(4 / max|g|)) (1 when g is all zero):
  *     single contributions are <= 4 in fp16, 16 000 same-sign maximal updates stay finite.
- *   unscale_cast: out[i] = (out_dtype)(acc_f16[i] / *scale).                                   */
+ *   unscale_cast: out[i] = (out_dtype)((acc_f16[i] + replicas) / *scale).  `tail` = the replicas
+ *     of sca_bwd's g_value_tail (or NULL): acc is n / map_elems value maps of map_elems elements
+ *     (Nk*M*Dh); the last tail_elems (tail_pixels*M*Dh) of each also sum tail_copies replica maps.  */
 int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream);
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
+                 const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
                  void* stream);
 
 /* ---------------------------------------------------------------------------------

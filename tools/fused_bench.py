@@ -38,6 +38,7 @@ def main():
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--which', default='sca,tsa')
     ap.add_argument('--accum', default='auto', help="'auto' (fp16 for 16-bit values) or 'fp32'")
+    ap.add_argument('--no-tail', action='store_true', help='no replicas of the accumulator tail')
     ap.add_argument('--coord', default='same', help="'same' = offsets/logits in the value dtype, 'fp32'")
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -73,6 +74,7 @@ def main():
         gv = torch.zeros(6, Nk, M, Dh, device=dev, dtype=torch.float16 if half_acc else torch.float32)
         sws = torch.zeros(64, device=dev)
         acode = 1 if half_acc else 0
+        tail = torch.zeros(7, 6, Nk // 16, M, Dh, device=dev, dtype=torch.float16) if (half_acc and not args.no_tail) else None
         goff = torch.empty_like(offsets)
         glog = torch.empty_like(logits)
         code = _DTYPE_CODE[dtype]
@@ -88,7 +90,8 @@ def main():
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
-                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, 0, 0, acode, sws[16:].data_ptr() if half_acc else None, st)
+                      1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, 0, 0, acode, sws[16:].data_ptr() if half_acc else None,
+                      tail.data_ptr() if tail is not None else None, 7 if tail is not None else 0, Nk // 16, st)
         res['sca_fwd_us'] = round(timeit(fwd, flush, args.iters), 1)
         res['sca_bwd_us'] = round(timeit(bwd, flush, args.iters), 1)
         res['sca_samples'] = pairs * M * L * P
