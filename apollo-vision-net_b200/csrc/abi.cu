@@ -392,4 +392,31 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
                              static_cast<cudaStream_t>(stream));
 }
 
+int bev_flatten_level(const void* feat, const void* cams_embeds, const void* level_embed, void* feat_flatten,
+                      int bs, int num_cam, int C, int hw, int64_t Nk, int64_t start, int dtype, void* stream) {
+  if (bs < 0 || num_cam <= 0 || C <= 0 || hw < 0 || Nk < 0 || start < 0 || start + hw > Nk)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_flatten_level: invalid sizes");
+  if (dtype != MSDA_F32 && dtype != MSDA_F16 && dtype != MSDA_BF16)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_flatten_level: unknown dtype %d", dtype);
+  if ((long long)bs * hw == 0) return MSDA_OK;
+  if (!feat || !level_embed || !feat_flatten) return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_flatten_level: NULL pointer");
+  return launch_flatten_level(feat, cams_embeds, level_embed, feat_flatten, bs, num_cam, C, hw, Nk, start, dtype,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int bev_rotate_nearest(const void* prev_bev, void* out, const float* theta, const float* xs, const float* ys,
+                       int bs, int bev_h, int bev_w, int C, int dtype, void* stream) {
+  if (bs < 0 || bev_h <= 0 || bev_w <= 0 || C <= 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_rotate_nearest: invalid sizes");
+  if (dtype != MSDA_F32 && dtype != MSDA_F16 && dtype != MSDA_BF16)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_rotate_nearest: unknown dtype %d", dtype);
+  if (bs == 0) return MSDA_OK;
+  if (!prev_bev || !out || !theta || !xs || !ys || prev_bev == out)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_rotate_nearest: NULL or aliased pointer");
+  if ((reinterpret_cast<uintptr_t>(prev_bev) | reinterpret_cast<uintptr_t>(out)) & 15u)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_rotate_nearest: tensors must be 16-byte aligned");
+  return launch_rotate_nearest(prev_bev, out, theta, xs, ys, bs, bev_h, bev_w, C, dtype,
+                               static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

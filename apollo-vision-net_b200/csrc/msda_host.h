@@ -73,6 +73,10 @@ int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const 
               bool dxsum, cudaStream_t st);
 int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype,
                   int out_dtype, cudaStream_t st);
+int launch_flatten_level(const void* feat, const void* cams, const void* lvl, void* out, int bs, int num_cam,
+                         int C, int hw, long long Nk, long long start, int dtype, cudaStream_t st);
+int launch_rotate_nearest(const void* prev, void* out, const float* theta, const float* xs, const float* ys,
+                          int bs, int H, int W, int C, int dtype, cudaStream_t st);
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st);
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,

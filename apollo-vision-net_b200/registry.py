@@ -70,6 +70,20 @@ except Exception:
     TRANSFORMER_LAYER_SEQUENCE = Registry('transformer-layers sequence')
 
 
+try:  # pragma: no cover - mmdet is not installed in the build image
+    from mmdet.models.utils.builder import TRANSFORMER
+except Exception:
+    if HAVE_MMCV:  # pragma: no cover
+        from mmcv.utils import Registry as _MMCVRegistry
+        TRANSFORMER = _MMCVRegistry('Transformer')
+    else:
+        TRANSFORMER = Registry('Transformer')
+
+
+def build_transformer(cfg, default_args=None):
+    return build_from_cfg(cfg, TRANSFORMER, default_args)
+
+
 def build_attention(cfg, default_args=None):
     return build_from_cfg(cfg, ATTENTION, default_args)
 

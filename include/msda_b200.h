@@ -265,6 +265,28 @@ int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dt
  * bench.py reports the delta over its timed region as "gpu_launches". */
 int64_t msda_launch_count(void);
 
+/* ---------------------------------------------------------------------------------
+ * Pre-processing in front of the encoder (reference
+ * PerceptionTransformer.get_bev_features, transformer.py:119-298).
+ *
+ * bev_flatten_level: one pyramid level of the image features
+ *   feat (bs, num_cam, C, hw) dtype  ->  rows [start, start + hw) of
+ *   feat_flatten (num_cam, Nk, bs, C) dtype, with non-finite values zeroed (:246-247 without the
+ *   reference's device->host `isfinite().all()` check) and cams_embeds (num_cam, C; may be NULL)
+ *   and level_embed (C,) added (:249-253).
+ * bev_rotate_nearest: the ego-motion rotation of the previous BEV (:182-203) =
+ *   torchvision.transforms.functional.rotate(nearest, no expand, zero fill), all samples at once:
+ *   prev_bev, out (bev_h*bev_w, bs, C) dtype (must not alias);
+ *   theta (bs, 6) fp32: the inverse affine matrix of torchvision's rotate, rows divided by
+ *   (bev_w / 2, bev_h / 2); xs (bev_w,), ys (bev_h,) fp32: the pixel-centre coordinates
+ *   linspace(-n/2 + 0.5, n/2 - 0.5, n) (the host builds all three exactly as torchvision does).
+ * ------------------------------------------------------------------------------- */
+int bev_flatten_level(const void* feat, const void* cams_embeds, const void* level_embed,
+                      void* feat_flatten, int bs, int num_cam, int C, int hw, int64_t Nk,
+                      int64_t start, int dtype, void* stream);
+int bev_rotate_nearest(const void* prev_bev, void* out, const float* theta, const float* xs,
+                       const float* ys, int bs, int bev_h, int bev_w, int C, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,8 +196,16 @@ def load_reference():
     _module('mmcv.cnn.bricks.registry', ATTENTION=ATTENTION, TRANSFORMER_LAYER=LAYER,
             TRANSFORMER_LAYER_SEQUENCE=LAYER_SEQ, FEEDFORWARD_NETWORK=FFN_REG,
             POSITIONAL_ENCODING=POS_REG)
+    def build_transformer_layer_sequence(cfg, default_args=None):
+        return _build_from_cfg(cfg, LAYER_SEQ, default_args)
+
     _module('mmcv.cnn.bricks.transformer', build_attention=build_attention,
-            TransformerLayerSequence=TransformerLayerSequence)
+            TransformerLayerSequence=TransformerLayerSequence,
+            build_transformer_layer_sequence=build_transformer_layer_sequence)
+    TRANSFORMER = _Registry('Transformer')
+    for pkg in ('mmdet', 'mmdet.models', 'mmdet.models.utils'):
+        _module(pkg).__path__ = []
+    _module('mmdet.models.utils.builder', TRANSFORMER=TRANSFORMER)
     runner = _module('mmcv.runner', force_fp32=_identity_decorator_factory,
                      auto_fp16=_identity_decorator_factory)
     runner.__path__ = []
@@ -233,6 +241,10 @@ def load_reference():
                          os.path.join(_MOD_DIR, 'spatial_cross_attention.py'))
         enc = _load_file(prefix + 'encoder', os.path.join(_MOD_DIR, 'encoder.py'))
         dec = _load_file(prefix + 'decoder', os.path.join(_MOD_DIR, 'decoder.py'))
+        try:                      # needs torchvision (prev_bev rotation); optional
+            trf = _load_file(prefix + 'transformer', os.path.join(_MOD_DIR, 'transformer.py'))
+        except ImportError:
+            trf = None
     finally:
         # keep the synthetic entries only as long as needed by the loaded modules' globals
         for k in list(sys.modules):
@@ -251,6 +263,7 @@ def load_reference():
         CustomMSDeformableAttention=dec.CustomMSDeformableAttention,
         Function_fp32=fn_mod.MultiScaleDeformableAttnFunction_fp32,
         Function_fp16=fn_mod.MultiScaleDeformableAttnFunction_fp16,
-        ATTENTION=ATTENTION, build_attention=build_attention,
-        modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod))
+        PerceptionTransformer=None if trf is None else trf.PerceptionTransformer,
+        ATTENTION=ATTENTION, LAYER_SEQ=LAYER_SEQ, build_attention=build_attention,
+        modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod, trf=trf))
     return _loaded

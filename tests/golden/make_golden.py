@@ -191,6 +191,64 @@ def decoder_case(ref, gen):
     return res
 
 
+def bev_features_case(ref, gen):
+    """PerceptionTransformer.get_bev_features (transformer.py:119-298): can_bus shift, prev_bev
+    rotation (torchvision rotate, nearest), can_bus MLP, camera / level embeddings, flattening of
+    the multi-level image features.  The encoder is replaced by a stub that records what it is
+    called with: that call contract is what the B200 pre-processing must reproduce."""
+    import torch.nn as nn
+    captured = {}
+
+    class CaptureEncoder(nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+
+        def forward(self, bev_queries, key, value, **kw):
+            captured.update(bev_queries=bev_queries, feat_flatten=key, **{
+                k: kw[k] for k in ('bev_pos', 'spatial_shapes', 'level_start_index', 'prev_bev', 'shift')})
+            return bev_queries.permute(1, 0, 2)
+
+    ref.LAYER_SEQ.module_dict['CaptureEncoder'] = CaptureEncoder
+    bs, num_cam, C, bev_h, bev_w = 2, 6, 64, 10, 12
+    levels = [(6, 10), (3, 5), (2, 3)]
+    trf = ref.PerceptionTransformer(num_feature_levels=len(levels), num_cams=num_cam, embed_dims=C,
+                                    encoder=dict(type='CaptureEncoder'), decoder=None,
+                                    rotate_center=[bev_w // 2, bev_h // 2])
+    trf.init_weights()
+    for prm in trf.parameters():                       # non-degenerate biases / norm too
+        if prm.dim() == 1:
+            prm.data = torch.randn(prm.shape, generator=gen) * 0.3
+    trf.eval()
+    mlvl = [torch.randn(bs, num_cam, C, h, w, generator=gen) for h, w in levels]
+    mlvl[1][0, 2, 5, 1, 1] = float('nan')              # the reference sanitises non-finite features
+    mlvl[2][1, 4, 7, 0, 2] = float('inf')
+    bev_queries = torch.randn(bev_h * bev_w, C, generator=gen)
+    bev_pos = torch.randn(bs, C, bev_h, bev_w, generator=gen)
+    prev_bev = torch.randn(bs, bev_h * bev_w, C, generator=gen)
+    can_bus = np.zeros((bs, 18))
+    can_bus[0, :3] = [0.8, -0.35, 0.0]
+    can_bus[0, -2:] = [0.21, 12.0]                     # ego angle (rad), rotation of prev_bev (deg)
+    can_bus[1, :3] = [-1.3, 0.6, 0.0]
+    can_bus[1, -2:] = [-0.4, -33.5]
+    can_bus[:, 3:16] = np.asarray(torch.randn(bs, 13, generator=gen))
+    metas = [dict(can_bus=list(can_bus[b])) for b in range(bs)]
+    grid_length = (0.512, 0.6)
+    out = trf.get_bev_features([m.clone() for m in mlvl], bev_queries, bev_h, bev_w,
+                               grid_length=grid_length, bev_pos=bev_pos, prev_bev=prev_bev.clone(),
+                               img_metas=metas)
+    res = dict(cfg=np.array([bs, num_cam, C, bev_h, bev_w]), levels=np.array(levels, np.int64),
+               bev_queries=_np(bev_queries), bev_pos=_np(bev_pos), prev_bev=_np(prev_bev),
+               can_bus=can_bus, grid_length=np.array(grid_length),
+               out_bev_queries=_np(captured['bev_queries']), out_feat_flatten=_np(captured['feat_flatten']),
+               out_bev_pos=_np(captured['bev_pos']), out_spatial_shapes=_np(captured['spatial_shapes']),
+               out_level_start_index=_np(captured['level_start_index']),
+               out_prev_bev=_np(captured['prev_bev']), out_shift=_np(captured['shift']), out=_np(out))
+    for i, m in enumerate(mlvl):
+        res[f'feat_{i}'] = _np(m)
+    res.update(_state(trf, 'param.'))
+    return res
+
+
 def main():
     ref = load_reference()
     gen = torch.Generator().manual_seed(20261018)
@@ -201,8 +259,12 @@ def main():
         'tsa_prev': tsa_case(ref, gen, True),
         'tsa_first_frame': tsa_case(ref, gen, False),
         'decoder_small': decoder_case(ref, gen),
+        'bev_features_small': bev_features_case(ref, gen),
     }
+    only = sys.argv[1:]                                # optional: names of the cases to (re)write
     for name, arrays in cases.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **arrays)
         print(f'{name}: {len(arrays)} arrays, {os.path.getsize(path) / 1024:.0f} KiB')

@@ -119,3 +119,33 @@ def test_oracle_equals_live_reference():
     kw = dict(query_pos=torch.randn(1, 20, 32), reference_points=hy,
               spatial_shapes=torch.tensor([[4, 5]]), level_start_index=torch.tensor([0]))
     assert torch.equal(r(q, None, None, **kw), o(q, None, None, **kw))
+
+
+def test_bev_features_oracle_matches_golden_exactly():
+    """get_bev_features pre-processing (transformer.py:119-298): the restatement reproduces what
+    the reference hands to its encoder -- shift, rotated prev_bev (torchvision rotate, nearest),
+    flattened features with camera / level embeddings -- bit for bit."""
+    import torch.nn as nn
+    from oracle import bev_features_oracle as B
+    g = gu.load('bev_features_small')
+    bs, num_cam, C, bev_h, bev_w = (int(x) for x in g['cfg'])
+    levels = [tuple(int(v) for v in r) for r in g['levels']]
+    prm = gu.params(g)
+    shift = B.can_bus_shift(g['can_bus'], tuple(g['grid_length']), bev_h, bev_w)
+    assert np.array_equal(shift.numpy(), g['out_shift'])
+    prev = gu.T(g['prev_bev']).permute(1, 0, 2).contiguous()
+    rot = B.rotate_prev_bev(prev, g['can_bus'][:, -1], bev_h, bev_w, [bev_w // 2, bev_h // 2])
+    assert np.array_equal(rot.numpy(), g['out_prev_bev'])
+    assert not np.array_equal(g['out_prev_bev'], prev.numpy())            # the rotation did something
+    feats = [gu.T(g[f'feat_{i}']) for i in range(len(levels))]
+    flat, shapes, starts = B.flatten_features(feats, prm['cams_embeds'], prm['level_embeds'])
+    assert np.array_equal(flat.numpy(), g['out_feat_flatten'])
+    assert np.array_equal(shapes.numpy(), g['out_spatial_shapes'])
+    assert np.array_equal(starts.numpy(), g['out_level_start_index'])
+    # can_bus MLP (transformer.py:206-210): Linear-ReLU-Linear-ReLU-LayerNorm added to every query
+    mlp = nn.Sequential(nn.Linear(18, C // 2), nn.ReLU(), nn.Linear(C // 2, C), nn.ReLU())
+    mlp.add_module('norm', nn.LayerNorm(C))
+    mlp.load_state_dict({k[len('can_bus_mlp.'):]: v for k, v in prm.items() if k.startswith('can_bus_mlp.')})
+    cb = mlp(torch.tensor(g['can_bus'], dtype=torch.float32))[None]
+    q = gu.T(g['bev_queries']).unsqueeze(1).repeat(1, bs, 1) + cb
+    assert np.allclose(q.detach().numpy(), g['out_bev_queries'], rtol=0, atol=1e-6)
