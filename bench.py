@@ -388,7 +388,7 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = run_reference_sample(steps=1, warmup=0)
+        cpu_baseline = run_reference_sample(steps=6, warmup=1)     # about 12 s of CPU work on the box
 
     if rank == 0:
         line = {
