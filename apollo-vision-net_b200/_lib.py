@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 # APOLLO_B200_LIB: load another build of the same ABI (kernel experiments, tools/dev_variants.sh)
 LIB_PATH = os.environ.get('APOLLO_B200_LIB') or os.path.join(_HERE, 'libmsda_b200.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
-SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'rowops.cu', 'bev_prep.cu']
+SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'rowops.cu', 'bev_prep.cu', 'wgrad.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -45,6 +45,8 @@ _SIGNATURES = {
     'colsum': (_c_int, [_c_vp] * 3 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
     'bev_flatten_level': (_c_int, [_c_vp] * 4 + [_c_int] * 4 + [_c_i64, _c_i64, _c_int, _c_vp]),
     'bev_rotate_nearest': (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp]),
+    'linear_wgrad_workspace_floats': (_c_i64, [_c_int, _c_int]),
+    'linear_wgrad': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
     'ln_residual_fwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd_dxsum': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
 }

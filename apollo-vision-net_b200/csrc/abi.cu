@@ -419,4 +419,18 @@ int bev_rotate_nearest(const void* prev_bev, void* out, const float* theta, cons
                                static_cast<cudaStream_t>(stream));
 }
 
+int64_t linear_wgrad_workspace_floats(int O, int I) { return wgrad_workspace_floats(O, I); }
+
+int linear_wgrad(const void* dy, const void* x, void* dW, void* db, float* workspace, int64_t N, int O, int I,
+                 int dtype, void* stream) {
+  if (N < 0 || O <= 0 || I <= 0 || O % 8 != 0 || I % 8 != 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "linear_wgrad: N >= 0 and O, I multiples of 8 required (got %lld, %d, %d)",
+                     (long long)N, O, I);
+  if (!dy || !x || !dW || !workspace) return set_error(MSDA_ERR_BAD_ARGUMENT, "linear_wgrad: NULL pointer");
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dW) |
+       reinterpret_cast<uintptr_t>(workspace)) & 15u)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "linear_wgrad: tensors must be 16-byte aligned");
+  return launch_wgrad(dy, x, dW, db, workspace, N, O, I, dtype, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

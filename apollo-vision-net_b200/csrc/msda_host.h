@@ -77,6 +77,10 @@ int launch_flatten_level(const void* feat, const void* cams, const void* lvl, vo
                          int C, int hw, long long Nk, long long start, int dtype, cudaStream_t st);
 int launch_rotate_nearest(const void* prev, void* out, const float* theta, const float* xs, const float* ys,
                           int bs, int H, int W, int C, int dtype, cudaStream_t st);
+constexpr int kWgHeaderFloats = 64;      // ticket counter in front of the linear_wgrad scratch
+long long wgrad_workspace_floats(int O, int I);
+int launch_wgrad(const void* dy, const void* x, void* dW, void* db, float* ws, long long N, int O, int I,
+                 int dtype, cudaStream_t st);
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st);
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,

@@ -134,7 +134,7 @@ class LinearAddLayerNormFunction(Function):
                       _DTYPE_CODE[s.dtype], _stream_ptr(s))
         x_shape, res_shape = ctx.shapes
         dx = (ds @ weight).view(x_shape) if ctx.needs_input_grad[0] else None
-        dw = ds.t() @ x2 if ctx.needs_input_grad[1] else None
+        dw = weight_bias_grad(ds, x2, weight, want_bias=False)[0] if ctx.needs_input_grad[1] else None
         return dx, dw, out3[2], ds.view(res_shape), out3[0], out3[1], None
 
 
@@ -151,6 +151,44 @@ def linear_add_layernorm(x, linear_mod, residual, norm):
     if not ok:
         return norm(linear_mod(x) + residual)
     return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps)
+
+
+def _wgrad_supported(dy2, x2, weight, want_bias=True):
+    """Whether ``linear_wgrad`` (tcgen05 split-row kernel, csrc/wgrad.cu) takes this gradient:
+    16-bit, many rows, a small O x I output.  OPT-IN: ``APOLLO_B200_WGRAD=1`` routes every such
+    shape to it, ``=bias`` only those whose bias gradient it fuses; default off (the library's
+    split-K GEMM plus our column-sum kernel is faster inside the measured step, see wgrad.cu)."""
+    import os
+    mode = os.environ.get('APOLLO_B200_WGRAD', '0')
+    if mode == '0' or (mode == 'bias' and not want_bias):
+        return False
+    O, I = weight.shape
+    return (dy2.is_cuda and dy2.dtype in (torch.bfloat16, torch.float16) and dy2.dtype == x2.dtype == weight.dtype and
+            O % 8 == 0 and I % 8 == 0 and O * I <= 131072 and dy2.shape[0] >= 8192)
+
+
+def weight_bias_grad(dy2, x2, weight, want_bias=True):
+    """(dW, db) of ``y = x W^T + b`` from dy (N, O) and x (N, I): one pass over both through the
+    tensor-core split-row kernel ``linear_wgrad`` where it applies, else the library GEMM plus the
+    column-sum kernel."""
+    if _wgrad_supported(dy2, x2, weight, want_bias):
+        O, I = weight.shape
+        dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        x2c = x2 if x2.is_contiguous() else x2.contiguous()
+        dW = torch.empty((O, I), dtype=weight.dtype, device=weight.device)
+        db = torch.empty((O,), dtype=weight.dtype, device=weight.device) if want_bias else None
+        ws = _workspace(dy2.device, int(_lib.lib().linear_wgrad_workspace_floats(O, I)))
+        with torch.cuda.device(dy2.device):
+            _lib.call('linear_wgrad', dy2c.data_ptr(), x2c.data_ptr(), dW.data_ptr(),
+                      None if db is None else db.data_ptr(), ws.data_ptr(), dy2c.shape[0], O, I,
+                      _DTYPE_CODE[dy2.dtype], _stream_ptr(dy2))
+        return dW, db
+    dW = dy2.t() @ x2
+    db = None
+    if want_bias:
+        dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)
+    return dW, db
 
 
 def column_sum(x2, out_dtype=None):
@@ -202,9 +240,10 @@ class LinearFunction(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = (dy2 @ weight).view(x.shape)
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = dy2.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dw, db = weight_bias_grad(dy2, x2, weight, want_bias=want_b)
+        elif want_b:
             dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
             db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)
         return dx, dw, db

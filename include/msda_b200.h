@@ -287,6 +287,20 @@ int bev_flatten_level(const void* feat, const void* cams_embeds, const void* lev
 int bev_rotate_nearest(const void* prev_bev, void* out, const float* theta, const float* xs,
                        const float* ys, int bs, int bev_h, int bev_w, int C, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Weight and bias gradient of a Linear layer y = x W^T + b in one launch (16-bit dtypes):
+ *   dW[o, i] = sum_n dy[n, o] * x[n, i]      db[o] = sum_n dy[n, o]   (db may be NULL)
+ *   dy (N, O), x (N, I), dW (O, I), db (O,): dtype (MSDA_BF16 / MSDA_F16), row-major, 16-byte
+ *   aligned, O and I multiples of 8.  Shaped for the transformer layer's backward: small O x I,
+ *   huge N.  The row dimension is split over the whole grid, tensor-core MMAs accumulate in fp32,
+ *   partial tiles are reduced in `workspace`: fp32, linear_wgrad_workspace_floats(O, I) floats,
+ *   ALL ZERO on entry and left all zero (one scratch per stream).  Replaces a split-K library GEMM +
+ *   its reduction kernel + the separate column sum of the bias gradient.
+ * ------------------------------------------------------------------------------- */
+int64_t linear_wgrad_workspace_floats(int O, int I);
+int linear_wgrad(const void* dy, const void* x, void* dW, void* db, float* workspace, int64_t N,
+                 int O, int I, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -666,3 +666,58 @@ def test_linear_add_layernorm_matches_composition(dtype, rows, Cin, C):
         y = torch.nn.functional.layer_norm(torch.nn.functional.linear(x1, lin.weight, lin.bias) + r1,
                                            (C,), norm.weight, norm.bias, norm.eps)
         assert rel_err(a[0], y) <= 1e-5
+
+
+@pytest.mark.parametrize('N,O,I,dtype', [(1000, 256, 256, torch.bfloat16), (37, 192, 512, torch.bfloat16),
+                                         (4099, 768, 256, torch.float16), (1, 8, 8, torch.bfloat16),
+                                         (40000, 256, 256, torch.bfloat16), (20011, 512, 264, torch.float16)])
+def test_linear_wgrad_tcgen05(N, O, I, dtype):
+    """linear_wgrad (tcgen05.mma with the tile in tensor memory, rows split over the grid, bias sums
+    fused): dW = dy^T x and db = column sums of dy against float64, with the error of the library GEMM
+    on the same 16-bit inputs as the yardstick; the scratch must come back zeroed."""
+    from apollo_vision_net_b200 import _lib
+    from apollo_vision_net_b200.multi_scale_deformable_attn_function import _DTYPE_CODE
+    g = torch.Generator().manual_seed(N + O + I)
+    dy = torch.randn(N, O, generator=g).to(dtype).to(DEV)
+    x = torch.randn(N, I, generator=g).to(dtype).to(DEV)
+    dW = torch.full((O, I), float('nan'), dtype=dtype, device=DEV)
+    db = torch.full((O,), float('nan'), dtype=dtype, device=DEV)
+    ws = torch.zeros(int(_lib.lib().linear_wgrad_workspace_floats(O, I)), device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):                                   # twice: the scratch is reused without a memset
+        _lib.call('linear_wgrad', dy.data_ptr(), x.data_ptr(), dW.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                  N, O, I, _DTYPE_CODE[dtype], st)
+    torch.cuda.synchronize()
+    rW, rb = dy.double().t() @ x.double(), dy.double().sum(0)
+    lib_err = rel_err(dy.t() @ x, rW)
+    assert rel_err(dW, rW) <= max(1.05 * lib_err, 1e-6)
+    assert rel_err(db, rb) <= (5e-3 if dtype == torch.bfloat16 else 1e-3)
+    assert float(ws.abs().max()) == 0.0
+    # without a bias gradient
+    _lib.call('linear_wgrad', dy.data_ptr(), x.data_ptr(), dW.data_ptr(), None, ws.data_ptr(), N, O, I,
+              _DTYPE_CODE[dtype], st)
+    assert rel_err(dW, rW) <= max(1.05 * lib_err, 1e-6)
+
+
+def test_linear_backward_through_wgrad(monkeypatch):
+    """APOLLO_B200_WGRAD=1 routes the Linear layers' weight / bias gradients through linear_wgrad."""
+    import apollo_vision_net_b200.rowops as ro
+    g = torch.Generator().manual_seed(3)
+    lin = ro.Linear(256, 512).to(DEV).to(torch.bfloat16)
+    x = torch.randn(2, 9000, 256, generator=g).to(torch.bfloat16).to(DEV)
+    go = torch.randn(2, 9000, 512, generator=g).to(torch.bfloat16).to(DEV)
+
+    def run():
+        lin.weight.grad = lin.bias.grad = None
+        x1 = x.clone().requires_grad_(True)
+        lin(x1).backward(go)
+        return x1.grad, lin.weight.grad, lin.bias.grad
+
+    monkeypatch.setenv('APOLLO_B200_WGRAD', '0')
+    base = run()
+    n0 = ro._lib.launch_count()
+    monkeypatch.setenv('APOLLO_B200_WGRAD', '1')
+    got = run()
+    assert ro._lib.launch_count() - n0 == 2                 # linear_wgrad + its finalize, no column sum
+    for a, b in zip(got, base):
+        assert rel_err(a, b) <= 1e-2
