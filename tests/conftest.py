@@ -20,3 +20,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_global_rng(request):
+    """Module constructors draw their initial weights from torch's global RNG: seed it per test
+    (from the test id, not from Python's salted hash) so that every run -- here and on the GPU box --
+    builds the same models.  Without this each process tested a different random instance, and the
+    three-layer encoder test, whose deep gradients are sensitive to samples sitting next to pixel
+    boundaries, passed or failed depending on the draw."""
+    import zlib
+    import torch
+    torch.manual_seed(zlib.crc32(request.node.nodeid.encode()) & 0x7fffffff)
+    yield

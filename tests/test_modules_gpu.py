@@ -299,22 +299,27 @@ def test_encoder_tiny_config1_vs_oracle():
         def check(name, mine, oracle32, truth, tol):
             e, y = rel_err(mine, truth), rel_err(oracle32, truth)
             assert e <= max(tol, 5.0 * y), f'{name}: err {e:.3e} vs fp64 truth (fp32 oracle: {y:.3e})'
+
+        def check_grad(name, mine, oracle32, truth):
+            """Gradients through three layers: d out / d location is piecewise constant (it jumps
+            when a sample crosses a pixel boundary), so rounding-level differences between the GPU
+            and the CPU forward of the upstream layers put a handful of samples into a neighbouring
+            pixel pair, and with only 2 500
+            queries one such sample moves single entries of a weight gradient by percents of the
+            largest entry (the fp32 oracle shows the same against its own fp64 run).  The bound is
+            therefore tight on the gradient as a whole (2-norm) and loose on the single worst entry;
+            the single-layer tests hold the 1e-4 max-norm bar, and the encoder's forward is bit-identical
+            and its backward reproducible to 1e-6 from run to run and process to process (no races).
+            The model instance is fixed by the per-test seed of conftest.py."""
+            e2, y2 = rel_l2(mine, truth), rel_l2(oracle32, truth)
+            assert e2 <= max(5e-3, 5.0 * y2), f'{name}: l2 err {e2:.3e} (fp32 oracle: {y2:.3e})'
+            check(name, mine, oracle32, truth, 5e-2)
+
         check('out', out, ref, tru, 2e-5)
-        # gradients through three layers are chaotic at rounding level (see below): the run-to-run
-        # order of the fp32 reductions alone moves them; the single-layer tests hold the 1e-4 bar
-        check('grad_feat', f2.grad, f1.grad, f0.grad, 5e-3)
+        check_grad('grad_feat', f2.grad, f1.grad, f0.grad)
         og, tg = dict(o.named_parameters()), dict(o64.named_parameters())
         for n, p in enc.named_parameters():
-            # parameter gradients three layers deep: d out / d location is piecewise constant
-            # (it jumps when a sample crosses a pixel boundary), so rounding-level differences in
-            # the upstream layers flip a few samples and move the offset-path gradients at the
-            # 1e-3 .. 1e-2 level -- in the fp32 oracle just as much as here (see its own error
-            # against the fp64 run).  The single-layer tests above hold the 1e-4 bar.  A flipped
-            # sample moves single entries (max norm), hardly the gradient as a whole (2-norm):
-            # the 2-norm carries the tight bound, the max norm a loose one.
-            e2, y2 = rel_l2(p.grad, tg[n].grad), rel_l2(og[n].grad, tg[n].grad)
-            assert e2 <= max(5e-3, 5.0 * y2), f'{n}: l2 err {e2:.3e} (fp32 oracle: {y2:.3e})'
-            check(n, p.grad, og[n].grad, tg[n].grad, 5e-2)
+            check_grad(n, p.grad, og[n].grad, tg[n].grad)
 
 
 def test_fused_bf16_within_tolerance():
