@@ -586,7 +586,7 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     import torch
-    torch.manual_seed(int(os.environ.get('RANK', '0')))     # initial weights come from the global RNG
+    torch.manual_seed(0)             # initial weights come from the global RNG: same model on every rank
     if args.impl == 'reference':
         args.steps = min(args.steps, 3)
         run_reference(args)
