@@ -380,7 +380,13 @@ int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream
 }
 
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
-                 const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems, void* stream) {
+                 const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
+                 void* colsum_out, float* partial, int C, void* stream) {
+  if (colsum_out) {
+    const int64_t m = (tail && tail_copies > 0) ? map_elems : n;
+    if (!partial || C <= 0 || C % 8 != 0 || 256 % (C / 8) != 0 || m % C != 0 || n % 8 != 0)
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: column sums need C = 8 * (a divisor of 256) dividing the map size");
+  }
   if (n < 0 || (n > 0 && (!acc_f16 || !out || !scale)))
     return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: bad argument");
   if (tail && tail_copies > 0 &&
@@ -389,7 +395,7 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
     return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: inconsistent tail replica sizes");
   if (n == 0) return MSDA_OK;
   return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, tail, tail_copies, map_elems, tail_elems,
-                             static_cast<cudaStream_t>(stream));
+                             partial, colsum_out, C, static_cast<cudaStream_t>(stream));
 }
 
 int bev_flatten_level(const void* feat, const void* cams_embeds, const void* level_embed, void* feat_flatten,

@@ -370,15 +370,23 @@ grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) 
 
 // out = acc / scale in the output dtype.  With tail replicas (see FusedArgs::g_tail): the last
 // `tail_elems` elements of every `map_elems`-long value map also sum `copies` replica maps.
-template <typename TO>
+// COLSUM: additionally the column sums over all rows of the (rows, C) view of the output (C = 8 * cgroups
+// columns: the bias gradient of the Linear layer that produced the value tensor), through the same
+// strip + ticket scheme as colsum_kernel.  The grid's x-stride is a multiple of cgroups, so a thread
+// always holds the same 8 columns.
+template <typename TO, bool COLSUM>
 __global__ void __launch_bounds__(256)
 unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n,
-                    const __half* __restrict__ tail, int copies, long long map_elems, long long tail_elems) {
+                    const __half* __restrict__ tail, int copies, long long map_elems, long long tail_elems,
+                    float* __restrict__ ws, TO* __restrict__ colsum_out, int cgroups) {
   const float inv = 1.0f / __ldg(scale);             // power of two: exact
   // grid: x over the 16-byte chunks of a value map, y over the maps (one map of n elements
   // when there are no tail replicas)
   const long long maps = n / map_elems;
   const long long chunks = map_elems / 8, tail_first = (map_elems - tail_elems) / 8;
+  float csum[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) csum[k] = 0.f;
   for (long long map = blockIdx.y; map < maps; map += gridDim.y) {
     const __half* a = acc + map * map_elems;
     TO* o = out + map * map_elems;
@@ -396,6 +404,10 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] *= inv;
+      if (COLSUM) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) csum[k] += v[k];
+      }
       if constexpr (sizeof(TO) == 2) {
         *reinterpret_cast<uint4*>(o + i * 8) = Vec16<TO>::pack(v);
       } else {
@@ -406,6 +418,40 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
   }
   if (blockIdx.x == 0 && blockIdx.y == 0)             // (only without replicas: map_elems need not divide by 8)
     for (long long i = maps * chunks * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
+  if constexpr (COLSUM) {
+    // threads with the same (threadIdx.x % cgroups) own the same 8 columns (map_elems, the x-stride and 256
+    // are multiples of 8 * cgroups)
+    __shared__ float part[256][9];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[threadIdx.x][k] = csum[k];
+    __syncthreads();
+    const int C = cgroups * 8;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int grp = c >> 3, k = c & 7;
+      float s = 0.f;
+      for (int th = grp; th < 256; th += cgroups) s += part[th][k];
+      atomicAdd(ws + kWsHeaderFloats + c, s);
+    }
+    // ticket over the whole (x, y) grid
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* counter = reinterpret_cast<unsigned*>(ws);
+      const unsigned ticket = atomicAdd(counter, 1u);
+      last = (ticket == gridDim.x * gridDim.y - 1);
+      if (last) *counter = 0u;
+    }
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      float* strip = ws + kWsHeaderFloats;
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        colsum_out[c] = from_f32<TO>(__ldcg(strip + c));
+        strip[c] = 0.f;
+      }
+    }
+  }
 }
 
 int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st) {
@@ -417,24 +463,36 @@ int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStre
   return check_launch("grad_amax_scale");
 }
 
+template <typename TO>
+static void unscale_launch(dim3 grid, cudaStream_t st, const __half* a, void* out, const float* scale, long long n,
+                           const __half* t, int copies, long long map_elems, long long tail_elems, float* ws,
+                           void* colsum_out, int cgroups) {
+  if (colsum_out)
+    unscale_cast_kernel<TO, true><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
+                                                         tail_elems, ws, static_cast<TO*>(colsum_out), cgroups);
+  else
+    unscale_cast_kernel<TO, false><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
+                                                          tail_elems, nullptr, nullptr, 1);
+}
+
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,
-                        cudaStream_t st) {
+                        float* ws, void* colsum_out, int C, cudaStream_t st) {
   const __half* a = static_cast<const __half*>(acc16);
   const __half* t = static_cast<const __half*>(tail);
   if (!t || copies <= 0) { t = nullptr; copies = 0; map_elems = n; tail_elems = 0; }
   const long long maps = n / map_elems;
   const long long need = (map_elems / 8 + 255) / 256;
-  long long gx = (long long)row_grid() * 4 / maps;
+  // with column sums every CTA ends with C reductions into the strip: a grid of ~4 CTAs per SM, as colsum
+  const long long budget = colsum_out ? row_grid() : (long long)row_grid() * 4;
+  long long gx = budget / maps;
   if (gx < 1) gx = 1;
   if (gx > need) gx = need > 0 ? need : 1;
   const dim3 grid((unsigned)gx, (unsigned)(maps < 65535 ? maps : 65535));
-  if (out_dtype == MSDA_F32)
-    unscale_cast_kernel<float><<<grid, 256, 0, st>>>(a, static_cast<float*>(out), scale, n, t, copies, map_elems, tail_elems);
-  else if (out_dtype == MSDA_BF16)
-    unscale_cast_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, static_cast<__nv_bfloat16*>(out), scale, n, t, copies, map_elems, tail_elems);
-  else
-    unscale_cast_kernel<__half><<<grid, 256, 0, st>>>(a, static_cast<__half*>(out), scale, n, t, copies, map_elems, tail_elems);
+  const int cgroups = C / 8;
+  if (out_dtype == MSDA_F32) unscale_launch<float>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
+  else if (out_dtype == MSDA_BF16) unscale_launch<__nv_bfloat16>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
+  else unscale_launch<__half>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
   count_launch();
   return check_launch("unscale_cast");
 }

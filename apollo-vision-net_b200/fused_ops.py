@@ -15,7 +15,7 @@ import ctypes
 import torch
 from torch.autograd.function import Function, once_differentiable
 
-from . import _lib
+from . import _lib, rowops
 from .multi_scale_deformable_attn_function import (_DTYPE_CODE, _require_cuda, _stream_ptr,
                                                    custom_bwd, custom_fwd)
 
@@ -132,11 +132,20 @@ def _finish_accumulator(acc, code, scale, value, tail=None, tail_px=0):
         return acc.to(value.dtype)
     out = torch.empty(value.shape, dtype=value.dtype, device=value.device)
     maps, Nk, M, Dh = value.shape
+    C = M * Dh
+    # the same pass returns the column sums of the (maps * Nk, C) view: the bias gradient of the value
+    # projection that produced `value` (rowops.offer_bias_grad hands it to that Linear's backward)
+    with_sums = C % 8 == 0 and 256 % (C // 8) == 0 and acc.numel() % 8 == 0
+    sums = torch.empty(C, dtype=value.dtype, device=value.device) if with_sums else None
+    ws = rowops._workspace(value.device, C) if with_sums else None
     with torch.cuda.device(value.device):
         _lib.call('unscale_cast', acc.data_ptr(), out.data_ptr(), scale.data_ptr(), acc.numel(),
                   _DTYPE_CODE[value.dtype], None if tail is None else tail.data_ptr(),
                   0 if tail is None else tail.shape[0], Nk * M * Dh, tail_px * M * Dh,
+                  None if sums is None else sums.data_ptr(), None if ws is None else ws.data_ptr(), C,
                   _stream_ptr(value))
+    if with_sums:
+        rowops.offer_bias_grad(out, sums)
     return out
 
 

@@ -153,6 +153,37 @@ def linear_add_layernorm(x, linear_mod, residual, norm):
     return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps)
 
 
+# ---- bias gradients that a producer kernel already has -----------------------------------------
+# The backward of the fused attention kernels ends with a pass over grad_value (unscale_cast); that pass
+# also returns the column sums, which are exactly the bias gradient of the value projection whose output
+# the attention consumed.  autograd only carries tensors, so the sums travel beside the gradient: the
+# producer registers them under the gradient's storage, LinearFunction.backward looks its dy up.  An entry
+# is honoured only while the registered tensor is alive (its memory cannot have been reused), still
+# unmodified (version counter), and covers exactly dy's bytes.
+_bias_grads = {}
+
+
+def offer_bias_grad(grad, colsum):
+    """``colsum`` = sum over all rows of ``grad`` viewed as (-1, colsum.numel())."""
+    import weakref
+    if len(_bias_grads) > 64:                               # entries nobody collected
+        for k in [k for k, (r, *_) in _bias_grads.items() if r() is None]:
+            del _bias_grads[k]
+    _bias_grads[grad.untyped_storage().data_ptr()] = (weakref.ref(grad), grad._version, grad.numel(), colsum)
+
+
+def _take_bias_grad(dy, C):
+    ent = _bias_grads.pop(dy.untyped_storage().data_ptr(), None) if _bias_grads else None
+    if ent is None:
+        return None
+    ref, version, numel, colsum = ent
+    g = ref()
+    if (g is None or g._version != version or numel != dy.numel() or colsum.numel() != C or
+            not dy.is_contiguous() or dy.storage_offset() != g.storage_offset() or dy.dtype != g.dtype):
+        return None
+    return colsum
+
+
 def _wgrad_supported(dy2, x2, weight, want_bias=True):
     """Whether ``linear_wgrad`` (tcgen05 split-row kernel, csrc/wgrad.cu) takes this gradient:
     16-bit, many rows, a small O x I output.  OPT-IN: ``APOLLO_B200_WGRAD=1`` routes every such
@@ -241,8 +272,13 @@ class LinearFunction(Function):
         if ctx.needs_input_grad[0]:
             dx = (dy2 @ weight).view(x.shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        ready = _take_bias_grad(dy, weight.shape[0]) if want_b else None
+        if ready is not None:                               # the producer of dy already summed its rows
+            db = ready.to(weight.dtype)
+            want_b = False
         if ctx.needs_input_grad[1]:
-            dw, db = weight_bias_grad(dy2, x2, weight, want_bias=want_b)
+            dw, db2 = weight_bias_grad(dy2, x2, weight, want_bias=want_b)
+            db = db2 if want_b else db
         elif want_b:
             dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
             db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)

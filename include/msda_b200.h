@@ -219,11 +219,14 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *     single contributions are <= 4 in fp16, 16 000 same-sign maximal updates stay finite.
  *   unscale_cast: out[i] = (out_dtype)((acc_f16[i] + replicas) / *scale).  `tail` = the replicas
  *     of sca_bwd's g_value_tail (or NULL): acc is n / map_elems value maps of map_elems elements
- *     (Nk*M*Dh); the last tail_elems (tail_pixels*M*Dh) of each also sum tail_copies replica maps.  */
+ *     (Nk*M*Dh); the last tail_elems (tail_pixels*M*Dh) of each also sum tail_copies replica maps.
+ *     colsum_out (C,) out_dtype or NULL: additionally the sums over all rows of the (n / C, C) view of
+ *     `out` -- the bias gradient of the value projection -- saving a pass over the tensor; `partial` is
+ *     the row kernels' zero-initialised scratch (64 + C floats, see below); C = 8 * (a divisor of 256). */
 int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream);
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
-                 void* stream);
+                 void* colsum_out, float* partial, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section

@@ -726,3 +726,49 @@ def test_linear_backward_through_wgrad(monkeypatch):
     assert ro._lib.launch_count() - n0 == 2                 # linear_wgrad + its finalize, no column sum
     for a, b in zip(got, base):
         assert rel_err(a, b) <= 1e-2
+
+
+def test_value_proj_bias_grad_comes_from_the_accumulator_pass(monkeypatch):
+    """bf16 model: unscale_cast (the last pass over grad_value) also returns its column sums, which the
+    value projection's backward picks up instead of running a column-sum kernel over 185 k rows.  Same
+    bias gradient with and without the shortcut; one launch fewer with it; a stale offer is not used."""
+    from apollo_vision_net_b200.modules import SpatialCrossAttention
+    import apollo_vision_net_b200.rowops as ro
+    import apollo_vision_net_b200.synthetic as syn
+    C = 256
+    levels = [(29, 50), (15, 25), (8, 13), (4, 7)]
+    cfg = dict(embed_dims=C, pc_range=syn.PC_RANGE, batch_first=True,
+               deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C, num_points=8,
+                                         num_levels=len(levels)))
+    m = SpatialCrossAttention(**cfg)
+    _randomize(m, 5)
+    m.to(DEV).to(torch.bfloat16).eval()
+    q, feat, go, uv, mask, shapes, starts = _sca_inputs(1, 40, 40, levels, C, seed=23)
+    bf = torch.bfloat16
+
+    def run():
+        m.zero_grad()
+        f = feat.to(DEV).to(bf).requires_grad_(True)
+        n0 = ro._lib.launch_count()
+        out = m(q.to(DEV).to(bf), f, f, reference_points_cam=uv.to(DEV), bev_mask=mask.to(DEV),
+                spatial_shapes=shapes.to(DEV), level_start_index=starts.to(DEV))
+        out.backward(go.to(DEV).to(bf))
+        torch.cuda.synchronize()
+        return (m.deformable_attention.value_proj.bias.grad.float().clone(), f.grad.float().clone(),
+                ro._lib.launch_count() - n0)
+
+    b1, f1, n1 = run()
+    monkeypatch.setattr(ro, 'offer_bias_grad', lambda grad, colsum: None)
+    b0, f0, n0 = run()
+    assert n0 == n1 + 1
+    assert rel_err(b1, b0) <= 1e-2 and rel_err(f1, f0) <= 1e-2
+    # an offer for a tensor that has since been modified (or freed) must be ignored
+    monkeypatch.undo()
+    t = torch.randn(64, C, device=DEV).to(bf)
+    ro.offer_bias_grad(t, torch.zeros(C, device=DEV, dtype=bf))
+    t.add_(1.0)                                                        # version counter moves
+    assert ro._take_bias_grad(t, C) is None
+    t2 = torch.randn(64, C, device=DEV).to(bf)
+    ro.offer_bias_grad(t2, torch.ones(C, device=DEV, dtype=bf))
+    assert ro._take_bias_grad(t2.view(8, 8, C), C) is not None        # a view of the same bytes is fine
+    assert ro._take_bias_grad(t2, C) is None                           # ... and an offer is used once
