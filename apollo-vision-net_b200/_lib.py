@@ -47,6 +47,7 @@ _SIGNATURES = {
     'bev_rotate_nearest': (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp]),
     'linear_wgrad_workspace_floats': (_c_i64, [_c_int, _c_int]),
     'linear_wgrad': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
+    'relu_bwd_colsum': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
     'ln_residual_fwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd_dxsum': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
 }

@@ -371,7 +371,14 @@ int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dt
            void* stream) {
   if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: invalid sizes");
   if (!x || !out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: NULL pointer");
-  return launch_colsum(x, out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+  return launch_colsum(x, nullptr, nullptr, out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, float* partial, int64_t rows, int C,
+                    int dtype, int out_dtype, void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_bwd_colsum: invalid sizes");
+  if (!dy || !y || !dx || !colsum_out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_bwd_colsum: NULL pointer");
+  return launch_colsum(dy, y, dx, colsum_out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream) {

@@ -71,8 +71,8 @@ int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const 
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
               long long rows, int C, float eps, int dtype, const void* residual, void* sum_out,
               bool dxsum, cudaStream_t st);
-int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype,
-                  int out_dtype, cudaStream_t st);
+int launch_colsum(const void* x, const void* y, void* dx, void* out, float* partial, long long rows, int C,
+                  int dtype, int out_dtype, cudaStream_t st);
 int launch_flatten_level(const void* feat, const void* cams, const void* lvl, void* out, int bs, int num_cam,
                          int C, int hw, long long Nk, long long start, int dtype, cudaStream_t st);
 int launch_rotate_nearest(const void* prev, void* out, const float* theta, const float* xs, const float* ys,

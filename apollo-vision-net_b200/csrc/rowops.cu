@@ -229,11 +229,16 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   finalize_columns<T>(ws, dgamma_dbeta, NOUT * C);
 }
 
-// Column sums of a (rows, C) matrix: stage 1, per-CTA partials (gridDim.x, C) fp32.  A thread
-// owns 16 bytes of columns; a CTA's threads cover C/VEC column groups x (256 / (C/VEC)) row lanes.
-template <typename T, typename TO>
+// Column sums of a (rows, C) matrix: every CTA reduces its rows, adds into the strip, the last CTA
+// converts.  A thread owns 16 bytes of columns; a CTA's threads cover C/VEC column groups x
+// (256 / (C/VEC)) row lanes.
+// RELU: the matrix summed is dx = (y > 0 ? x : 0) -- the backward of ReLU with upstream gradient x and
+// forward output y -- and dx is written out as well: one pass gives the activation's input gradient and
+// the bias gradient of the Linear layer in front of it.
+template <typename T, typename TO, bool RELU>
 __global__ void __launch_bounds__(kRowThreads)
-colsum_kernel(const T* __restrict__ x, float* __restrict__ ws, TO* __restrict__ out, long long rows, int C) {
+colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ dx, float* __restrict__ ws,
+              TO* __restrict__ out, long long rows, int C) {
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ float sm[];                       // [row_lanes][C]
   const int groups = C / VEC;                         // <= 256
@@ -242,22 +247,32 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ ws, TO* __restrict__ 
   float acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  auto fetch = [&](long long r, float (&t)[VEC]) {
+    Vec16IO<T>::load(x + r * C + gidx * VEC, t);
+    if (RELU) {
+      float m[VEC];
+      Vec16IO<T>::load(y + r * C + gidx * VEC, m);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) t[i] = m[i] > 0.f ? t[i] : 0.f;
+      Vec16IO<T>::store(dx + r * C + gidx * VEC, t);
+    }
+  };
   if (rl < row_lanes) {
     const long long step = (long long)gridDim.x * row_lanes;
     long long r = (long long)blockIdx.x * row_lanes + rl;
     // four independent 16-byte loads in flight per thread
     for (; r + 3 * step < rows; r += 4 * step) {
       float t0[VEC], t1[VEC], t2[VEC], t3[VEC];
-      Vec16IO<T>::load(x + r * C + gidx * VEC, t0);
-      Vec16IO<T>::load(x + (r + step) * C + gidx * VEC, t1);
-      Vec16IO<T>::load(x + (r + 2 * step) * C + gidx * VEC, t2);
-      Vec16IO<T>::load(x + (r + 3 * step) * C + gidx * VEC, t3);
+      fetch(r, t0);
+      fetch(r + step, t1);
+      fetch(r + 2 * step, t2);
+      fetch(r + 3 * step, t3);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
     }
     for (; r < rows; r += step) {
       float t[VEC];
-      Vec16IO<T>::load(x + r * C + gidx * VEC, t);
+      fetch(r, t);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] += t[i];
     }
@@ -511,19 +526,22 @@ int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const 
                              residual, sum_out, dxsum, st);
 }
 
-template <typename T>
-static int colsum_out(const void* x, void* out, float* ws, long long rows, int C, int out_dtype, int grid,
-                      size_t smem, cudaStream_t st) {
+template <typename T, bool RELU>
+static int colsum_out(const void* x, const void* y, void* dx, void* out, float* ws, long long rows, int C,
+                      int out_dtype, int grid, size_t smem, cudaStream_t st) {
   const T* xi = static_cast<const T*>(x);
-  if (out_dtype == MSDA_F32) colsum_kernel<T, float><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<float*>(out), rows, C);
-  else if (out_dtype == MSDA_BF16) colsum_kernel<T, __nv_bfloat16><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<__nv_bfloat16*>(out), rows, C);
-  else colsum_kernel<T, __half><<<grid, kRowThreads, smem, st>>>(xi, ws, static_cast<__half*>(out), rows, C);
+  const T* yi = static_cast<const T*>(y);
+  T* di = static_cast<T*>(dx);
+  if (out_dtype == MSDA_F32) colsum_kernel<T, float, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<float*>(out), rows, C);
+  else if (out_dtype == MSDA_BF16) colsum_kernel<T, __nv_bfloat16, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__nv_bfloat16*>(out), rows, C);
+  else colsum_kernel<T, __half, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__half*>(out), rows, C);
   count_launch();
-  return check_launch("colsum");
+  return check_launch(RELU ? "relu_bwd_colsum" : "colsum");
 }
 
-int launch_colsum(const void* x, void* out, float* partial, long long rows, int C, int dtype, int out_dtype,
-                  cudaStream_t st) {
+// y == nullptr: plain column sums of x.  Otherwise dx = relu'(y) * x is written and summed.
+int launch_colsum(const void* x, const void* y, void* dx, void* out, float* partial, long long rows, int C,
+                  int dtype, int out_dtype, cudaStream_t st) {
   const int vec = dtype == MSDA_F32 ? 4 : 8;
   if (C % vec != 0 || C / vec > kRowThreads)
     return set_error(MSDA_ERR_UNSUPPORTED, "colsum: C=%d must be a multiple of %d and <= %d", C, vec, vec * kRowThreads);
@@ -531,9 +549,13 @@ int launch_colsum(const void* x, void* out, float* partial, long long rows, int 
   const long long need = (rows + row_lanes - 1) / row_lanes;
   const int grid = (int)(need < row_grid() ? (need > 0 ? need : 1) : row_grid());
   const size_t smem = (size_t)row_lanes * C * sizeof(float);
-  if (dtype == MSDA_F32) return colsum_out<float>(x, out, partial, rows, C, out_dtype, grid, smem, st);
-  if (dtype == MSDA_BF16) return colsum_out<__nv_bfloat16>(x, out, partial, rows, C, out_dtype, grid, smem, st);
-  return colsum_out<__half>(x, out, partial, rows, C, out_dtype, grid, smem, st);
+  const bool relu = y != nullptr;
+#define COLSUM_CASE(T) (relu ? colsum_out<T, true>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, st) \
+                             : colsum_out<T, false>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, st))
+  if (dtype == MSDA_F32) return COLSUM_CASE(float);
+  if (dtype == MSDA_BF16) return COLSUM_CASE(__nv_bfloat16);
+  return COLSUM_CASE(__half);
+#undef COLSUM_CASE
 }
 
 }  // namespace msda

@@ -19,9 +19,20 @@ import torch
 import torch.nn as nn
 
 from ..fused_ops import BevGeometry, bev_point_sampling
-from ..rowops import LayerNorm, Linear, linear_add_layernorm
+from ..rowops import LayerNorm, Linear, ReLU, linear_add_layernorm
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
                         build_transformer_layer)
+
+
+def _activation(act_cfg):
+    """mmcv ``build_activation_layer`` for the activations the reference's configs use here."""
+    cfg = dict(act_cfg or dict(type='ReLU', inplace=True))
+    typ = cfg.pop('type', 'ReLU')
+    if typ == 'ReLU':
+        return ReLU(inplace=cfg.get('inplace', True))       # fused backward (rowops.ReLU)
+    if typ == 'GELU':
+        return nn.GELU()
+    raise KeyError(f'unsupported activation {typ}')
 
 
 class FFN(BaseModule):
@@ -38,7 +49,7 @@ class FFN(BaseModule):
         in_channels = embed_dims
         for _ in range(num_fcs - 1):
             layers.append(nn.Sequential(Linear(in_channels, feedforward_channels),
-                                        nn.ReLU(inplace=True), nn.Dropout(ffn_drop)))
+                                        _activation(act_cfg), nn.Dropout(ffn_drop)))
             in_channels = feedforward_channels
         layers.append(Linear(feedforward_channels, embed_dims))
         layers.append(nn.Dropout(ffn_drop))

@@ -184,6 +184,47 @@ def _take_bias_grad(dy, C):
     return colsum
 
 
+class ReLUFunction(Function):
+    """In-place ReLU whose backward also sums its result over the rows: the bias gradient of the Linear
+    layer in front of it (offered to that layer's backward through :func:`offer_bias_grad`)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.relu_(x)
+        ctx.mark_dirty(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, = ctx.saved_tensors
+        C = y.shape[-1]
+        dy2 = dy.reshape(-1, C).to(y.dtype).contiguous()
+        y2 = y.reshape(-1, C)
+        dx = torch.empty_like(dy2)
+        sums = torch.empty(C, dtype=y.dtype, device=y.device)
+        ws = _workspace(y.device, _lib.lib().rowops_workspace_rows() * C)
+        with torch.cuda.device(y.device):
+            _lib.call('relu_bwd_colsum', dy2.data_ptr(), y2.data_ptr(), dx.data_ptr(), sums.data_ptr(),
+                      ws.data_ptr(), dy2.shape[0], C, _DTYPE_CODE[y.dtype], _DTYPE_CODE[y.dtype],
+                      _stream_ptr(y))
+        dx = dx.view(y.shape)
+        offer_bias_grad(dx, sums)
+        return dx
+
+
+class ReLU(nn.ReLU):
+    """``nn.ReLU(inplace=True)`` after a Linear layer: same forward; on CUDA the backward is one kernel
+    that also yields that Linear's bias gradient."""
+
+    def forward(self, x):
+        if (self.inplace and x.is_cuda and x.requires_grad and torch.is_grad_enabled() and x.is_contiguous()
+                and x.dim() >= 2 and _colsum_supported(x.reshape(-1, x.shape[-1]))):
+            return ReLUFunction.apply(x)
+        return super().forward(x)
+
+
 def _wgrad_supported(dy2, x2, weight, want_bias=True):
     """Whether ``linear_wgrad`` (tcgen05 split-row kernel, csrc/wgrad.cu) takes this gradient:
     16-bit, many rows, a small O x I output.  OPT-IN: ``APOLLO_B200_WGRAD=1`` routes every such

@@ -263,6 +263,12 @@ int ln_bwd_dxsum(const void* x, const void* dy, const void* gamma, const float* 
                  int C, int dtype, void* stream);
 int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,
            void* stream);
+/* ReLU backward fused with the bias gradient of the Linear layer in front of the activation (the FFN's
+ * first Linear, custom_base_transformer_layer.py:142-155): dx = (y > 0 ? dy : 0) for the activation's
+ * forward output y, and colsum_out (C,) = column sums of dx; one pass instead of two.  dx must not
+ * alias dy or y.                                                                                   */
+int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, float* partial,
+                    int64_t rows, int C, int dtype, int out_dtype, void* stream);
 
 /* Number of kernel launches this library has enqueued since load (all entry points);
  * bench.py reports the delta over its timed region as "gpu_launches". */

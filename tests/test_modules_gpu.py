@@ -772,3 +772,32 @@ def test_value_proj_bias_grad_comes_from_the_accumulator_pass(monkeypatch):
     ro.offer_bias_grad(t2, torch.ones(C, device=DEV, dtype=bf))
     assert ro._take_bias_grad(t2.view(8, 8, C), C) is not None        # a view of the same bytes is fine
     assert ro._take_bias_grad(t2, C) is None                           # ... and an offer is used once
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_ffn_relu_backward_with_fused_bias_grad(dtype, monkeypatch):
+    """FFN (Linear - ReLU - Linear + identity): the ReLU's backward kernel also sums its rows and the first
+    Linear takes that as its bias gradient.  Against the same FFN with torch's ReLU."""
+    import apollo_vision_net_b200.rowops as ro
+    from apollo_vision_net_b200.modules.encoder import FFN
+    g = torch.Generator().manual_seed(8)
+    ffn = FFN(256, 512).to(DEV).to(dtype)
+    x = torch.randn(1, 5000, 256, generator=g).to(dtype).to(DEV)
+    go = torch.randn(1, 5000, 256, generator=g).to(dtype).to(DEV)
+
+    def run():
+        ffn.zero_grad()
+        x1 = x.clone().requires_grad_(True)
+        n0 = ro._lib.launch_count()
+        y = ffn(x1)
+        y.backward(go)
+        return [y.detach(), x1.grad] + [p.grad.clone() for p in ffn.parameters()], ro._lib.launch_count() - n0
+
+    fused, n_fused = run()
+    monkeypatch.setattr(ro.ReLU, 'forward', lambda self, t: torch.nn.functional.relu(t, inplace=True))
+    plain, n_plain = run()
+    assert n_fused == n_plain                       # relu_bwd_colsum replaces the column-sum launch
+    assert torch.equal(fused[0], plain[0])
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b in zip(fused[1:], plain[1:]):
+        assert rel_err(a, b) <= tol
