@@ -406,9 +406,9 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
     const __half* a = acc + map * map_elems;
     TO* o = out + map * map_elems;
     const __half* t = copies > 0 ? tail + map * tail_elems - tail_first * 8 : nullptr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    auto finish = [&](long long i, const uint4& raw) {
       float v[8];
-      Vec16<__half>::unpack(ldg128(a + i * 8), v);
+      Vec16<__half>::unpack(raw, v);
       if (copies > 0 && i >= tail_first) {
         for (int c = 0; c < copies; ++c) {
           float u[8];
@@ -429,7 +429,18 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[i * 8 + k] = from_f32<TO>(v[k]);
       }
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < chunks; i += 4 * stride) {       // four independent 16-byte loads in flight
+      const uint4 r0 = ldg128(a + i * 8), r1 = ldg128(a + (i + stride) * 8);
+      const uint4 r2 = ldg128(a + (i + 2 * stride) * 8), r3 = ldg128(a + (i + 3 * stride) * 8);
+      finish(i, r0);
+      finish(i + stride, r1);
+      finish(i + 2 * stride, r2);
+      finish(i + 3 * stride, r3);
     }
+    for (; i < chunks; i += stride) finish(i, ldg128(a + i * 8));
   }
   if (blockIdx.x == 0 && blockIdx.y == 0)             // (only without replicas: map_elems need not divide by 8)
     for (long long i = maps * chunks * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
