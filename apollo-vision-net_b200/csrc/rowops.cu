@@ -14,6 +14,9 @@
 namespace msda {
 
 constexpr int kRowThreads = 256;
+#ifndef LN_BWD_MINBLOCKS
+#define LN_BWD_MINBLOCKS 4
+#endif
 
 template <typename T> struct Vec16IO {
   static constexpr int N = Vec16<T>::N;
@@ -134,7 +137,7 @@ ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ 
 // layer whose output (plus a residual) this LayerNorm normalised; output rows: d gamma, d beta,
 // sum of dx.
 template <typename T, int PER_LANE, bool DXSUM>
-__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? 3 : 1)
+__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? LN_BWD_MINBLOCKS : 1)
 ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
               float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C) {
@@ -145,14 +148,11 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + wid;
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
-  float g[PER_LANE], dg[PER_LANE], db[PER_LANE], dsum[DXSUM ? PER_LANE : 1];
+  float dg[PER_LANE], db[PER_LANE], dsum[DXSUM ? PER_LANE : 1];
+  constexpr int NVG = NV > 0 ? NV : 1;
+  uint4 gpk[NVG];                                     // gamma stays packed (registers), unpacked per row
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    float t[VEC];
-    Vec16IO<T>::load(gamma + (v * 32 + lane) * VEC, t);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) g[v * VEC + i] = t[i];
-  }
+  for (int v = 0; v < NV; ++v) gpk[v] = ldg128(gamma + (v * 32 + lane) * VEC);
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) { dg[i] = 0.f; db[i] = 0.f; }
 #pragma unroll
@@ -180,14 +180,15 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      float tx[VEC], td[VEC];
+      float tx[VEC], td[VEC], tg[VEC];
       Vec16<T>::unpack(cx[v], tx);
       Vec16<T>::unpack(cd[v], td);
+      Vec16<T>::unpack(gpk[v], tg);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const int k = v * VEC + i;
         xh[k] = (tx[i] - mu) * rs;
-        gd[k] = td[i] * g[k];
+        gd[k] = td[i] * tg[i];
         dg[k] = fmaf(td[i], xh[k], dg[k]);
         db[k] += td[i];
         s1 += gd[k];
