@@ -144,7 +144,7 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
   constexpr int NOUT = DXSUM ? 3 : 2;
-  extern __shared__ float sm[];                       // [warps][NOUT][C]
+  extern __shared__ __align__(16) float sm[];                       // [warps][NOUT][C]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + wid;
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
@@ -221,11 +221,15 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
       if (DXSUM) mine[2 * C + c] = dsum[v * VEC + i];
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < NOUT * C; c += kRowThreads) {
-    float s = 0.f;
+  // four columns per thread and one 16-byte vector reduction into the strip (C is a multiple of 128)
+  for (int c = threadIdx.x * 4; c < NOUT * C; c += kRowThreads * 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < kRowThreads / 32; ++w) s += sm[(size_t)w * NOUT * C + c];
-    atomicAdd(ws + kWsHeaderFloats + c, s);
+    for (int w = 0; w < kRowThreads / 32; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)w * NOUT * C + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red_add_f32x4(ws + kWsHeaderFloats + c, s.x, s.y, s.z, s.w);
   }
   finalize_columns<T>(ws, dgamma_dbeta, NOUT * C);
 }
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(kRowThreads)
 colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ dx, float* __restrict__ ws,
               TO* __restrict__ out, long long rows, int C) {
   constexpr int VEC = Vec16<T>::N;
-  extern __shared__ float sm[];                       // [row_lanes][C]
+  extern __shared__ __align__(16) float sm[];                       // [row_lanes][C]
   const int groups = C / VEC;                         // <= 256
   const int row_lanes = kRowThreads / groups;
   const int gidx = threadIdx.x % groups, rl = threadIdx.x / groups;
@@ -281,10 +285,21 @@ colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
     for (int i = 0; i < VEC; ++i) sm[(size_t)rl * C + gidx * VEC + i] = acc[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += kRowThreads) {
-    float s = 0.f;
-    for (int w = 0; w < row_lanes; ++w) s += sm[(size_t)w * C + c];
-    atomicAdd(ws + kWsHeaderFloats + c, s);
+  if (C % 4 == 0) {                                   // (always for 16-bit types: VEC = 8)
+    for (int c = threadIdx.x * 4; c < C; c += kRowThreads * 4) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = 0; w < row_lanes; ++w) {
+        const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)w * C + c);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      red_add_f32x4(ws + kWsHeaderFloats + c, s.x, s.y, s.z, s.w);
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += kRowThreads) {
+      float s = 0.f;
+      for (int w = 0; w < row_lanes; ++w) s += sm[(size_t)w * C + c];
+      atomicAdd(ws + kWsHeaderFloats + c, s);
+    }
   }
   finalize_columns<TO>(ws, out, C);
 }
