@@ -41,9 +41,11 @@ constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the 
 template <typename TO>
 __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __restrict__ out, int ncols) {
   __shared__ bool last;
-  __threadfence();
+  // the CTA barrier orders every thread's strip reductions before thread 0's fence (fences are
+  // cumulative), which orders them before the ticket: one device-scope fence per CTA, not one per thread
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned* counter = reinterpret_cast<unsigned*>(ws);
     const unsigned ticket = atomicAdd(counter, 1u);
     last = (ticket == gridDim.x - 1);
@@ -382,9 +384,9 @@ grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) 
   unsigned* wsu = reinterpret_cast<unsigned*>(ws);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(wsu + 1, __float_as_uint(m));   // non-negative floats order like uints
   __shared__ bool last;
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned ticket = atomicAdd(wsu, 1u);
     last = ticket == gridDim.x - 1;
   }
@@ -476,9 +478,9 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
     }
     // ticket over the whole (x, y) grid
     __shared__ bool last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence();
       unsigned* counter = reinterpret_cast<unsigned*>(ws);
       const unsigned ticket = atomicAdd(counter, 1u);
       last = (ticket == gridDim.x * gridDim.y - 1);
