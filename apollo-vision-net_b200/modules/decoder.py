@@ -20,6 +20,44 @@ def inverse_sigmoid(x, eps=1e-5):
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
+def hoist_value_proj(attns, value, batch_first=False):
+    """``[a.value_proj(value) for a in attns]`` as ONE batched GEMM.
+
+    Every decoder layer projects the SAME BEV map with its own ``value_proj`` (decoder.py:299-303
+    of the reference, once per layer inside the layer loop); the BEV does not change between the
+    layers, so the projections of all layers can be computed before the loop: one launch forward,
+    one batched dX / dW launch backward instead of one each per layer plus the gradient
+    accumulation adds on the BEV.  ``value`` is (HW, bs, C) (``batch_first=False``) or (bs, HW, C);
+    returns a list of batch-major (bs, HW, C) tensors, one per attention module."""
+    if not batch_first:
+        value = value.permute(1, 0, 2)
+    bs, n, C = value.shape
+    w = torch.stack([a.value_proj.weight for a in attns]).transpose(1, 2)      # (layers, C_in, C_out)
+    b = torch.stack([a.value_proj.bias for a in attns]).unsqueeze(1)           # (layers, 1, C_out)
+    x = value.reshape(1, bs * n, C).expand(len(attns), -1, -1)
+    out = torch.baddbmm(b, x, w)                                                 # (layers, bs * n, C_out)
+    return [out[i].view(bs, n, -1) for i in range(len(attns))]
+
+
+def hoisted_projections(layers, args, kwargs):
+    """Per-layer ``projected_value`` tensors for a decoder's layer loop, or None when the layers do
+    not each hold exactly one seq-first ``CustomMSDeformableAttention`` with identically shaped
+    ``value_proj`` parameters (then every layer projects its own value, as the reference does)."""
+    value = kwargs.get('value', args[1] if len(args) > 1 else None)
+    if len(layers) < 2 or not torch.is_tensor(value) or value.dim() != 3:
+        return None
+    found = []
+    for layer in layers:
+        mods = [a for a in getattr(layer, 'attentions', []) if isinstance(a, CustomMSDeformableAttention)]
+        if len(mods) != 1 or mods[0].batch_first or mods[0].value_proj.bias is None:
+            return None
+        found.append(mods[0])
+    w0 = found[0].value_proj.weight
+    if any(a.value_proj.weight.shape != w0.shape for a in found) or value.dtype != w0.dtype:
+        return None
+    return hoist_value_proj(found, value)
+
+
 @ATTENTION.register_module()
 class CustomMSDeformableAttention(DeformAttnBase):
 
@@ -34,7 +72,8 @@ class CustomMSDeformableAttention(DeformAttnBase):
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None,
                 key_padding_mask=None, reference_points=None, spatial_shapes=None,
-                level_start_index=None, flag='decoder', post_norm=None, **kwargs):
+                level_start_index=None, flag='decoder', post_norm=None, projected_value=None,
+                **kwargs):
         if 'residual' in kwargs and identity is None:      # mmcv's deprecated_api_warning alias
             identity = kwargs.pop('residual')
         if value is None:
@@ -50,7 +89,13 @@ class CustomMSDeformableAttention(DeformAttnBase):
         _, num_value, _ = value.shape
         M, L, P = self.num_heads, self.num_levels, self.num_points
 
-        value = self.value_proj(value)
+        if projected_value is not None:
+            # value_proj(value) of this layer, computed by the caller for all decoder layers in one
+            # batched GEMM (hoist_value_proj below); batch-major (bs, num_value, C)
+            assert projected_value.shape == value.shape, (projected_value.shape, value.shape)
+            value = projected_value
+        else:
+            value = self.value_proj(value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.view(bs, num_value, M, -1)

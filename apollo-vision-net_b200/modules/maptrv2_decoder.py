@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from ..registry import (ATTENTION, HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                         BaseModule, build_attention, build_transformer_layer)
-from .decoder import inverse_sigmoid
+from .decoder import hoisted_projections, inverse_sigmoid
 from ..rowops import LayerNorm
 from .encoder import FFN
 
@@ -159,16 +159,20 @@ class MapTRv2Decoder(BaseModule):
         self.embed_dims = self.layers[0].embed_dims
         self.return_intermediate = return_intermediate
         self.fp16_enabled = False
+        # project the BEV for the cross-attentions of ALL layers in one batched GEMM before the loop
+        self.hoist_value_proj = True
 
     def forward(self, query, *args, reference_points=None, reg_branches=None,
                 key_padding_mask=None, **kwargs):
         """query (Nq, bs, C); reference_points (bs, Nq, 2) in [0, 1]; value=(HW, bs, C) in kwargs."""
         output = query
         intermediate, intermediate_refs = [], []
+        projected = hoisted_projections(self.layers, args, kwargs) if self.hoist_value_proj else None
         for lid, layer in enumerate(self.layers):
             ref_in = reference_points[..., :2].unsqueeze(2)
+            extra = {} if projected is None else {'projected_value': projected[lid]}
             output = layer(output, *args, reference_points=ref_in,
-                           key_padding_mask=key_padding_mask, **kwargs)
+                           key_padding_mask=key_padding_mask, **kwargs, **extra)
             output = output.permute(1, 0, 2)
             if reg_branches is not None:
                 tmp = reg_branches[lid](output)

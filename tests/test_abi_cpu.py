@@ -54,3 +54,35 @@ def test_host_scratch_size_is_consistent():
     n_bwd = lib.msda_host_scratch_bytes(2, 100, 8, 32, 1, 50, 4, 0, 0, 1)
     assert 0 < n_fwd < n_bwd
     assert n_fwd >= 2 * 100 * 256 * 4 + 2 * 50 * 8 * 4 * 12 + 2 * 50 * 256 * 4
+
+
+def test_hoisted_decoder_value_projection_equals_per_layer_linears():
+    """hoist_value_proj (one batched GEMM before the decoder's layer loop) returns what each
+    layer's own ``value_proj`` returns (reference decoder.py:299-303), with gradients for the BEV
+    and for every layer's parameters.  Host logic only: plain torch on the CPU."""
+    import torch
+    from apollo_vision_net_b200.modules.decoder import CustomMSDeformableAttention, hoist_value_proj
+    torch.manual_seed(5)
+    attns = [CustomMSDeformableAttention(embed_dims=64, num_heads=4, num_levels=1) for _ in range(3)]
+    for a in attns:
+        torch.nn.init.normal_(a.value_proj.bias, std=0.5)
+    bev = torch.randn(35, 2, 64, dtype=torch.float64)
+    for a in attns:
+        a.double()
+    b1 = bev.clone().requires_grad_(True)
+    ref = [a.value_proj(b1.permute(1, 0, 2)) for a in attns]
+    go = [torch.randn_like(r) for r in ref]
+    torch.autograd.backward(ref, go)
+    ref_grads = [(a.value_proj.weight.grad.clone(), a.value_proj.bias.grad.clone()) for a in attns]
+    for a in attns:
+        a.zero_grad()
+    b2 = bev.clone().requires_grad_(True)
+    out = hoist_value_proj(attns, b2)
+    assert len(out) == 3 and all(o.shape == (2, 35, 64) for o in out)
+    torch.autograd.backward(out, go)
+    for o, r in zip(out, ref):
+        assert torch.allclose(o, r, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(b2.grad, b1.grad, rtol=1e-12, atol=1e-12)
+    for a, (gw, gb) in zip(attns, ref_grads):
+        assert torch.allclose(a.value_proj.weight.grad, gw, rtol=1e-12, atol=1e-12)
+        assert torch.allclose(a.value_proj.bias.grad, gb, rtol=1e-12, atol=1e-12)

@@ -559,6 +559,107 @@ def test_maptrv2_decoder_stack_runs_config4():
     assert torch.isfinite(query.grad).all()
 
 
+def test_detection_decoder_vs_oracle_cross_attention():
+    """DetectionTransformerDecoder (reference decoder.py:50-126): 3 DetrTransformerDecoderLayers,
+    900-query style stack at a small size, 3-d reference points refined by reg_branches.  The
+    CPU twin is the same stack with every cross-attention replaced by the oracle module (which
+    projects the value per layer, as the reference does) -- outputs, refined points and gradients
+    must agree within the fp32 tolerances."""
+    import copy
+    import apollo_vision_net_b200 as pkg
+    C, Nq, bs, H, W = 256, 90, 2, 25, 20
+    dec = pkg.build_transformer_layer_sequence(dict(
+        type='DetectionTransformerDecoder', num_layers=3, return_intermediate=True,
+        transformerlayers=dict(
+            type='DetrTransformerDecoderLayer',
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_levels=1)],
+            feedforward_channels=512, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    _randomize(dec, 21)
+    dec.eval()
+    twin = copy.deepcopy(dec)
+    for layer in twin.layers:
+        o = OracleCustomMSDeformableAttention(embed_dims=C, num_levels=1)
+        o.load_state_dict(layer.attentions[1].state_dict())
+        layer.attentions[1] = o.eval()
+    reg = torch.nn.ModuleList([torch.nn.Linear(C, 10) for _ in range(3)])
+    reg_gpu = copy.deepcopy(reg).to(DEV)
+    dec.to(DEV)
+    g = torch.Generator().manual_seed(23)
+    query = torch.randn(Nq, bs, C, generator=g)
+    qpos = torch.randn(Nq, bs, C, generator=g)
+    bev = torch.randn(H * W, bs, C, generator=g)
+    refp = torch.rand(bs, Nq, 3, generator=g)
+    go = torch.randn(3, Nq, bs, C, generator=g)
+    shapes, starts = torch.tensor([[H, W]]), torch.tensor([0])
+
+    q1, b1 = query.clone().requires_grad_(True), bev.clone().requires_grad_(True)
+    ref_out, ref_pts = twin(q1, key=None, value=b1, query_pos=qpos, reference_points=refp,
+                            reg_branches=reg, spatial_shapes=shapes, level_start_index=starts)
+    ref_out.backward(go)
+    q2, b2 = query.to(DEV).requires_grad_(True), bev.to(DEV).requires_grad_(True)
+    out, pts = dec(q2, key=None, value=b2, query_pos=qpos.to(DEV), reference_points=refp.to(DEV),
+                   reg_branches=reg_gpu, spatial_shapes=shapes.to(DEV),
+                   level_start_index=starts.to(DEV))
+    out.backward(go.to(DEV))
+    assert out.shape == (3, Nq, bs, C) and pts.shape == (3, bs, Nq, 3)
+    assert rel_err(out, ref_out) <= 10 * FWD           # three stacked layers of fp32 GEMMs + softmax
+    assert torch.allclose(pts.cpu(), ref_pts, atol=1e-5)
+    assert rel_err(q2.grad, q1.grad) <= 10 * BWD and rel_err(b2.grad, b1.grad) <= 10 * BWD
+    for (n, p), (_, pr) in zip(dec.layers[0].attentions[1].named_parameters(),
+                               twin.layers[0].attentions[1].named_parameters()):
+        assert rel_err(p.grad, pr.grad) <= 10 * BWD, n
+
+
+def test_maptrv2_decoder_hoisted_value_projection_matches_per_layer():
+    """The MapTRv2 decoder projects the BEV for all six cross-attentions in one batched GEMM before
+    the layer loop; outputs, refined reference points and every
+    gradient equal the per-layer projection of the reference (decoder.py:299-303)."""
+    import apollo_vision_net_b200 as pkg
+    C, V, Pn, bs, H, W = 256, 12, 20, 2, 30, 20
+    dec = pkg.build_transformer_layer_sequence(dict(
+        type='MapTRv2Decoder', num_layers=3, return_intermediate=True,
+        transformerlayers=dict(
+            type='MapTRv2DecoupledDetrTransformerDecoderLayer', num_vec=V, num_pts_per_vec=Pn,
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='MultiheadAttention', embed_dims=C, num_heads=8, dropout=0.1),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_levels=1)],
+            feedforward_channels=512, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    _randomize(dec, 8)
+    dec.to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    query0 = torch.randn(V * Pn, bs, C, generator=g).to(DEV)
+    qpos = torch.randn(V * Pn, bs, C, generator=g).to(DEV)
+    bev0 = torch.randn(H * W, bs, C, generator=g).to(DEV)
+    refp = torch.rand(bs, V * Pn, 2, generator=g).to(DEV)
+    kpm = (torch.rand(bs, H * W, generator=g) < 0.05).to(DEV)
+    reg = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(3)]).to(DEV)
+    go = torch.randn(3, V * Pn, bs, C, generator=g).to(DEV)
+
+    def run(hoist):
+        dec.hoist_value_proj = hoist
+        dec.zero_grad()
+        query = query0.clone().requires_grad_(True)
+        bev = bev0.clone().requires_grad_(True)
+        inter, refs = dec(query, key=None, value=bev, query_pos=qpos, reference_points=refp,
+                          reg_branches=reg, key_padding_mask=kpm,
+                          spatial_shapes=torch.tensor([[H, W]], device=DEV),
+                          level_start_index=torch.tensor([0], device=DEV), num_vec=V, num_pts_per_vec=Pn)
+        inter.backward(go)
+        grads = {n: p.grad.clone() for n, p in dec.named_parameters() if p.grad is not None}
+        return inter.detach(), refs, query.grad, bev.grad, grads
+
+    a = run(True)
+    b = run(False)
+    assert rel_err(a[0], b[0]) <= FWD and torch.allclose(a[1], b[1], atol=1e-6)
+    assert rel_err(a[2], b[2]) <= BWD and rel_err(a[3], b[3]) <= BWD
+    assert a[4].keys() == b[4].keys() and any('value_proj.weight' in k for k in a[4])
+    for k in a[4]:
+        assert rel_err(a[4][k], b[4][k]) <= BWD, k
+
+
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_merged_projection_layout_matches_separate_tensors(dtype):
     """The fused Functions take offsets and logits either as two tensors or as the column blocks
