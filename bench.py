@@ -455,15 +455,50 @@ def run_rowshard(args):
     d = {k: v.to(dev) for k, v in host.items()}
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
+    def shard_forward():
+        with torch.no_grad():
+            return enc(d['bev_query'], d['feat'], d['feat'], bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
+                       spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
+                       shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape,
+                       row_shard=(rank, world) if world > 1 else
+                       ((0, args.shard_sim) if args.shard_sim > 1 else None))
+
+    # A rank's share of the frame is a few milliseconds of GPU work spread over ~150 launches: run
+    # eagerly the step is bound by the host's launch rate at N >= 4.  The shard forward never
+    # synchronises with the host, so it is captured once into a CUDA graph; the all-gather of the
+    # rows stays outside the graph (one NCCL launch per frame).
+    graph, static, graph_error = None, {}, None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    shard_forward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static['out'] = shard_forward()
+            torch.cuda.synchronize()
+        except Exception as exc:                   # pragma: no cover - reported in the JSON line
+            graph, graph_error = None, f'{type(exc).__name__}: {exc}'[:200]
+            torch.cuda.synchronize()
+    eager_launches = [0]
+    if graph is not None:                          # our launches per frame, counted on an eager pass
+        n0 = _lib.launch_count()
+        shard_forward()
+        eager_launches[0] = _lib.launch_count() - n0
+
     def step():
         flush.zero_()
-        with torch.no_grad():
-            out = enc(d['bev_query'], d['feat'], d['feat'], bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
-                      spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
-                      shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape,
-                      row_shard=(rank, world) if world > 1 else None)
-            if world > 1:
-                out = all_gather_bev_rows(out, bev, bev)
+        if graph is None:
+            out = shard_forward()
+        else:
+            graph.replay()
+            out = static['out']
+        if world > 1:
+            out = all_gather_bev_rows(out, bev, bev)
         return out
 
     for _ in range(max(args.warmup, 3)):
@@ -491,8 +526,11 @@ def run_rowshard(args):
             'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': f'BEVFormer-base encoder forward, {bev}x{bev} BEV, 6 cams, 4 levels, '
                                    f'{args.layers} layers, rows sharded over {world} rank(s), value maps '
-                                   'replicated, one all-gather at exit (BASELINE configs[4])'},
-            'gpu_launches': _lib.launch_count() - launches0}), flush=True)
+                                   'replicated, one all-gather at exit (BASELINE configs[4])',
+                       'cuda_graph': graph is not None, 'cuda_graph_error': graph_error,
+                       'l2': 'flushed every step (192 MiB write inside the timed region)'},
+            'gpu_launches': (_lib.launch_count() - launches0) if graph is None
+            else eager_launches[0] * args.steps}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -582,6 +620,9 @@ def main():
     ap.add_argument('--layers', type=int, default=6)
     ap.add_argument('--workload', default='encoder', choices=['encoder', 'rowshard'],
                     help="'encoder' (default, the contract line) or 'rowshard' (400x400 forward, strong scaling)")
+    ap.add_argument('--shard-sim', type=int, default=0,
+                    help='rowshard on ONE GPU: run rank 0 of this many row shards, no collective '
+                         '(profiling aid: what one rank of an N-way run executes)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
