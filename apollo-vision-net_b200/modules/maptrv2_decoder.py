@@ -53,8 +53,10 @@ if not HAVE_MMCV:
                 key = key + key_pos
             if self.batch_first:
                 query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+            # need_weights=False: the averaged attention map mmcv discards (`[0]`) is never built,
+            # and torch runs the fused scaled_dot_product_attention kernels
             out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
-                            key_padding_mask=key_padding_mask)[0]
+                            key_padding_mask=key_padding_mask, need_weights=False)[0]
             if self.batch_first:
                 out = out.transpose(0, 1)
             return identity + self.dropout_layer(self.proj_drop(out))
