@@ -261,9 +261,10 @@ def load_reference():
         BEVFormerEncoder=enc.BEVFormerEncoder,
         BEVFormerLayer=enc.BEVFormerLayer,
         CustomMSDeformableAttention=dec.CustomMSDeformableAttention,
+        DetectionTransformerDecoder=dec.DetectionTransformerDecoder,
         Function_fp32=fn_mod.MultiScaleDeformableAttnFunction_fp32,
         Function_fp16=fn_mod.MultiScaleDeformableAttnFunction_fp16,
         PerceptionTransformer=None if trf is None else trf.PerceptionTransformer,
-        ATTENTION=ATTENTION, LAYER_SEQ=LAYER_SEQ, build_attention=build_attention,
+        ATTENTION=ATTENTION, LAYER=LAYER, LAYER_SEQ=LAYER_SEQ, build_attention=build_attention,
         modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod, trf=trf))
     return _loaded

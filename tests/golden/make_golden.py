@@ -191,6 +191,57 @@ def decoder_case(ref, gen):
     return res
 
 
+def det_decoder_case(ref, gen):
+    """The reference's DetectionTransformerDecoder (decoder.py:50-126) -- layer loop, 3-d reference
+    point refinement through reg_branches, detaching, stacking of the intermediates -- driven with
+    a small stub layer (the reference's CustomMSDeformableAttention followed by a LayerNorm), so
+    that the decoder-level logic is pinned without mmdet's DetrTransformerDecoderLayer."""
+    import torch.nn as nn
+    bs, H, W, C, heads, P, Nq, NL = 2, 9, 7, 64, 4, 4, 23, 3
+
+    class StubDecLayer(nn.Module):
+        def __init__(self, embed_dims, num_heads, num_points):
+            super().__init__()
+            self.embed_dims = embed_dims
+            self.attn = ref.CustomMSDeformableAttention(embed_dims=embed_dims, num_heads=num_heads,
+                                                        num_levels=1, num_points=num_points)
+            self.norm = nn.LayerNorm(embed_dims)
+
+        def forward(self, query, key=None, value=None, query_pos=None, reference_points=None,
+                    spatial_shapes=None, level_start_index=None, key_padding_mask=None, **kw):
+            q = self.attn(query, key, value, query_pos=query_pos, reference_points=reference_points,
+                          spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                          key_padding_mask=key_padding_mask)
+            return self.norm(q)
+
+    # the shim's TransformerLayerSequence builds its layers from the shim's TRANSFORMER_LAYER registry
+    ref.LAYER.module_dict['StubDecLayer'] = StubDecLayer
+    dec = ref.DetectionTransformerDecoder(
+        transformerlayers=dict(type='StubDecLayer', embed_dims=C, num_heads=heads, num_points=P),
+        num_layers=NL, return_intermediate=True)
+    _randomize(dec, gen)
+    dec.eval()
+    reg = nn.ModuleList([nn.Linear(C, 10) for _ in range(NL)])
+    for m in reg:
+        m.weight.data = torch.randn(m.weight.shape, generator=gen) * 0.05
+        m.bias.data = torch.randn(m.bias.shape, generator=gen) * 0.05
+    query = torch.randn(Nq, bs, C, generator=gen).requires_grad_(True)
+    qpos = torch.randn(Nq, bs, C, generator=gen)
+    value = torch.randn(H * W, bs, C, generator=gen).requires_grad_(True)
+    refp = torch.rand(bs, Nq, 3, generator=gen)
+    inter, refs = dec(query, key=None, value=value, query_pos=qpos, reference_points=refp,
+                      reg_branches=reg, spatial_shapes=torch.tensor([[H, W]]),
+                      level_start_index=torch.tensor([0]))
+    go = torch.randn(inter.shape, generator=gen)
+    inter.backward(go)
+    res = dict(query=_np(query), query_pos=_np(qpos), value=_np(value), ref=_np(refp),
+               inter=_np(inter), refs=_np(refs), grad_out=_np(go), grad_query=_np(query.grad),
+               grad_value=_np(value.grad), cfg=np.array([bs, H, W, C, heads, P, Nq, NL]))
+    res.update(_state(dec, 'param.'))
+    res.update(_state(reg, 'reg.'))
+    return res
+
+
 def bev_features_case(ref, gen):
     """PerceptionTransformer.get_bev_features (transformer.py:119-298): can_bus shift, prev_bev
     rotation (torchvision rotate, nearest), can_bus MLP, camera / level embeddings, flattening of
@@ -260,6 +311,7 @@ def main():
         'tsa_first_frame': tsa_case(ref, gen, False),
         'decoder_small': decoder_case(ref, gen),
         'bev_features_small': bev_features_case(ref, gen),
+        'det_decoder_small': det_decoder_case(ref, gen),
     }
     only = sys.argv[1:]                                # optional: names of the cases to (re)write
     for name, arrays in cases.items():

@@ -104,3 +104,54 @@ def run_decoder(m, g, device='cpu'):
             level_start_index=torch.tensor([0], device=device))
     out.backward(T(g['grad_out'], device))
     return out, q.grad, v.grad, r.grad
+
+
+class StubDecLayer(torch.nn.Module):
+    """Decoder layer of the ``det_decoder_small`` fixture: deformable cross-attention + LayerNorm
+    (same parameter names as the stub the fixture was generated with, make_golden.py)."""
+
+    def __init__(self, embed_dims, num_heads, num_points, kind='oracle'):
+        super().__init__()
+        self.embed_dims = embed_dims
+        if kind == 'oracle':
+            from oracle.modules_oracle import OracleCustomMSDeformableAttention as cls
+        else:
+            from apollo_vision_net_b200.modules import CustomMSDeformableAttention as cls
+        self.attn = cls(embed_dims=embed_dims, num_heads=num_heads, num_levels=1, num_points=num_points)
+        self.norm = torch.nn.LayerNorm(embed_dims)
+        self.attentions = [self.attn]           # lets the decoder hoist the value projections
+
+    def forward(self, query, key=None, value=None, query_pos=None, reference_points=None,
+                spatial_shapes=None, level_start_index=None, key_padding_mask=None, **kw):
+        q = self.attn(query, key, value, query_pos=query_pos, reference_points=reference_points,
+                      spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                      key_padding_mask=key_padding_mask, **kw)
+        return self.norm(q)
+
+
+def build_det_decoder(g, kind, device='cpu'):
+    """The package's DetectionTransformerDecoder around stub layers, with the fixture's parameters;
+    returns (decoder, reg_branches)."""
+    from apollo_vision_net_b200.modules import DetectionTransformerDecoder
+    from apollo_vision_net_b200.registry import TRANSFORMER_LAYER
+    bs, H, W, C, heads, P, Nq, NL = (int(x) for x in g['cfg'])
+    if TRANSFORMER_LAYER.get('StubDecLayer') is None:
+        TRANSFORMER_LAYER.register_module(name='StubDecLayer', module=StubDecLayer)
+    dec = DetectionTransformerDecoder(
+        transformerlayers=dict(type='StubDecLayer', embed_dims=C, num_heads=heads, num_points=P, kind=kind),
+        num_layers=NL, return_intermediate=True)
+    dec.load_state_dict(params(g))
+    reg = torch.nn.ModuleList([torch.nn.Linear(C, 10) for _ in range(NL)])
+    reg.load_state_dict({k[len('reg.'):]: torch.from_numpy(v) for k, v in g.items() if k.startswith('reg.')})
+    return dec.to(device).eval(), reg.to(device)
+
+
+def run_det_decoder(dec, reg, g, device='cpu'):
+    bs, H, W = (int(x) for x in g['cfg'][:3])
+    query, value = T(g['query'], device, True), T(g['value'], device, True)
+    inter, refs = dec(query, key=None, value=value, query_pos=T(g['query_pos'], device),
+                      reference_points=T(g['ref'], device), reg_branches=reg,
+                      spatial_shapes=torch.tensor([[H, W]], device=device),
+                      level_start_index=torch.tensor([0], device=device))
+    inter.backward(T(g['grad_out'], device))
+    return inter, refs, query.grad, value.grad

@@ -559,6 +559,18 @@ def test_maptrv2_decoder_stack_runs_config4():
     assert torch.isfinite(query.grad).all()
 
 
+def test_detection_decoder_golden():
+    """DetectionTransformerDecoder + CUDA CustomMSDeformableAttention (value projections hoisted
+    into one batched GEMM) against the fixture of the unmodified reference class."""
+    g = gu.load('det_decoder_small')
+    dec, reg = gu.build_det_decoder(g, 'b200', DEV)
+    inter, refs, gq, gv = gu.run_det_decoder(dec, reg, g, DEV)
+    assert rel_err(inter, g['inter']) <= 10 * FWD      # three stacked layers
+    assert rel_err(refs, g['refs']) <= 10 * FWD
+    assert rel_err(gq, g['grad_query']) <= 10 * BWD
+    assert rel_err(gv, g['grad_value']) <= 10 * BWD
+
+
 def test_detection_decoder_vs_oracle_cross_attention():
     """DetectionTransformerDecoder (reference decoder.py:50-126): 3 DetrTransformerDecoderLayers,
     900-query style stack at a small size, 3-d reference points refined by reg_branches.  The

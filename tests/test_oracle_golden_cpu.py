@@ -94,6 +94,21 @@ def test_decoder_oracle_matches_golden():
     assert rel_err(gr, g['grad_ref']) <= 1e-5
 
 
+def test_detection_decoder_host_logic_matches_reference_golden():
+    """DetectionTransformerDecoder of the package (layer loop, refinement of (x, y, z) reference
+    points through reg_branches outputs 0:2 and 4, detach, stacking) against the fixture produced
+    by the UNMODIFIED reference class (decoder.py:50-126); the cross-attention inside the stub
+    layers is the CPU oracle here, the CUDA module in tests/test_modules_gpu.py."""
+    g = gu.load('det_decoder_small')
+    dec, reg = gu.build_det_decoder(g, 'oracle')
+    inter, refs, gq, gv = gu.run_det_decoder(dec, reg, g)
+    assert inter.shape == g['inter'].shape and refs.shape == g['refs'].shape
+    assert rel_err(inter, g['inter']) <= 1e-6
+    assert rel_err(refs, g['refs']) <= 1e-6
+    assert rel_err(gq, g['grad_query']) <= 1e-5
+    assert rel_err(gv, g['grad_value']) <= 1e-5
+
+
 @pytest.mark.skipif(not reference_available(), reason='/root/reference not present on this box')
 def test_oracle_equals_live_reference():
     """Where the reference sources exist (the build container), run them live against the oracle."""
