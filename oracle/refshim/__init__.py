@@ -199,13 +199,120 @@ def load_reference():
     def build_transformer_layer_sequence(cfg, default_args=None):
         return _build_from_cfg(cfg, LAYER_SEQ, default_args)
 
+    # mmcv 1.4.0 bricks the MapTRv2 decoder layer derives from / is configured with, restated from
+    # their documented behaviour (third-party code, not under /root/reference): MultiheadAttention
+    # (nn.MultiheadAttention + positional adds + identity), FFN, BaseTransformerLayer.__init__.
+    class MultiheadAttention(_BaseModule):
+        def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0.,
+                     dropout_layer=dict(type='Dropout', drop_prob=0.), init_cfg=None,
+                     batch_first=False, **kwargs):
+            super().__init__(init_cfg)
+            if 'dropout' in kwargs:
+                attn_drop = kwargs.pop('dropout')
+                dropout_layer = dict(type='Dropout', drop_prob=attn_drop)
+            self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+            self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop, **kwargs)
+            self.proj_drop = nn.Dropout(proj_drop)
+            p = (dropout_layer or {}).get('drop_prob', 0.)
+            self.dropout_layer = nn.Dropout(p) if dropout_layer else nn.Identity()
+
+        def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None,
+                    attn_mask=None, key_padding_mask=None, **kwargs):
+            if key is None:
+                key = query
+            if value is None:
+                value = key
+            if identity is None:
+                identity = query
+            if key_pos is None and query_pos is not None and query_pos.shape == key.shape:
+                key_pos = query_pos
+            if query_pos is not None:
+                query = query + query_pos
+            if key_pos is not None:
+                key = key + key_pos
+            if self.batch_first:
+                query, key, value = (t.transpose(0, 1) for t in (query, key, value))
+            out = self.attn(query=query, key=key, value=value, attn_mask=attn_mask,
+                            key_padding_mask=key_padding_mask)[0]
+            if self.batch_first:
+                out = out.transpose(0, 1)
+            return identity + self.dropout_layer(self.proj_drop(out))
+
+    ATTENTION.module_dict['MultiheadAttention'] = MultiheadAttention
+
+    class FFN(_BaseModule):
+        def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                     act_cfg=dict(type='ReLU', inplace=True), ffn_drop=0., dropout_layer=None,
+                     add_identity=True, init_cfg=None, **kwargs):
+            super().__init__(init_cfg)
+            layers, cin = [], embed_dims
+            for _ in range(num_fcs - 1):
+                layers.append(nn.Sequential(nn.Linear(cin, feedforward_channels), nn.ReLU(inplace=True),
+                                            nn.Dropout(ffn_drop)))
+                cin = feedforward_channels
+            layers.append(nn.Linear(feedforward_channels, embed_dims))
+            layers.append(nn.Dropout(ffn_drop))
+            self.layers = nn.Sequential(*layers)
+            self.dropout_layer = nn.Dropout(dropout_layer['drop_prob']) if dropout_layer else nn.Identity()
+            self.add_identity = add_identity
+
+        def forward(self, x, identity=None):
+            out = self.layers(x)
+            if not self.add_identity:
+                return self.dropout_layer(out)
+            if identity is None:
+                identity = x
+            return identity + self.dropout_layer(out)
+
+    class BaseTransformerLayer(_BaseModule):
+        def __init__(self, attn_cfgs=None, ffn_cfgs=None, operation_order=None, norm_cfg=dict(type='LN'),
+                     init_cfg=None, batch_first=False, **kwargs):
+            super().__init__(init_cfg)
+            ffn_cfgs = dict(ffn_cfgs or dict(type='FFN', embed_dims=256, feedforward_channels=1024,
+                                             num_fcs=2, ffn_drop=0.))
+            for old_name, new_name in (('feedforward_channels', 'feedforward_channels'),
+                                       ('ffn_dropout', 'ffn_drop'), ('ffn_num_fcs', 'num_fcs')):
+                if old_name in kwargs:
+                    ffn_cfgs[new_name] = kwargs[old_name]
+            self.batch_first = batch_first
+            num_attn = operation_order.count('self_attn') + operation_order.count('cross_attn')
+            if isinstance(attn_cfgs, dict):
+                attn_cfgs = [copy.deepcopy(attn_cfgs) for _ in range(num_attn)]
+            assert num_attn == len(attn_cfgs)
+            self.num_attn = num_attn
+            self.operation_order = operation_order
+            self.norm_cfg = norm_cfg
+            self.pre_norm = operation_order[0] == 'norm'
+            self.attentions = nn.ModuleList()
+            index = 0
+            for name in operation_order:
+                if name in ('self_attn', 'cross_attn'):
+                    cfg = copy.deepcopy(attn_cfgs[index])
+                    cfg['batch_first'] = batch_first
+                    att = build_attention(cfg)
+                    att.operation_name = name
+                    self.attentions.append(att)
+                    index += 1
+            self.embed_dims = self.attentions[0].embed_dims
+            ffn_cfgs.pop('type', None)
+            ffn_cfgs['embed_dims'] = self.embed_dims
+            self.ffns = nn.ModuleList([FFN(**copy.deepcopy(ffn_cfgs))
+                                       for _ in range(operation_order.count('ffn'))])
+            self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims)
+                                        for _ in range(operation_order.count('norm'))])
+
+    def inverse_sigmoid(x, eps=1e-5):              # mmdet.models.utils.transformer
+        x = x.clamp(min=0, max=1)
+        return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
     _module('mmcv.cnn.bricks.transformer', build_attention=build_attention,
-            TransformerLayerSequence=TransformerLayerSequence,
+            TransformerLayerSequence=TransformerLayerSequence, BaseTransformerLayer=BaseTransformerLayer,
             build_transformer_layer_sequence=build_transformer_layer_sequence)
     TRANSFORMER = _Registry('Transformer')
     for pkg in ('mmdet', 'mmdet.models', 'mmdet.models.utils'):
         _module(pkg).__path__ = []
     _module('mmdet.models.utils.builder', TRANSFORMER=TRANSFORMER)
+    _module('mmdet.models.utils.transformer', inverse_sigmoid=inverse_sigmoid)
     runner = _module('mmcv.runner', force_fp32=_identity_decorator_factory,
                      auto_fp16=_identity_decorator_factory)
     runner.__path__ = []
@@ -245,6 +352,9 @@ def load_reference():
             trf = _load_file(prefix + 'transformer', os.path.join(_MOD_DIR, 'transformer.py'))
         except ImportError:
             trf = None
+        mapdec = _load_file('projects.mmdet3d_plugin.maptrv2.modules.decoder',
+                            os.path.join(REFERENCE_ROOT, 'projects', 'mmdet3d_plugin', 'maptrv2',
+                                         'modules', 'decoder.py'))
     finally:
         # keep the synthetic entries only as long as needed by the loaded modules' globals
         for k in list(sys.modules):
@@ -262,9 +372,11 @@ def load_reference():
         BEVFormerLayer=enc.BEVFormerLayer,
         CustomMSDeformableAttention=dec.CustomMSDeformableAttention,
         DetectionTransformerDecoder=dec.DetectionTransformerDecoder,
+        MapTRv2Decoder=mapdec.MapTRv2Decoder,
+        MapTRv2DecoupledDetrTransformerDecoderLayer=mapdec.MapTRv2DecoupledDetrTransformerDecoderLayer,
         Function_fp32=fn_mod.MultiScaleDeformableAttnFunction_fp32,
         Function_fp16=fn_mod.MultiScaleDeformableAttnFunction_fp16,
         PerceptionTransformer=None if trf is None else trf.PerceptionTransformer,
         ATTENTION=ATTENTION, LAYER=LAYER, LAYER_SEQ=LAYER_SEQ, build_attention=build_attention,
-        modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod, trf=trf))
+        modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod, trf=trf, mapdec=mapdec))
     return _loaded

@@ -242,6 +242,53 @@ def det_decoder_case(ref, gen):
     return res
 
 
+MAPTR_ORDER = ('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')
+
+
+def maptrv2_decoder_case(ref, gen):
+    """The reference's MapTRv2Decoder + MapTRv2DecoupledDetrTransformerDecoderLayer
+    (maptrv2/modules/decoder.py:10-213): inter-vector / intra-vector self-attention reshapes,
+    deformable cross-attention on the BEV, 2-d reference refinement -- one-to-one and one-to-many
+    vectors separated by the self-attention mask.  mmcv's MultiheadAttention / FFN /
+    BaseTransformerLayer constructor come from the shim (third-party, restated)."""
+    import torch.nn as nn
+    bs, H, W, C, heads, P, V, Pn, NL = 2, 8, 6, 64, 4, 4, 6, 4, 2
+    dec = ref.MapTRv2Decoder(
+        transformerlayers=dict(
+            type='MapTRv2DecoupledDetrTransformerDecoderLayer', num_vec=V, num_pts_per_vec=Pn,
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=heads, dropout=0.1),
+                       dict(type='MultiheadAttention', embed_dims=C, num_heads=heads, dropout=0.1),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_heads=heads,
+                            num_levels=1, num_points=P)],
+            feedforward_channels=2 * C, ffn_dropout=0.1, operation_order=MAPTR_ORDER),
+        num_layers=NL, return_intermediate=True)
+    _randomize(dec, gen)
+    dec.eval()
+    reg = nn.ModuleList([nn.Linear(C, 2) for _ in range(NL)])
+    for m in reg:
+        m.weight.data = torch.randn(m.weight.shape, generator=gen) * 0.05
+        m.bias.data = torch.randn(m.bias.shape, generator=gen) * 0.05
+    query = torch.randn(V * Pn, bs, C, generator=gen).requires_grad_(True)
+    qpos = torch.randn(V * Pn, bs, C, generator=gen)
+    value = torch.randn(H * W, bs, C, generator=gen).requires_grad_(True)
+    refp = torch.rand(bs, V * Pn, 2, generator=gen)
+    mask = torch.zeros(V, V, dtype=torch.bool)
+    mask[V // 2:, :V // 2] = True
+    mask[:V // 2, V // 2:] = True
+    inter, refs = dec(query, key=None, value=value, query_pos=qpos, reference_points=refp,
+                      reg_branches=reg, spatial_shapes=torch.tensor([[H, W]]),
+                      level_start_index=torch.tensor([0]), self_attn_mask=mask, num_vec=V,
+                      num_pts_per_vec=Pn)
+    go = torch.randn(inter.shape, generator=gen)
+    inter.backward(go)
+    res = dict(query=_np(query), query_pos=_np(qpos), value=_np(value), ref=_np(refp), mask=_np(mask),
+               inter=_np(inter), refs=_np(refs), grad_out=_np(go), grad_query=_np(query.grad),
+               grad_value=_np(value.grad), cfg=np.array([bs, H, W, C, heads, P, V, Pn, NL]))
+    res.update(_state(dec, 'param.'))
+    res.update(_state(reg, 'reg.'))
+    return res
+
+
 def bev_features_case(ref, gen):
     """PerceptionTransformer.get_bev_features (transformer.py:119-298): can_bus shift, prev_bev
     rotation (torchvision rotate, nearest), can_bus MLP, camera / level embeddings, flattening of
@@ -312,6 +359,7 @@ def main():
         'decoder_small': decoder_case(ref, gen),
         'bev_features_small': bev_features_case(ref, gen),
         'det_decoder_small': det_decoder_case(ref, gen),
+        'maptrv2_decoder_small': maptrv2_decoder_case(ref, gen),
     }
     only = sys.argv[1:]                                # optional: names of the cases to (re)write
     for name, arrays in cases.items():

@@ -155,3 +155,44 @@ def run_det_decoder(dec, reg, g, device='cpu'):
                       level_start_index=torch.tensor([0], device=device))
     inter.backward(T(g['grad_out'], device))
     return inter, refs, query.grad, value.grad
+
+
+MAPTR_ORDER = ('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')
+
+
+def build_maptrv2_decoder(g, kind, device='cpu'):
+    """The package's MapTRv2Decoder (decoupled layers) with the fixture's parameters; ``kind`` picks
+    the deformable cross-attention: the CPU oracle module or the CUDA module."""
+    import apollo_vision_net_b200 as pkg
+    from apollo_vision_net_b200.registry import ATTENTION
+    bs, H, W, C, heads, P, V, Pn, NL = (int(x) for x in g['cfg'])
+    xattn = 'CustomMSDeformableAttention'
+    if kind == 'oracle':
+        from oracle.modules_oracle import OracleCustomMSDeformableAttention
+        xattn = 'OracleCustomMSDeformableAttention'
+        if ATTENTION.get(xattn) is None:
+            ATTENTION.register_module(name=xattn, module=OracleCustomMSDeformableAttention)
+    dec = pkg.build_transformer_layer_sequence(dict(
+        type='MapTRv2Decoder', num_layers=NL, return_intermediate=True,
+        transformerlayers=dict(
+            type='MapTRv2DecoupledDetrTransformerDecoderLayer', num_vec=V, num_pts_per_vec=Pn,
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=heads, dropout=0.1),
+                       dict(type='MultiheadAttention', embed_dims=C, num_heads=heads, dropout=0.1),
+                       dict(type=xattn, embed_dims=C, num_heads=heads, num_levels=1, num_points=P)],
+            feedforward_channels=2 * C, ffn_dropout=0.1, operation_order=MAPTR_ORDER)))
+    dec.load_state_dict(params(g))
+    reg = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(NL)])
+    reg.load_state_dict({k[len('reg.'):]: torch.from_numpy(v) for k, v in g.items() if k.startswith('reg.')})
+    return dec.to(device).eval(), reg.to(device)
+
+
+def run_maptrv2_decoder(dec, reg, g, device='cpu'):
+    bs, H, W, C, heads, P, V, Pn, NL = (int(x) for x in g['cfg'])
+    query, value = T(g['query'], device, True), T(g['value'], device, True)
+    inter, refs = dec(query, key=None, value=value, query_pos=T(g['query_pos'], device),
+                      reference_points=T(g['ref'], device), reg_branches=reg,
+                      spatial_shapes=torch.tensor([[H, W]], device=device),
+                      level_start_index=torch.tensor([0], device=device),
+                      self_attn_mask=T(g['mask'], device), num_vec=V, num_pts_per_vec=Pn)
+    inter.backward(T(g['grad_out'], device))
+    return inter, refs, query.grad, value.grad

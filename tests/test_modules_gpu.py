@@ -559,6 +559,18 @@ def test_maptrv2_decoder_stack_runs_config4():
     assert torch.isfinite(query.grad).all()
 
 
+def test_maptrv2_decoder_golden():
+    """MapTRv2Decoder with the CUDA cross-attention (hoisted value projections, fused kernel)
+    against the fixture of the unmodified reference decoder (2 layers, one-to-many mask)."""
+    g = gu.load('maptrv2_decoder_small')
+    dec, reg = gu.build_maptrv2_decoder(g, 'b200', DEV)
+    inter, refs, gq, gv = gu.run_maptrv2_decoder(dec, reg, g, DEV)
+    assert rel_err(inter, g['inter']) <= 10 * FWD
+    assert rel_err(refs, g['refs']) <= 10 * FWD
+    assert rel_err(gq, g['grad_query']) <= 10 * BWD
+    assert rel_err(gv, g['grad_value']) <= 10 * BWD
+
+
 def test_detection_decoder_golden():
     """DetectionTransformerDecoder + CUDA CustomMSDeformableAttention (value projections hoisted
     into one batched GEMM) against the fixture of the unmodified reference class."""

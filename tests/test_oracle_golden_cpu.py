@@ -109,6 +109,22 @@ def test_detection_decoder_host_logic_matches_reference_golden():
     assert rel_err(gv, g['grad_value']) <= 1e-5
 
 
+def test_maptrv2_decoder_host_logic_matches_reference_golden():
+    """MapTRv2Decoder + MapTRv2DecoupledDetrTransformerDecoderLayer of the package (the
+    inter-vector / intra-vector reshapes around the two self-attentions, cross-attention call
+    contract, 2-d reference refinement) against the fixture produced by the UNMODIFIED reference
+    classes (maptrv2/modules/decoder.py:10-213), one-to-many mask included; the deformable
+    cross-attention is the CPU oracle here, the CUDA module in tests/test_modules_gpu.py."""
+    g = gu.load('maptrv2_decoder_small')
+    dec, reg = gu.build_maptrv2_decoder(g, 'oracle')
+    inter, refs, gq, gv = gu.run_maptrv2_decoder(dec, reg, g)
+    assert inter.shape == g['inter'].shape and refs.shape == g['refs'].shape
+    assert rel_err(inter, g['inter']) <= 1e-5
+    assert rel_err(refs, g['refs']) <= 1e-5
+    assert rel_err(gq, g['grad_query']) <= 1e-4
+    assert rel_err(gv, g['grad_value']) <= 1e-4
+
+
 @pytest.mark.skipif(not reference_available(), reason='/root/reference not present on this box')
 def test_oracle_equals_live_reference():
     """Where the reference sources exist (the build container), run them live against the oracle."""
