@@ -305,8 +305,24 @@ def load_reference():
         x = x.clamp(min=0, max=1)
         return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
+    FFN_REG.module_dict['FFN'] = FFN
+
+    def build_feedforward_network(cfg, default_args=None):
+        return _build_from_cfg(cfg, FFN_REG, default_args)
+
+    def build_norm_layer(cfg, num_features, postfix=''):
+        assert cfg.get('type') == 'LN', cfg
+        return 'ln' + str(postfix), nn.LayerNorm(num_features, eps=cfg.get('eps', 1e-5))
+
+    def build_activation_layer(cfg):
+        assert cfg.get('type') == 'ReLU', cfg
+        return nn.ReLU(inplace=cfg.get('inplace', False))
+
+    cnn.build_norm_layer = build_norm_layer
+    cnn.build_activation_layer = build_activation_layer
     _module('mmcv.cnn.bricks.transformer', build_attention=build_attention,
             TransformerLayerSequence=TransformerLayerSequence, BaseTransformerLayer=BaseTransformerLayer,
+            build_feedforward_network=build_feedforward_network,
             build_transformer_layer_sequence=build_transformer_layer_sequence)
     TRANSFORMER = _Registry('Transformer')
     for pkg in ('mmdet', 'mmdet.models', 'mmdet.models.utils'):
@@ -336,11 +352,12 @@ def load_reference():
     _module('projects.mmdet3d_plugin.models.utils.bricks',
             run_time=lambda name: (lambda fn: fn))
     _module('projects.mmdet3d_plugin.models.utils.visual', save_tensor=lambda *a, **k: None)
-    _module('projects.mmdet3d_plugin.bevformer.modules.custom_base_transformer_layer',
-            MyCustomBaseTransformerLayer=_BaseModule)
-
     prefix = 'projects.mmdet3d_plugin.bevformer.modules.'
     try:
+        # the reference's own base layer (attention / FFN / norm construction and the generic
+        # operation loop BEVFormerLayer falls back to), executed from the reference tree
+        _load_file(prefix + 'custom_base_transformer_layer',
+                   os.path.join(_MOD_DIR, 'custom_base_transformer_layer.py'))
         fn_mod = _load_file(prefix + 'multi_scale_deformable_attn_function',
                             os.path.join(_MOD_DIR, 'multi_scale_deformable_attn_function.py'))
         tsa = _load_file(prefix + 'temporal_self_attention', tsa_path)

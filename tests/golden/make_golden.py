@@ -289,6 +289,56 @@ def maptrv2_decoder_case(ref, gen):
     return res
 
 
+ENC_ORDER = ('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')
+
+
+def encoder_case(ref, gen):
+    """The reference's BEVFormerEncoder + BEVFormerLayer (encoder.py:243-352, 354-519) built on its
+    own MyCustomBaseTransformerLayer (custom_base_transformer_layer.py), two layers, with history
+    and a CAN-bus shift: reference points, point_sampling from img_metas, the hybrid ref_2d stack
+    (incl. the aliasing quirk, encoder.py:309-311), the [prev_bev, bev] value pair, TSA -> norm ->
+    SCA -> norm -> FFN -> norm, all on the reference's CPU branch."""
+    bs, H, W, C, heads = 2, 8, 10, 64, 8
+    levels = [(6, 10), (3, 5)]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    enc = ref.BEVFormerEncoder(
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_heads=heads, num_levels=1,
+                            num_points=4),
+                       dict(type='SpatialCrossAttention', embed_dims=C, num_cams=6, pc_range=syn.PC_RANGE,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_heads=heads, num_points=8,
+                                                      num_levels=len(levels)))],
+            feedforward_channels=2 * C, ffn_dropout=0.1,
+            ffn_cfgs=dict(type='FFN', embed_dims=C, feedforward_channels=2 * C, num_fcs=2, ffn_drop=0.1,
+                          act_cfg=dict(type='ReLU', inplace=True)),
+            operation_order=ENC_ORDER),
+        num_layers=2, pc_range=syn.PC_RANGE, num_points_in_pillar=4, return_intermediate=False)
+    _randomize(enc, gen)
+    enc.eval()
+    l2i, img_shape = syn.camera_rig(0.05, bs=bs, jitter=4.0, seed=5)
+    metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6)
+             for b in range(bs)]
+    bevq = torch.randn(H * W, bs, C, generator=gen).requires_grad_(True)
+    pos = torch.randn(H * W, bs, C, generator=gen)
+    prev = torch.randn(H * W, bs, C, generator=gen).requires_grad_(True)
+    feat = torch.randn(6, Nk, bs, C, generator=gen).requires_grad_(True)
+    shift = torch.tensor([[0.012, -0.02], [-0.03, 0.007]])
+    out = enc(bevq, feat, feat, bev_h=H, bev_w=W, bev_pos=pos, spatial_shapes=torch.tensor(shapes_l),
+              level_start_index=torch.tensor(starts_l), prev_bev=prev, shift=shift, img_metas=metas)
+    go = torch.randn(out.shape, generator=gen)
+    out.backward(go)
+    res = dict(bev_query=_np(bevq), bev_pos=_np(pos), prev_bev=_np(prev), feat=_np(feat), shift=_np(shift),
+               lidar2img=l2i, img_shape=np.array(img_shape), levels=np.array(levels, np.int64),
+               out=_np(out), grad_out=_np(go), grad_bev_query=_np(bevq.grad), grad_prev_bev=_np(prev.grad),
+               grad_feat=_np(feat.grad), cfg=np.array([bs, H, W, C, heads]))
+    res.update(_state(enc, 'param.'))
+    for n, p in enc.named_parameters():
+        res['pgrad.' + n] = _np(p.grad)
+    return res
+
+
 def bev_features_case(ref, gen):
     """PerceptionTransformer.get_bev_features (transformer.py:119-298): can_bus shift, prev_bev
     rotation (torchvision rotate, nearest), can_bus MLP, camera / level embeddings, flattening of
@@ -360,6 +410,7 @@ def main():
         'bev_features_small': bev_features_case(ref, gen),
         'det_decoder_small': det_decoder_case(ref, gen),
         'maptrv2_decoder_small': maptrv2_decoder_case(ref, gen),
+        'encoder_small': encoder_case(ref, gen),
     }
     only = sys.argv[1:]                                # optional: names of the cases to (re)write
     for name, arrays in cases.items():

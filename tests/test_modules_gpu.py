@@ -322,6 +322,49 @@ def test_encoder_tiny_config1_vs_oracle():
             check_grad(n, p.grad, og[n].grad, tg[n].grad)
 
 
+def test_encoder_golden():
+    """The CUDA BEVFormerEncoder (2 layers, history + CAN-bus shift, 2 feature levels, batch of 2 with
+    jittered cameras) against the fixture produced by the UNMODIFIED reference encoder classes
+    (encoder.py:243-519 on custom_base_transformer_layer.py), forward and gradients."""
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    g = gu.load('encoder_small')
+    bs, H, W, C, heads = (int(x) for x in g['cfg'])
+    levels = [tuple(int(v) for v in r) for r in g['levels']]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    enc = pkg.build_transformer_layer_sequence(dict(
+        type='BEVFormerEncoder', num_layers=2, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+        return_intermediate=False,
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_heads=heads, num_levels=1,
+                            num_points=4),
+                       dict(type='SpatialCrossAttention', pc_range=syn.PC_RANGE, embed_dims=C,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_heads=heads, num_points=8,
+                                                      num_levels=len(levels)))],
+            feedforward_channels=2 * C, ffn_dropout=0.1,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    enc.load_state_dict(gu.params(g))
+    enc.to(DEV).eval()
+    l2i = g['lidar2img']
+    img_shape = tuple(int(v) for v in g['img_shape'])
+    metas = [dict(lidar2img=[l2i[b, i] for i in range(6)], img_shape=[img_shape] * 6) for b in range(bs)]
+    bevq, prev, feat = (gu.T(g[k], DEV, True) for k in ('bev_query', 'prev_bev', 'feat'))
+    out = enc(bevq, feat, feat, bev_h=H, bev_w=W, bev_pos=gu.T(g['bev_pos'], DEV),
+              spatial_shapes=torch.tensor(shapes_l, device=DEV),
+              level_start_index=torch.tensor(starts_l, device=DEV), prev_bev=prev,
+              shift=gu.T(g['shift'], DEV), img_metas=metas)
+    out.backward(gu.T(g['grad_out'], DEV))
+    assert rel_err(out, g['out']) <= 1e-4
+    assert rel_l2(bevq.grad, gu.T(g['grad_bev_query'])) <= 5e-3
+    assert rel_l2(prev.grad, gu.T(g['grad_prev_bev'])) <= 5e-3
+    assert rel_l2(feat.grad, gu.T(g['grad_feat'])) <= 5e-3
+    pg = gu.pgrads(g)
+    for n, p in enc.named_parameters():
+        assert rel_l2(p.grad, gu.T(pg[n])) <= 5e-3, n
+
+
 def test_fused_bf16_within_tolerance():
     """bf16 value path of the fused SCA kernel: within 1e-2 of the fp32 oracle (north_star)."""
     from apollo_vision_net_b200.modules import SpatialCrossAttention

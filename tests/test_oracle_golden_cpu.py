@@ -109,6 +109,35 @@ def test_detection_decoder_host_logic_matches_reference_golden():
     assert rel_err(gv, g['grad_value']) <= 1e-5
 
 
+def test_encoder_oracle_matches_reference_golden():
+    """OracleBEVFormerEncoder (the checker of the CUDA encoder tests) against the fixture produced by
+    the UNMODIFIED reference BEVFormerEncoder / BEVFormerLayer / MyCustomBaseTransformerLayer: two
+    layers, history, CAN-bus shift, two feature levels, forward and every gradient."""
+    from oracle.modules_oracle import OracleBEVFormerEncoder
+    import apollo_vision_net_b200.synthetic as syn
+    g = gu.load('encoder_small')
+    bs, H, W, C, heads = (int(x) for x in g['cfg'])
+    levels = [tuple(int(v) for v in r) for r in g['levels']]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    o = OracleBEVFormerEncoder(num_layers=2, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+                               embed_dims=C, feedforward_channels=2 * C, num_levels=len(levels))
+    o.load_state_dict(gu.params(g))
+    o.eval()
+    bevq, prev, feat = (gu.T(g[k], grad=True) for k in ('bev_query', 'prev_bev', 'feat'))
+    out = o(bevq, feat, feat, bev_h=H, bev_w=W, bev_pos=gu.T(g['bev_pos']),
+            spatial_shapes=torch.tensor(shapes_l), level_start_index=torch.tensor(starts_l),
+            prev_bev=prev, shift=gu.T(g['shift']), lidar2img=g['lidar2img'],
+            img_h=int(g['img_shape'][0]), img_w=int(g['img_shape'][1]))
+    out.backward(gu.T(g['grad_out']))
+    assert rel_err(out, g['out']) <= 1e-5
+    assert rel_err(bevq.grad, g['grad_bev_query']) <= 1e-4
+    assert rel_err(prev.grad, g['grad_prev_bev']) <= 1e-4
+    assert rel_err(feat.grad, g['grad_feat']) <= 1e-4
+    pg = gu.pgrads(g)
+    for n, p in o.named_parameters():
+        assert rel_err(p.grad, pg[n]) <= 1e-4, n
+
+
 def test_maptrv2_decoder_host_logic_matches_reference_golden():
     """MapTRv2Decoder + MapTRv2DecoupledDetrTransformerDecoderLayer of the package (the
     inter-vector / intra-vector reshapes around the two self-attentions, cross-attention call
