@@ -42,12 +42,12 @@ class _RowWiseEncoder(torch.nn.Module):
         return out
 
 
-def _worker(rank, world, port, bev_h, bev_w, ret):
+def _worker(rank, world, port, bev_h, bev_w, ret, bs=2):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         from apollo_vision_net_b200.parallel import sharded_encoder_forward
-        C, bs = 16, 2
+        C = 16
         g = torch.Generator().manual_seed(1)
         HW = bev_h * bev_w
         bevq, pos, prev = (torch.randn(HW, bs, C, generator=g) for _ in range(3))
@@ -65,12 +65,14 @@ def _worker(rank, world, port, bev_h, bev_w, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,bev_h,bev_w', [(2, 10, 6), (2, 7, 5), (3, 8, 4)])
-def test_row_sharded_forward_equals_full(world, bev_h, bev_w):
+@pytest.mark.parametrize('world,bev_h,bev_w,bs', [(2, 10, 6, 2), (2, 7, 5, 2), (3, 8, 4, 2), (2, 10, 6, 1)])
+def test_row_sharded_forward_equals_full(world, bev_h, bev_w, bs):
+    """Even and uneven row splits; bs = 1 with an even split takes the all-gather's no-copy path
+    (the gathered buffer is already in row order)."""
     ctx = mp.get_context('spawn')
     ret = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, bev_h, bev_w, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bev_h, bev_w, ret, bs)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
