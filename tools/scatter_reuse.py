@@ -67,6 +67,7 @@ def main():
     # totals[tile][level] = [updates, unique slots per (tile, cam, head), unique per (row = q, cam, head)]
     totals = {t: np.zeros((len(levels), 2), dtype=np.int64) for t in tiles}
     row_unique = np.zeros(len(levels), dtype=np.int64)
+    per_slot = [[] for _ in levels]
     for c in range(6):
         qs = np.nonzero(hit[c])[0]
         ref = uv[c, qs]                                                      # (n, D, 2)
@@ -93,6 +94,8 @@ def main():
             slot = h * (Hl * Wl) + pix                                       # (head, pixel) of this camera
             nslot = M * Hl * Wl
             row_unique[li] += len(np.unique(q * nslot + slot))
+            _, cnt = np.unique(slot, return_counts=True)          # contributors per (camera, head, pixel) slot
+            per_slot[li].append(cnt)
             for t in tiles:
                 tid = (qy[q] // t[0]) * ((bev + t[1] - 1) // t[1]) + qx[q] // t[1]
                 totals[t][li, 0] += len(slot)
@@ -101,6 +104,12 @@ def main():
     print('level  updates(M)  distinct/updates within one (query, head) row')
     for li in range(len(levels)):
         print(f'  {li}     {upd[li] / 1e6:7.2f}     {row_unique[li] / upd[li]:.3f}')
+    print('contributors per touched (camera, head, pixel) slot over the whole frame (an owner-computes backward '
+          'would walk these lists):')
+    for li, (Hl, Wl) in enumerate(levels):
+        c = np.concatenate(per_slot[li])
+        print(f'  L{li}: {len(c)} of {6 * M * Hl * Wl} slots touched, updates per slot mean {c.mean():.0f}  '
+              f'median {np.median(c):.0f}  p99 {np.percentile(c, 99):.0f}  max {c.max()}')
     for t in tiles:
         tot = totals[t]
         n_tiles = ((bev + t[0] - 1) // t[0]) * ((bev + t[1] - 1) // t[1])
