@@ -14,9 +14,10 @@ from .fused_ops import (QueueDeformAttnFunction, SpatialCrossAttnFunction, bev_p
 from .registry import (ATTENTION, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, build_attention,
                        build_transformer_layer, build_transformer_layer_sequence)
 from .multi_scale_deformable_attn_function import (
-    MultiScaleDeformableAttnFunction_fp16, MultiScaleDeformableAttnFunction_fp32, ext_module,
+    MultiScaleDeformableAttnFunction_bf16, MultiScaleDeformableAttnFunction_fp16,
+    MultiScaleDeformableAttnFunction_fp32, ext_module,
     ms_deform_attn_backward, ms_deform_attn_forward)
 
 __all__ = ['build', 'launch_count', 'ext_module', 'ms_deform_attn_forward',
            'ms_deform_attn_backward', 'MultiScaleDeformableAttnFunction_fp32',
-           'MultiScaleDeformableAttnFunction_fp16']
+           'MultiScaleDeformableAttnFunction_fp16', 'MultiScaleDeformableAttnFunction_bf16']

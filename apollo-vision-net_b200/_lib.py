@@ -37,8 +37,8 @@ _SIGNATURES = {
     'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 12 + [_c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
     'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_vp]),
     'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
-    'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp]),
-    'unscale_cast': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp]),
+    'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp]),
+    'unscale_cast': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_vp]),
     'rowops_workspace_rows': (_c_int, []),
     'ln_fwd': (_c_int, [_c_vp] * 6 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
@@ -53,6 +53,7 @@ _SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 3          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
 
 
 def _stale():
@@ -107,6 +108,19 @@ def lib():
                 '`python -c "import __graft_entry__ as g; g.build()"` at the repo root. '
                 'There is no CPU fallback.')
         l = ctypes.CDLL(LIB_PATH)
+        # the .so is a build artefact that travels outside version control: refuse a binary whose
+        # argument lists may differ from the ctypes signatures below, and say so when it is older
+        # than its sources (the caller decides whether to rebuild: build() does)
+        l.msda_abi_version.restype = _c_int
+        l.msda_abi_version.argtypes = []
+        found = int(l.msda_abi_version())
+        if found != ABI_VERSION:
+            raise RuntimeError(
+                f'{LIB_PATH} has ABI version {found}, this package needs {ABI_VERSION}: stale binary. '
+                'Rebuild with `python -c "import __graft_entry__ as g; g.build()"`.')
+        if not os.environ.get('APOLLO_B200_LIB') and _stale():
+            import warnings
+            warnings.warn(f'{LIB_PATH} is older than its sources under {CSRC}; rebuild with build()')
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype = res
@@ -171,3 +185,9 @@ def header_symbols():
     text = open(HEADER).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
     return sorted(set(re.findall(r'\b([a-z_0-9]+)\s*\(', text)) - {'defined'})
+
+
+def header_abi_version():
+    """MSDA_ABI_VERSION as include/msda_b200.h declares it."""
+    import re
+    return int(re.search(r'#define\s+MSDA_ABI_VERSION\s+(\d+)', open(HEADER).read()).group(1))

@@ -381,14 +381,15 @@ int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, f
   return launch_colsum(dy, y, dx, colsum_out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
-int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream) {
-  if (n < 0 || !ws || (n > 0 && !g)) return set_error(MSDA_ERR_BAD_ARGUMENT, "grad_amax_scale: bad argument");
-  return launch_grad_scale(g, n, dtype, ws, static_cast<cudaStream_t>(stream));
+int grad_amax_scale(const void* g, int64_t n, int dtype, float limit, float* ws, void* stream) {
+  if (n < 0 || !ws || (n > 0 && !g) || !(limit > 0.f))
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "grad_amax_scale: bad argument");
+  return launch_grad_scale(g, n, dtype, limit, ws, static_cast<cudaStream_t>(stream));
 }
 
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
-                 void* colsum_out, float* partial, int C, void* stream) {
+                 void* colsum_out, float* partial, int C, int32_t* overflow_flag, void* stream) {
   if (colsum_out) {
     const int64_t m = (tail && tail_copies > 0) ? map_elems : n;
     if (!partial || C <= 0 || C % 8 != 0 || 256 % (C / 8) != 0 || m % C != 0 || n % 8 != 0)
@@ -402,7 +403,7 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
     return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: inconsistent tail replica sizes");
   if (n == 0) return MSDA_OK;
   return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, tail, tail_copies, map_elems, tail_elems,
-                             partial, colsum_out, C, static_cast<cudaStream_t>(stream));
+                             partial, colsum_out, C, overflow_flag, static_cast<cudaStream_t>(stream));
 }
 
 int bev_flatten_level(const void* feat, const void* cams_embeds, const void* level_embed, void* feat_flatten,

@@ -344,7 +344,8 @@ fused_fwd_kernel(const FusedArgs a) {
           for (int j = 0; j < TPH; ++j) {
             if (j < count && mine) {
               const uint4 o = *reinterpret_cast<const uint4*>(my_rec + 8 * j);
-              const uint4 u00 = ldg128(vb + o.x);
+              if (!(o.x & 1u)) continue;          // sample entirely outside the map: nothing to read
+              const uint4 u00 = ldg128(vb + (o.x & ~15u));
               const uint4 u01 = ldg128(vb + o.y);
               const uint4 u10 = ldg128(vb + o.z);
               const uint4 u11 = ldg128(vb + o.w);
@@ -363,8 +364,11 @@ fused_fwd_kernel(const FusedArgs a) {
           const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
           const int base = lv.t.start[l] * pix_stride;
           constexpr unsigned ES = sizeof(T);
+          // (bit 0 of the first offset -- offsets are multiples of 16 -- flags a sample with at least
+          // one corner inside the map; the others are skipped, so a non-finite value only reaches
+          // samples that touch it)
           *reinterpret_cast<uint4*>(my_rec + 8 * chunk) =
-              make_uint4((unsigned)(base + c.o00) * ES, (unsigned)(base + c.o01) * ES,
+              make_uint4(((unsigned)(base + c.o00) * ES) | (c.valid ? 1u : 0u), (unsigned)(base + c.o01) * ES,
                          (unsigned)(base + c.o10) * ES, (unsigned)(base + c.o11) * ES);
           if constexpr (MIXED) {
             *reinterpret_cast<uint2*>(my_rec + 8 * chunk + 4) =
@@ -402,6 +406,7 @@ fused_fwd_kernel(const FusedArgs a) {
           // exchange would cost more than it saves
           auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
             const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+            if (c.valid == 0u) return;            // entirely outside the map
             const uint4 u00 = ldg128(lbase + c.o00);
             const uint4 u01 = ldg128(lbase + c.o01);
             const uint4 u10 = ldg128(lbase + c.o10);

@@ -92,8 +92,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float lx = to_f32<CT>(my_loc[2 * s]);
       const float ly = to_f32<CT>(my_loc[2 * s + 1]);
       const float a = to_f32<CT>(my_att[s]);
-      // clamped corners: unpredicated 128-bit loads, weight zero for corners outside the map
+      // clamped corners: unpredicated 128-bit loads, weight zero for corners outside the map.  An
+      // invalid corner of a partly valid sample clamps onto the pixel of one of its valid corners;
+      // a sample entirely outside the map is skipped, so a non-finite value only reaches the samples
+      // that touch it (the reference kernel never reads such corners)
       const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      if (c.valid == 0u) continue;
       const uint4 u00 = ldg128(lbase + c.o00);
       const uint4 u01 = ldg128(lbase + c.o01);
       const uint4 u10 = ldg128(lbase + c.o10);

@@ -367,7 +367,7 @@ static int ln_dispatch(bool bwd, const void* x, const void* dy, const void* gamm
 // ws layout (floats): [0] ticket counter, [1] running max bits, [16] scale out.
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) {
+grad_scale_kernel(const T* __restrict__ g, long long n, float limit, float* __restrict__ ws) {
   constexpr int VEC = Vec16<T>::N;
   float m = 0.f;
   const long long nv = n / VEC;
@@ -395,7 +395,7 @@ grad_scale_kernel(const T* __restrict__ g, long long n, float* __restrict__ ws) 
     __threadfence();
     const float amax = __uint_as_float(atomicExch(wsu + 1, 0u));
     float s = 1.f;
-    if (amax > 0.f && isfinite(amax)) s = exp2f(floorf(log2f(4.0f / amax)));
+    if (amax > 0.f && isfinite(amax)) s = exp2f(floorf(log2f(limit / amax)));
     ws[16] = s;
     wsu[0] = 0u;
   }
@@ -411,8 +411,9 @@ template <typename TO, bool COLSUM>
 __global__ void __launch_bounds__(256)
 unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n,
                     const __half* __restrict__ tail, int copies, long long map_elems, long long tail_elems,
-                    float* __restrict__ ws, TO* __restrict__ colsum_out, int cgroups) {
+                    float* __restrict__ ws, TO* __restrict__ colsum_out, int cgroups, int* __restrict__ overflow) {
   const float inv = 1.0f / __ldg(scale);             // power of two: exact
+  bool bad = false;                                  // a saturated (inf / NaN) accumulator slot was seen
   // grid: x over the 16-byte chunks of a value map, y over the maps (one map of n elements
   // when there are no tail replicas)
   const long long maps = n / map_elems;
@@ -436,7 +437,10 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
         }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] *= inv;
+      for (int k = 0; k < 8; ++k) {
+        bad |= !(fabsf(v[k]) <= 3.0e38f);            // fp16 inf / NaN survive the conversion and the sums
+        v[k] *= inv;
+      }
       if (COLSUM) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) csum[k] += v[k];
@@ -461,7 +465,13 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
     for (; i < chunks; i += stride) finish(i, ldg128(a + i * 8));
   }
   if (blockIdx.x == 0 && blockIdx.y == 0)             // (only without replicas: map_elems need not divide by 8)
-    for (long long i = maps * chunks * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = from_f32<TO>(__half2float(acc[i]) * inv);
+    for (long long i = maps * chunks * 8 + threadIdx.x; i < n; i += blockDim.x) {
+      const float v = __half2float(acc[i]);
+      bad |= !(fabsf(v) <= 3.0e38f);
+      out[i] = from_f32<TO>(v * inv);
+    }
+  // sticky flag word: the host may poll it whenever it likes (no synchronisation on the good path)
+  if (overflow != nullptr && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(overflow, 1);
   if constexpr (COLSUM) {
     // threads with the same (threadIdx.x % cgroups) own the same 8 columns (map_elems, the x-stride and 256
     // are multiples of 8 * cgroups)
@@ -498,11 +508,11 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
   }
 }
 
-int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStream_t st) {
+int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, cudaStream_t st) {
   const int grid = row_grid();
-  if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, ws);
-  else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, ws);
-  else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, ws);
+  if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, limit, ws);
+  else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, limit, ws);
+  else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, limit, ws);
   count_launch();
   return check_launch("grad_amax_scale");
 }
@@ -510,18 +520,18 @@ int launch_grad_scale(const void* g, long long n, int dtype, float* ws, cudaStre
 template <typename TO>
 static void unscale_launch(dim3 grid, cudaStream_t st, const __half* a, void* out, const float* scale, long long n,
                            const __half* t, int copies, long long map_elems, long long tail_elems, float* ws,
-                           void* colsum_out, int cgroups) {
+                           void* colsum_out, int cgroups, int* overflow) {
   if (colsum_out)
     unscale_cast_kernel<TO, true><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
-                                                         tail_elems, ws, static_cast<TO*>(colsum_out), cgroups);
+                                                         tail_elems, ws, static_cast<TO*>(colsum_out), cgroups, overflow);
   else
     unscale_cast_kernel<TO, false><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
-                                                          tail_elems, nullptr, nullptr, 1);
+                                                          tail_elems, nullptr, nullptr, 1, overflow);
 }
 
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,
-                        float* ws, void* colsum_out, int C, cudaStream_t st) {
+                        float* ws, void* colsum_out, int C, int* overflow, cudaStream_t st) {
   const __half* a = static_cast<const __half*>(acc16);
   const __half* t = static_cast<const __half*>(tail);
   if (!t || copies <= 0) { t = nullptr; copies = 0; map_elems = n; tail_elems = 0; }
@@ -534,9 +544,9 @@ int launch_unscale_cast(const void* acc16, void* out, const float* scale, long l
   if (gx > need) gx = need > 0 ? need : 1;
   const dim3 grid((unsigned)gx, (unsigned)(maps < 65535 ? maps : 65535));
   const int cgroups = C / 8;
-  if (out_dtype == MSDA_F32) unscale_launch<float>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
-  else if (out_dtype == MSDA_BF16) unscale_launch<__nv_bfloat16>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
-  else unscale_launch<__half>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups);
+  if (out_dtype == MSDA_F32) unscale_launch<float>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
+  else if (out_dtype == MSDA_BF16) unscale_launch<__nv_bfloat16>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
+  else unscale_launch<__half>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
   count_launch();
   return check_launch("unscale_cast");
 }

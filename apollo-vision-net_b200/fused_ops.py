@@ -89,7 +89,7 @@ def _check_value(value):
 
 
 _scale_ws = {}
-
+_overflow_flags = {}
 
 # fp16 accumulator: replicas of the coarse tail of every value map (see sca_bwd in msda_b200.h).
 # The coarse pyramid levels sit at the end of the pixel axis and hold ~1/16 of the pixels but half of
@@ -97,27 +97,80 @@ _scale_ws = {}
 _TAIL_FRACTION = 16
 _TAIL_COPIES = 7
 
+_accum_mode = ['fp32' if __import__('os').environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1' else 'fp16']
 
-def _accumulator(value, g_out, num_levels=1):
+
+def set_grad_accumulator(mode):
+    """Accumulator of grad_value in the fused backward kernels for 16-bit value dtypes: ``'fp16'``
+    (default: scaled fp16, half the L2 reduction traffic, overflow excluded by the scale bound of
+    :func:`_accumulator`) or ``'fp32'`` (the reference's arithmetic: fp32 atomics).  fp32 models always
+    use fp32.  Returns the previous mode.  (``APOLLO_B200_FP32_ACCUM=1`` selects 'fp32' at import.)"""
+    if mode not in ('fp16', 'fp32'):
+        raise ValueError(f"grad accumulator mode must be 'fp16' or 'fp32', got {mode!r}")
+    prev, _accum_mode[0] = _accum_mode[0], mode
+    return prev
+
+
+class grad_accumulator:
+    """``with grad_accumulator('fp32'): ...`` -- scoped :func:`set_grad_accumulator`."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_grad_accumulator(self.mode)
+
+    def __exit__(self, *exc):
+        set_grad_accumulator(self.prev)
+
+
+def _overflow_flag(dev):
+    f = _overflow_flags.get(dev.index)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=dev)
+        _overflow_flags[dev.index] = f
+    return f
+
+
+def grad_accumulator_overflowed(device=None, reset=True):
+    """True when an fp16 accumulator pass on ``device`` met a non-finite slot since the last reset
+    (sticky device flag set by ``unscale_cast``).  Reading it synchronises; the training path never
+    does.  The scale bound makes this unreachable for finite inputs -- it is the safety net."""
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    f = _overflow_flags.get(dev.index)
+    if f is None:
+        return False
+    hit = bool(int(f.item()))
+    if reset:
+        f.zero_()
+    return hit
+
+
+def _accumulator(value, g_out, num_levels=1, rows_per_slot=0):
     """grad_value accumulator for the fused backward kernels.
 
     fp32 value: fp32 accumulator (red.global.add.v4.f32).  16-bit value: fp16 accumulator scaled by
     a power of two derived on the device from max|g_out| (no host sync) -- half the L2 sectors per
-    update; set ``APOLLO_B200_FP32_ACCUM=1`` to force fp32.  Multi-level value maps additionally get
-    replicas of their coarse tail.  Returns (buffer, code, scale_tensor, tail, tail_pixels).
+    update; :func:`set_grad_accumulator` selects fp32 instead.  ``rows_per_slot`` = how many
+    (query, head) rows can add into one slot of a value map (the number of queries): a row's attention
+    weights sum to one and bilinear weights are <= 1, so with a single scaled contribution bounded by
+    ``min(4, 32768 / rows_per_slot)`` no slot can exceed 32768 -- fp16 cannot overflow whatever the
+    signs and locations.  Multi-level value maps additionally get replicas of their coarse tail.
+    Returns (buffer, code, scale_tensor, tail, tail_pixels).
     """
     import os
     dev = value.device
-    if value.dtype == torch.float32 or os.environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1':
+    if value.dtype == torch.float32 or _accum_mode[0] == 'fp32':
         return torch.zeros(value.shape, dtype=torch.float32, device=dev), _lib.F32, None, None, 0
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _scale_ws.get(key)
     if ws is None:
         ws = torch.zeros(64, dtype=torch.float32, device=dev)
         _scale_ws[key] = ws
+    limit = min(4.0, 32768.0 / max(1, int(rows_per_slot)))
     with torch.cuda.device(dev):
         _lib.call('grad_amax_scale', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
-                  ws.data_ptr(), _stream_ptr(value))
+                  float(limit), ws.data_ptr(), _stream_ptr(value))
     maps, Nk, M, Dh = value.shape
     tail, tail_px = None, 0
     if num_levels > 1 and Nk >= 4 * _TAIL_FRACTION and (M * Dh) % 8 == 0 and \
@@ -143,7 +196,7 @@ def _finish_accumulator(acc, code, scale, value, tail=None, tail_px=0):
                   _DTYPE_CODE[value.dtype], None if tail is None else tail.data_ptr(),
                   0 if tail is None else tail.shape[0], Nk * M * Dh, tail_px * M * Dh,
                   None if sums is None else sums.data_ptr(), None if ws is None else ws.data_ptr(), C,
-                  _stream_ptr(value))
+                  _overflow_flag(value.device).data_ptr(), _stream_ptr(value))
     if with_sums:
         rowops.offer_bias_grad(out, sums)
     return out
@@ -259,7 +312,7 @@ class SpatialCrossAttnFunction(Function):
         off_ptr = coords[0].data_ptr()
         log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_slots = g_slots.to(value.dtype).contiguous()
-        g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L)
+        g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L, rows_per_slot=HW)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,
@@ -322,7 +375,7 @@ class QueueDeformAttnFunction(Function):
         off_ptr = coords[0].data_ptr()
         log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_out = g_out.to(value.dtype).contiguous()
-        g_value, acc_code, acc_scale, _, _ = _accumulator(value, g_out)
+        g_value, acc_code, acc_scale, _, _ = _accumulator(value, g_out, rows_per_slot=Nq)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('tsa_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,

@@ -6,7 +6,8 @@ import warnings
 import torch
 import torch.nn as nn
 
-from ..multi_scale_deformable_attn_function import (MultiScaleDeformableAttnFunction_fp16,
+from ..multi_scale_deformable_attn_function import (MultiScaleDeformableAttnFunction_bf16,
+                                                    MultiScaleDeformableAttnFunction_fp16,
                                                     MultiScaleDeformableAttnFunction_fp32)
 from ..registry import BaseModule, constant_init, xavier_init
 from ..rowops import Linear, linear, linear_add_layernorm
@@ -105,11 +106,13 @@ def finish_block(mod, output, identity, post_norm=None):
 def msda_apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
                im2col_step):
     """Op-boundary call, as the reference selects it (spatial_cross_attention.py:389-396): fp32
-    tensors use the ``_fp32`` Function; half / bf16 value uses the ``_fp16`` one."""
+    tensors use the ``_fp32`` Function, an fp16 value the ``_fp16`` one and a bf16 value the
+    ``_bf16`` one (whose autocast decorator keeps bf16 instead of casting to fp16)."""
     if not value.is_cuda:
         raise RuntimeError('deformable attention needs CUDA tensors: this build has no CPU path '
                            '(the reference falls back to multi_scale_deformable_attn_pytorch)')
-    fn = (MultiScaleDeformableAttnFunction_fp32 if value.dtype == torch.float32
-          else MultiScaleDeformableAttnFunction_fp16)
+    fn = {torch.float32: MultiScaleDeformableAttnFunction_fp32,
+          torch.bfloat16: MultiScaleDeformableAttnFunction_bf16}.get(value.dtype,
+                                                                     MultiScaleDeformableAttnFunction_fp16)
     return fn.apply(value, spatial_shapes, level_start_index, sampling_locations,
                     attention_weights, im2col_step)

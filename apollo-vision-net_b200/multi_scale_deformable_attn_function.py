@@ -195,3 +195,23 @@ class MultiScaleDeformableAttnFunction_fp16(Function):
     @custom_bwd
     def backward(ctx, grad_output):
         return _backward(ctx, grad_output)
+
+
+class MultiScaleDeformableAttnFunction_bf16(Function):
+    """bf16 twin of ``_fp16`` (not in the reference): under ``torch.autocast(dtype=bfloat16)`` the
+    inputs are cast to bf16, not to fp16 -- ``_fp16``'s decorator would silently turn a bf16 value
+    into fp16 (range 65504) -- and outside autocast nothing is cast.  The module-level paths pick
+    the Function by the value dtype (``deform_common.msda_apply``)."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=torch.bfloat16)
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                sampling_locations, attention_weights, im2col_step):
+        return _forward(ctx, value, value_spatial_shapes, value_level_start_index,
+                        sampling_locations, attention_weights, im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, grad_output):
+        return _backward(ctx, grad_output)

@@ -34,12 +34,15 @@ def _workspace(device, floats):
     return ws
 
 
+_LN_WIDTHS = (128, 256, 512, 1024)
+
+
 def _ln_supported(x, weight, bias):
     if not x.is_cuda or weight is None or bias is None or x.dtype not in _DTYPE_CODE:
         return False
-    C = x.shape[-1]
-    vec = 4 if x.dtype == torch.float32 else 8
-    return C % (32 * vec) == 0 and C <= 1024 and weight.dtype == x.dtype and bias.dtype == x.dtype
+    # exactly the widths csrc/rowops.cu instantiates (ln_dispatch: C / 32 in {4, 8, 16, 32}); any
+    # other width takes torch's layer_norm instead of failing in the kernel dispatch
+    return x.shape[-1] in _LN_WIDTHS and weight.dtype == x.dtype and bias.dtype == x.dtype
 
 
 class LayerNormFunction(Function):

@@ -395,7 +395,7 @@ def run_b200(args):
     L, P, M, Dh = len(levels), SCA_POINTS, HEADS, C // HEADS
     ev = 2                       # bf16 value / outputs / upstream gradients
     ec = 2                       # offsets / logits and their gradients arrive in the model dtype (bf16)
-    ea = 4 if os.environ.get('APOLLO_B200_FP32_ACCUM', '0') == '1' else 2   # grad_value accumulator
+    ea = 4 if pkg.fused_ops._accum_mode[0] == 'fp32' else 2      # grad_value accumulator
     # compulsory traffic, every operand once: value + offsets + logits + ref_cam +
     # hit bits + out; backward adds g_out (= |out|), 2 x accumulator (zero-fill + final), g_offsets, g_logits
     sca_fwd_bytes = (6 * Nk * C * ev + HW * M * L * P * 3 * ec + 6 * HW * PILLAR * 2 * 4 + HW * 4

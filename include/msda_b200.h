@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 3
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -215,18 +215,25 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
 
 /* Helpers of the fp16 gradient accumulator.
  *   grad_amax_scale: ws is a zero-initialised fp32 scratch of >= 64 floats (left zeroed except
- *     ws[16]); on return (stream order) ws[16] = 2^floor(log2(4 / max|g|)) (1 when g is all zero):
- *     single contributions are <= 4 in fp16, 16 000 same-sign maximal updates stay finite.
+ *     ws[16]); on return (stream order) ws[16] = 2^floor(log2(limit / max|g|)) (1 when g is all zero),
+ *     i.e. a single scaled contribution is <= limit in fp16.  Overflow is excluded BY CONSTRUCTION when
+ *     limit <= 32768 / R with R = the number of (query, head) rows that can add into one slot of a value
+ *     map (= the number of queries): the attention weights of a row sum to one and bilinear weights are
+ *     <= 1, so a row adds at most max|g| to any slot and a slot's sum stays <= 32768 < 65504 whatever the
+ *     signs and locations.  The host passes limit = min(4, 32768 / Nq).
  *   unscale_cast: out[i] = (out_dtype)((acc_f16[i] + replicas) / *scale).  `tail` = the replicas
  *     of sca_bwd's g_value_tail (or NULL): acc is n / map_elems value maps of map_elems elements
  *     (Nk*M*Dh); the last tail_elems (tail_pixels*M*Dh) of each also sum tail_copies replica maps.
  *     colsum_out (C,) out_dtype or NULL: additionally the sums over all rows of the (n / C, C) view of
  *     `out` -- the bias gradient of the value projection -- saving a pass over the tensor; `partial` is
- *     the row kernels' zero-initialised scratch (64 + C floats, see below); C = 8 * (a divisor of 256). */
-int grad_amax_scale(const void* g, int64_t n, int dtype, float* ws, void* stream);
+ *     the row kernels' zero-initialised scratch (64 + C floats, see below); C = 8 * (a divisor of 256).
+ *     overflow_flag (may be NULL): a device int32 that is OR-ed with 1 when a non-finite accumulator
+ *     slot is met -- a sticky word the host can poll at its leisure (defence in depth behind the
+ *     scale bound above; nothing synchronises on the good path). */
+int grad_amax_scale(const void* g, int64_t n, int dtype, float limit, float* ws, void* stream);
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
-                 void* colsum_out, float* partial, int C, void* stream);
+                 void* colsum_out, float* partial, int C, int32_t* overflow_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section

@@ -368,8 +368,13 @@ class OracleBEVFormerEncoder(nn.Module):
 
     def forward(self, bev_query, key, value, bev_h=None, bev_w=None, bev_pos=None,
                 spatial_shapes=None, level_start_index=None, prev_bev=None, shift=None,
-                lidar2img=None, img_h=None, img_w=None):
-        """bev_query, bev_pos (HW, bs, C); key=value (num_cam, Nk, bs, C); prev_bev (HW, bs, C) | None."""
+                lidar2img=None, img_h=None, img_w=None, layer_inputs=None, return_all=False):
+        """bev_query, bev_pos (HW, bs, C); key=value (num_cam, Nk, bs, C); prev_bev (HW, bs, C) | None.
+
+        ``layer_inputs`` (test aid): a list with one (bs, HW, C) tensor or None per layer; where
+        given, that layer runs on it instead of the previous layer's output ("teacher forcing": a
+        deep low-precision model is compared one layer at a time).  ``return_all`` returns the list
+        of every layer's output instead of the last one."""
         bs = bev_query.size(1)
         ref_3d = reference_points_3d(bev_h, bev_w, self.pc_range[5] - self.pc_range[2],
                                      self.num_points_in_pillar, bs=bs,
@@ -390,10 +395,14 @@ class OracleBEVFormerEncoder(nn.Module):
         else:
             hybrid = torch.stack([ref_2d, ref_2d], 1).reshape(bs * 2, len_bev, nlvl, 2)
         out = bev_query
-        for layer in self.layers:
+        outs = []
+        for i, layer in enumerate(self.layers):
+            if layer_inputs is not None and layer_inputs[i] is not None:
+                bev_query = layer_inputs[i]
             out = layer(bev_query, key, value, bev_pos=bev_pos, ref_2d=hybrid, ref_3d=ref_3d,
                         bev_h=bev_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
                         level_start_index=level_start_index, reference_points_cam=ref_cam,
                         bev_mask=bev_mask, prev_bev=prev_bev)
             bev_query = out
-        return out
+            outs.append(out)
+        return outs if return_all else out

@@ -10,13 +10,27 @@ def test_library_builds_loads_and_exports_header_symbols():
     import apollo_vision_net_b200 as pkg
     pkg.build()
     lib = pkg._lib.lib()
-    assert lib.msda_abi_version() == 2
+    assert lib.msda_abi_version() == pkg._lib.ABI_VERSION == pkg._lib.header_abi_version()
     syms = pkg._lib.header_symbols()
     assert {'msda_fwd', 'msda_bwd', 'bev_point_sampling', 'sca_fwd', 'sca_bwd', 'tsa_fwd',
             'tsa_bwd', 'msda_fwd_host', 'msda_fwd_bwd_host'} <= set(syms)
     for s in syms:
         assert hasattr(lib, s), f'{s} declared in include/msda_b200.h but not exported'
     assert set(pkg._lib._SIGNATURES) == set(syms)
+
+
+def test_stale_binary_is_refused(monkeypatch):
+    """A binary whose ABI version differs from the ctypes signatures must not be called through them
+    (the .so travels outside version control)."""
+    import apollo_vision_net_b200 as pkg
+    pkg.build()
+    monkeypatch.setattr(pkg._lib, '_lib', None)
+    monkeypatch.setattr(pkg._lib, 'ABI_VERSION', pkg._lib.ABI_VERSION + 1)
+    with pytest.raises(RuntimeError, match='stale binary'):
+        pkg._lib.lib()
+    monkeypatch.undo()
+    pkg._lib._lib = None
+    assert pkg._lib.lib().msda_abi_version() == pkg._lib.ABI_VERSION
 
 
 def test_library_is_sm100a_only():

@@ -399,7 +399,8 @@ def test_fused_bf16_backward_accumulators(accum, monkeypatch):
     also for tiny upstream gradients (the scale is derived on the device from max|g_out|)."""
     from apollo_vision_net_b200.fused_ops import QueueDeformAttnFunction
     from oracle.msda_oracle import msda_torch
-    monkeypatch.setenv('APOLLO_B200_FP32_ACCUM', '1' if accum == 'fp32' else '0')
+    import apollo_vision_net_b200.fused_ops as fo
+    monkeypatch.setattr(fo, '_accum_mode', [accum])
     g = torch.Generator().manual_seed(31)
     bs, H, W, M, Dh, L, P, Nq = 1, 24, 40, 8, 32, 1, 4, 3000
     value = torch.randn(bs, H * W, M, Dh, generator=g).bfloat16()
@@ -969,3 +970,27 @@ def test_ffn_relu_backward_with_fused_bias_grad(dtype, monkeypatch):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     for a, b in zip(fused[1:], plain[1:]):
         assert rel_err(a, b) <= tol
+
+
+@pytest.mark.parametrize('C', [384, 768, 640, 96])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_layernorm_unsupported_widths_fall_back_to_torch(C, dtype):
+    """Widths the row kernels do not instantiate (anything but 128/256/512/1024) must take torch's
+    layer_norm -- LayerNorm, the fused Linear+residual+LayerNorm tail and the FFN tail alike --
+    instead of failing in the kernel dispatch."""
+    import torch.nn.functional as F
+    from apollo_vision_net_b200 import rowops
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(70, C, generator=g).to(dtype).to(DEV).requires_grad_(True)
+    res = torch.randn(70, C, generator=g).to(dtype).to(DEV)
+    ln = rowops.LayerNorm(C).to(DEV).to(dtype)
+    lin = rowops.Linear(C, C).to(DEV).to(dtype)
+    n0 = rowops._lib.launch_count()
+    y = ln(x)
+    z = rowops.linear_add_layernorm(x, lin, res, ln)
+    (y.float().sum() + z.float().sum()).backward()
+    assert torch.equal(y, F.layer_norm(x, (C,), ln.weight, ln.bias, ln.eps))
+    assert torch.equal(z, F.layer_norm(lin(x) + res, (C,), ln.weight, ln.bias, ln.eps))
+    assert x.grad is not None and torch.isfinite(x.grad.float()).all()
+    # no LayerNorm kernel of ours ran (the Linear's bias column sum may)
+    assert rowops._lib.launch_count() - n0 <= 4

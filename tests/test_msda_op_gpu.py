@@ -150,3 +150,98 @@ def test_linearity_at_base_size():
     idx = torch.arange(0, 9690, 97)
     ref = msda_torch(value, shapes, loc[:, idx], att[:, idx])
     assert rel_err(o1[:, idx.to(dev)], ref) <= 1e-5
+
+
+def test_host_buffer_entry_points_match_oracle():
+    """`msda_fwd_host` / `msda_fwd_bwd_host` (include/msda_b200.h): the op driven from pinned HOST
+    buffers through the C ABI -- H2D, kernels, D2H and the stream synchronisation inside the call --
+    against the CPU oracle (fp32: forward 1e-5, gradients 1e-4)."""
+    import ctypes
+    from apollo_vision_net_b200 import _lib
+    from oracle.msda_oracle import msda_torch_fwd_bwd
+    DEV = torch.device('cuda:0')
+    B, M, Dh, Nq, P = 2, 8, 32, 300, 4
+    levels = [(20, 30), (10, 15)]
+    value, shapes, starts, loc, att = make_op_inputs(B, levels, M, Dh, Nq, P, seed=11)
+    L, Nk = len(levels), value.shape[1]
+    g = torch.Generator().manual_seed(12)
+    go = torch.randn(B, Nq, M * Dh, generator=g)
+    ref_out, ref_gv, ref_gl, ref_ga = msda_torch_fwd_bwd(value, shapes, loc, att, go)
+
+    pin = lambda t: t.contiguous().pin_memory()
+    value_h, shapes_h, starts_h, loc_h, att_h, go_h = (pin(t) for t in (value, shapes, starts, loc, att, go))
+    out_h = torch.empty(B, Nq, M * Dh).pin_memory()
+    gv_h, gl_h, ga_h = (torch.empty(t.shape).pin_memory() for t in (value, loc, att))
+    need = int(_lib.lib().msda_host_scratch_bytes(B, Nk, M, Dh, L, Nq, P, _lib.F32, _lib.F32, 1))
+    assert need > 0
+    scratch = torch.empty(need, dtype=torch.uint8, device=DEV)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    n0 = _lib.launch_count()
+    _lib.call('msda_fwd_host', value_h.data_ptr(), shapes_h.data_ptr(), starts_h.data_ptr(), loc_h.data_ptr(),
+              att_h.data_ptr(), out_h.data_ptr(), B, Nk, M, Dh, L, Nq, P, _lib.F32, _lib.F32,
+              scratch.data_ptr(), need, stream)
+    assert rel_err(out_h, ref_out) <= 1e-5            # the call returns after its own stream sync
+    out_h.zero_()
+    _lib.call('msda_fwd_bwd_host', value_h.data_ptr(), shapes_h.data_ptr(), starts_h.data_ptr(),
+              loc_h.data_ptr(), att_h.data_ptr(), go_h.data_ptr(), out_h.data_ptr(), gv_h.data_ptr(),
+              gl_h.data_ptr(), ga_h.data_ptr(), B, Nk, M, Dh, L, Nq, P, _lib.F32, _lib.F32,
+              scratch.data_ptr(), need, stream)
+    assert _lib.launch_count() - n0 >= 3
+    assert rel_err(out_h, ref_out) <= 1e-5
+    assert rel_err(gv_h, ref_gv) <= 1e-4
+    assert rel_err(gl_h, ref_gl) <= 1e-4
+    assert rel_err(ga_h, ref_ga) <= 1e-4
+    # a scratch buffer that is too small is refused, not overrun
+    need_fwd = int(_lib.lib().msda_host_scratch_bytes(B, Nk, M, Dh, L, Nq, P, _lib.F32, _lib.F32, 0))
+    with pytest.raises(RuntimeError, match='scratch too small'):
+        _lib.call('msda_fwd_host', value_h.data_ptr(), shapes_h.data_ptr(), starts_h.data_ptr(),
+                  loc_h.data_ptr(), att_h.data_ptr(), out_h.data_ptr(), B, Nk, M, Dh, L, Nq, P, _lib.F32,
+                  _lib.F32, scratch.data_ptr(), need_fwd - 1, stream)
+
+
+def test_bf16_autocast_keeps_bf16():
+    """Under torch.autocast(dtype=bfloat16) the module-level op-boundary path must stay in bf16: a
+    bf16 value beyond the fp16 range (65504) must not be routed through an fp16 cast."""
+    import apollo_vision_net_b200 as pkg
+    from apollo_vision_net_b200.modules.deform_common import msda_apply
+    value, shapes, starts, loc, att = make_op_inputs(1, [(8, 9)], 8, 32, 40, 4, seed=21)
+    value = (value * 1.0e5).bfloat16()                  # |v| up to ~4e5 > 65504
+    ref = msda_torch(value.float(), shapes, loc, att)
+    dev = 'cuda:0'
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        out = msda_apply(value.to(dev), shapes.to(dev), starts.to(dev), loc.to(dev), att.to(dev), 64)
+    assert out.dtype == torch.bfloat16
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) <= 2e-2
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        out2 = pkg.MultiScaleDeformableAttnFunction_bf16.apply(
+            value.float().to(dev), shapes.to(dev), starts.to(dev), loc.to(dev), att.to(dev), 64)
+    assert out2.dtype == torch.bfloat16 and rel_err(out2, ref) <= 2e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_non_finite_value_only_reaches_samples_that_touch_it(dtype):
+    """A non-finite value pixel must only affect samples with a VALID corner on it: samples outside
+    the map, or whose clamped (zero-weight) corner address falls on that pixel, stay finite -- the
+    reference kernel skips such corners instead of multiplying them by zero."""
+    import apollo_vision_net_b200 as pkg
+    H, W = 6, 8
+    value, shapes, starts, loc, att = make_op_inputs(1, [(H, W)], 2, 32, 6, 2, seed=8, dtype=dtype)
+    value[0, 0] = float('inf')                         # pixel (0, 0): a clamp target of the border
+    value[0, W - 1] = float('nan')                     # pixel (0, W-1)
+    loc[:, 0] = -2.0                                   # query 0: every sample far outside
+    loc[:, 1, :, :, :, 0] = (W - 0.25) / W             # query 1: x_pix = W - 0.75 -> x1 = W is outside,
+    loc[:, 1, :, :, :, 1] = 3.5 / H                    #   rows 3 / 3 (y_pix = 3.0): never touches row 0
+    loc[:, 2, :, :, :, 0] = 4.5 / W                    # query 2: y_pix = -0.75 -> row -1 outside, row 0
+    loc[:, 2, :, :, :, 1] = -0.25 / H                  #   at x = 4, 5: finite pixels only
+    loc[:, 3:] = loc[:, 3:].clamp(0.3, 0.7)            # interior, rows >= 1
+    dev = 'cuda:0'
+    out = pkg.ms_deform_attn_forward(value.to(dev), shapes.to(dev), starts.to(dev), loc.to(dev),
+                                     att.to(dev), im2col_step=64).cpu()
+    assert torch.all(out[:, 0] == 0)
+    assert torch.isfinite(out.float()).all(), 'a zero-weight corner leaked a non-finite value'
+    v_ok = value.clone().float()
+    v_ok[0, 0] = 0
+    v_ok[0, W - 1] = 0
+    ref = msda_torch(v_ok, shapes, loc, att)
+    assert rel_err(out, ref) <= (1e-5 if dtype == torch.float32 else 1e-2)

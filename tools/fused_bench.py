@@ -86,7 +86,7 @@ def main():
 
         def bwd():
             if half_acc:
-                _lib.call('grad_amax_scale', gs.data_ptr(), gs.numel(), code, sws.data_ptr(), st)
+                _lib.call('grad_amax_scale', gs.data_ptr(), gs.numel(), code, float(min(4.0, 32768.0 / HW)), sws.data_ptr(), st)
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
@@ -121,7 +121,7 @@ def main():
 
         def tbwd():
             if half_acc:
-                _lib.call('grad_amax_scale', go.data_ptr(), go.numel(), code, sws.data_ptr(), st)
+                _lib.call('grad_amax_scale', go.data_ptr(), go.numel(), code, float(min(4.0, 32768.0 / HW)), sws.data_ptr(), st)
             _lib.call('tsa_bwd', value.data_ptr(), tshape.data_ptr(), tstart.data_ptr(), offsets.data_ptr(),
                       logits.data_ptr(), ref.data_ptr(), go.data_ptr(), gv.data_ptr(), goff.data_ptr(),
                       glog.data_ptr(), 1, Q, HW, M, Dh, 1, Pt, HW, W, -1.0, code, ccode, 0, 0, acode,
