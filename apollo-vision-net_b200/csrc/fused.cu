@@ -249,7 +249,8 @@ fused_fwd_kernel(const FusedArgs a) {
   constexpr int REC_PITCH = 8 * TPH + 4;               // in 4-byte words
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_w + (size_t)ROWS * pw);
   // per-sample (level | anchor << 16); the anchor follows the SCA point ordering p = k*D + z
-  // (quirk 5).  Keeps the integer divisions out of the sample loops.
+  // (quirk 5); TSA / decoder rows keep the queue entry there instead.  Keeps the integer divisions
+  // out of the sample loops.
   uint32_t* s_meta = s_rec + (size_t)ROWS * REC_PITCH;
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
@@ -257,7 +258,8 @@ fused_fwd_kernel(const FusedArgs a) {
   load_fused_levels(lv, a);
   for (int i = tid; i < S; i += kFusedThreads) {
     const int sl = i % LP, l = sl / a.P;
-    s_meta[i] = (uint32_t)l | ((uint32_t)((sl - l * a.P) % a.D) << 16);
+    const int hi = (MODE == MODE_SCA) ? (sl - l * a.P) % a.D : i / LP;   // Z-anchor | queue entry
+    s_meta[i] = (uint32_t)l | ((uint32_t)hi << 16);
   }
   __syncthreads();
 
@@ -360,16 +362,17 @@ fused_fwd_kernel(const FusedArgs a) {
           }
           __syncwarp();
         };
-        auto write_record = [&](int l, float lx, float ly, float w) {
+        // `map_off`: element offset of the sample's value map from the base the block is walked with
+        auto write_record = [&](int l, float lx, float ly, float w, unsigned map_off) {
           const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
-          const int base = lv.t.start[l] * pix_stride;
+          const unsigned base = map_off + (unsigned)(lv.t.start[l] * pix_stride);
           constexpr unsigned ES = sizeof(T);
           // (bit 0 of the first offset -- offsets are multiples of 16 -- flags a sample with at least
           // one corner inside the map; the others are skipped, so a non-finite value only reaches
           // samples that touch it)
           *reinterpret_cast<uint4*>(my_rec + 8 * chunk) =
-              make_uint4(((unsigned)(base + c.o00) * ES) | (c.valid ? 1u : 0u), (unsigned)(base + c.o01) * ES,
-                         (unsigned)(base + c.o10) * ES, (unsigned)(base + c.o11) * ES);
+              make_uint4(((base + (unsigned)c.o00) * ES) | (c.valid ? 1u : 0u), (base + (unsigned)c.o01) * ES,
+                         (base + (unsigned)c.o10) * ES, (base + (unsigned)c.o11) * ES);
           if constexpr (MIXED) {
             *reinterpret_cast<uint2*>(my_rec + 8 * chunk + 4) =
                 make_uint2(Vec16<T>::pack2(w * c.w00, w * c.w01), Vec16<T>::pack2(w * c.w10, w * c.w11));
@@ -396,42 +399,27 @@ fused_fwd_kernel(const FusedArgs a) {
                 const uint32_t meta = s_meta[s];
                 const float2 r = __ldg(rc + (meta >> 16));
                 const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-                write_record((int)(meta & 0xffffu), r.x + o.x, r.y + o.y, my_w[s]);
+                write_record((int)(meta & 0xffffu), r.x + o.x, r.y + o.y, my_w[s], 0u);
               }
               accumulate_block(vcam, min(TPH, LP - s0), mine);
             }
           }
-        } else if (live) {
-          // short rows (4-8 samples per queue entry): every lane sets up its own samples, the
-          // exchange would cost more than it saves
-          auto sample = [&](const T* lbase, int H, int W, float lx, float ly, float w) {
-            const Corners c = corner_setup(lx, ly, H, W, pix_stride);
-            if (c.valid == 0u) return;            // entirely outside the map
-            const uint4 u00 = ldg128(lbase + c.o00);
-            const uint4 u01 = ldg128(lbase + c.o01);
-            const uint4 u10 = ldg128(lbase + c.o10);
-            const uint4 u11 = ldg128(lbase + c.o11);
-            if constexpr (MIXED) {
-              blend(u00, u01, u10, u11, 0.f, 0.f, 0.f, 0.f, Vec16<T>::pack2(w * c.w00, w * c.w01),
-                    Vec16<T>::pack2(w * c.w10, w * c.w11));
-            } else {
-              blend(u00, u01, u10, u11, w * c.w00, w * c.w01, w * c.w10, w * c.w11, 0u, 0u);
-            }
-          };
-          for (int j = 0; j < a.groups; ++j) {
-            const T* vb = vhead + ((size_t)b * a.groups + j) * batch_stride;
-            for (int l = 0; l < a.L; ++l) {
-              const int H = lv.t.h[l], W = lv.t.w[l];
-              const T* lbase = vb + (size_t)lv.t.start[l] * pix_stride;
+        } else {
+          // TSA / decoder rows (4-8 samples per queue entry): the same exchange -- lane c sets up
+          // sample s0 + c of the row (queue entry and level from the shared table), every lane
+          // walks the block -- so a sample is set up once per row, not once per lane
+          const T* vb = vhead + (size_t)b * a.groups * batch_stride;
+          for (int s0 = 0; s0 < S; s0 += TPH) {
+            const int s = s0 + chunk;
+            if (s < S && live) {
+              const uint32_t meta = s_meta[s];
+              const int l = (int)(meta & 0xffffu), j = (int)(meta >> 16);
               const float2 r = __ldg(reinterpret_cast<const float2*>(
                   a.ref + ((((size_t)b * a.groups + j) * a.Nq + q) * a.L + l) * 2));
-#pragma unroll 4
-              for (int p = 0; p < a.P; ++p) {
-                const int s = (j * a.L + l) * a.P + p;
-                const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-                sample(lbase, H, W, r.x + o.x, r.y + o.y, my_w[s]);
-              }
+              const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
+              write_record(l, r.x + o.x, r.y + o.y, my_w[s], (unsigned)j * (unsigned)batch_stride);
             }
+            accumulate_block(vb, min(TPH, S - s0), live);
           }
         }
         float out[VEC];
@@ -487,7 +475,8 @@ fused_bwd_kernel(const FusedArgs a) {
   load_fused_levels(lv, a);
   for (int i = tid; i < S; i += kFusedThreads) {
     const int sl = i % LP, l = sl / a.P;
-    s_meta[i] = (uint32_t)l | ((uint32_t)((sl - l * a.P) % a.D) << 16);
+    const int hi = (MODE == MODE_SCA) ? (sl - l * a.P) % a.D : i / LP;   // Z-anchor | queue entry
+    s_meta[i] = (uint32_t)l | ((uint32_t)hi << 16);
   }
   __syncthreads();
 
@@ -702,12 +691,68 @@ fused_bwd_kernel(const FusedArgs a) {
         }
       };
 
+      // Blocks of TPH samples: lane c sets up sample s0 + c and publishes its record (corner
+      // offsets, fractions, validity, attention weight) in the row's exchange buffer; every lane
+      // then walks the block; after the lane sums, lane c owns the totals of sample s0 + c and
+      // adds them to the row's accumulators (d loc / d offset = 1 / (W_l, H_l) cancels the
+      // (W_l, H_l) factor of d pixel / d loc).  `have`: this lane's sample exists; `keep`: its row takes
+      // part (it accumulates the totals); (l, lx, ly, wgt) level, location and attention weight (zero
+      // for rows that do not take part: their gathers stay unpredicated, nothing is scattered);
+      // `map_off`: element offset of its value map from `coff`, the base the block is walked with.
+      auto run_block = [&](size_t coff, int s, int count, bool have, bool keep, int l, float lx, float ly,
+                           float wgt, unsigned map_off) {
+        float my_wgt = 0.f;
+        {
+          uint4 ro = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t rw[REC_WORDS - 4];
+#pragma unroll
+          for (int i = 0; i < REC_WORDS - 4; ++i) rw[i] = 0u;
+          if (have) {
+            const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
+            const unsigned base = map_off + (unsigned)(lv.t.start[l] * pix_stride);
+            my_wgt = wgt;
+            ro = make_uint4(((base + (unsigned)c.o00) * ES) | c.valid, (base + (unsigned)c.o01) * ES,
+                            (base + (unsigned)c.o10) * ES, (base + (unsigned)c.o11) * ES);
+            scatter_weights(c, my_wgt, rw);
+          }
+          uint32_t* rec = my_rec + REC_WORDS * chunk;
+          *reinterpret_cast<uint4*>(rec) = ro;
+          *reinterpret_cast<uint4*>(rec + 4) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+          if constexpr (!ACC_HALF)
+            *reinterpret_cast<uint4*>(rec + 8) = make_uint4(rw[4], rw[5], rw[6], rw[7]);
+        }
+        __syncwarp();
+        float tga = 0.f, tgx = 0.f, tgy = 0.f;
+FUSED_UNROLL(FUSED_BWD_UNROLL)
+        for (int j = 0; j < TPH; ++j) {
+          if (j < count) {
+            const uint32_t* rec = my_rec + REC_WORDS * j;
+            const uint4 ro = *reinterpret_cast<const uint4*>(rec);
+            const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
+            float ga, gx, gy;
+            core(coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
+                 ra.x, ra.y, ra.z, ra.w, ga, gx, gy);
+            ga = group_sum<TPH>(ga);
+            gx = group_sum<TPH>(gx);
+            gy = group_sum<TPH>(gy);
+            if (j == chunk) { tga = ga; tgx = gx; tgy = gy; }
+          }
+        }
+        if (keep) {
+          my_ga[s] += tga * dscale;
+          float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
+          float2 cur = *go2;
+          const float ws = my_wgt * dscale;
+          cur.x += ws * tgx;
+          cur.y += ws * tgy;
+          *go2 = cur;
+        }
+        __syncwarp();
+      };
+
       if (MODE == MODE_SCA) {
-        // Blocks of TPH samples: lane c sets up sample s0 + c and publishes its record (corner
-        // offsets, fractions, validity, attention weight) in the row's exchange buffer; every lane
-        // then walks the block; after the lane sums, lane c owns the totals of sample s0 + c and
-        // adds them to the row's accumulators (d loc / d offset = 1 / (W_l, H_l) cancels the
-        // (W_l, H_l) factor of d pixel / d loc).
         uint32_t warp_hits = __reduce_or_sync(0xffffffffu, hits);
         while (warp_hits) {
           const int cam = __ffs(warp_hits) - 1;
@@ -722,100 +767,44 @@ fused_bwd_kernel(const FusedArgs a) {
                        tail_from;
           for (int s0 = 0; s0 < LP; s0 += TPH) {
             const int s = s0 + chunk;
-            float my_wgt = 0.f;
-            {
-              uint4 ro = make_uint4(0u, 0u, 0u, 0u);
-              uint32_t rw[REC_WORDS - 4];
-#pragma unroll
-              for (int i = 0; i < REC_WORDS - 4; ++i) rw[i] = 0u;
-              if (s < LP) {
-                const uint32_t meta = s_meta[s];
-                const int l = (int)(meta & 0xffffu);
-                const float2 r = __ldg(rc + (meta >> 16));
-                const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-                const Corners c = corner_setup(r.x + o.x, r.y + o.y, lv.t.h[l], lv.t.w[l], pix_stride);
-                const int base = lv.t.start[l] * pix_stride;
-                my_wgt = mine ? my_w[s] : 0.f;
-                ro = make_uint4(((unsigned)(base + c.o00) * ES) | c.valid, (unsigned)(base + c.o01) * ES,
-                                (unsigned)(base + c.o10) * ES, (unsigned)(base + c.o11) * ES);
-                scatter_weights(c, my_wgt, rw);
-              }
-              uint32_t* rec = my_rec + REC_WORDS * chunk;
-              *reinterpret_cast<uint4*>(rec) = ro;
-              *reinterpret_cast<uint4*>(rec + 4) = make_uint4(rw[0], rw[1], rw[2], rw[3]);
-              if constexpr (!ACC_HALF)
-                *reinterpret_cast<uint4*>(rec + 8) = make_uint4(rw[4], rw[5], rw[6], rw[7]);
+            int l = 0;
+            float lx = 0.f, ly = 0.f, wgt = 0.f;
+            const bool in_row = s < LP;
+            if (in_row) {
+              const uint32_t meta = s_meta[s];
+              l = (int)(meta & 0xffffu);
+              const float2 r = __ldg(rc + (meta >> 16));
+              const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
+              lx = r.x + o.x;
+              ly = r.y + o.y;
+              wgt = mine ? my_w[s] : 0.f;
             }
-            __syncwarp();
-            float tga = 0.f, tgx = 0.f, tgy = 0.f;
-            const int count = min(TPH, LP - s0);
-FUSED_UNROLL(FUSED_BWD_UNROLL)
-            for (int j = 0; j < TPH; ++j) {
-              if (j < count) {
-                const uint32_t* rec = my_rec + REC_WORDS * j;
-                const uint4 ro = *reinterpret_cast<const uint4*>(rec);
-                const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
-                float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
-                float ga, gx, gy;
-                core(coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
-                     ra.x, ra.y, ra.z, ra.w, ga, gx, gy);
-                ga = group_sum<TPH>(ga);
-                gx = group_sum<TPH>(gx);
-                gy = group_sum<TPH>(gy);
-                if (j == chunk) { tga = ga; tgx = gx; tgy = gy; }
-              }
-            }
-            if (s < LP && mine) {
-              my_ga[s] += tga * dscale;
-              float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
-              float2 cur = *go2;
-              const float ws = my_wgt * dscale;
-              cur.x += ws * tgx;
-              cur.y += ws * tgy;
-              *go2 = cur;
-            }
-            __syncwarp();
+            run_block(coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u);
           }
         }
       } else {
-        for (int j = 0; j < a.groups; ++j) {
-          const size_t boff = ((size_t)b * a.groups + j) * batch_stride;
-          for (int l = 0; l < a.L; ++l) {
-            const int H = lv.t.h[l], W = lv.t.w[l];
-            const size_t loff = boff + (size_t)lv.t.start[l] * pix_stride;
+        // TSA / decoder rows: the same exchange; the queue entry and the level of a sample come from
+        // the shared table
+        const size_t coff = (size_t)b * a.groups * batch_stride;
+        for (int s0 = 0; s0 < S; s0 += TPH) {
+          const int s = s0 + chunk;
+          int l = 0;
+          float lx = 0.f, ly = 0.f, wgt = 0.f;
+          unsigned map_off = 0u;
+          const bool in_row = s < S;
+          if (in_row) {
+            const uint32_t meta = s_meta[s];
+            l = (int)(meta & 0xffffu);
+            const int j = (int)(meta >> 16);
             const float2 r = __ldg(reinterpret_cast<const float2*>(
                 a.ref + ((((size_t)b * a.groups + j) * a.Nq + q) * a.L + l) * 2));
-FUSED_UNROLL(FUSED_BWD_UNROLL)
-            for (int p = 0; p < a.P; ++p) {
-              const int s = (j * a.L + l) * a.P + p;
-              const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
-              const float w = live ? my_w[s] : 0.f;
-              const Corners c = corner_setup(r.x + o.x, r.y + o.y, H, W, pix_stride);
-              uint32_t rw[REC_WORDS - 4];
-              scatter_weights(c, w, rw);
-              float ga, gx, gy;
-              if constexpr (ACC_HALF)
-                core(loff, ((unsigned)c.o00 * ES) | c.valid, (unsigned)c.o01 * ES, (unsigned)c.o10 * ES,
-                     (unsigned)c.o11 * ES, c.lw, c.lh, rw[2], rw[3], 0.f, 0.f, 0.f, 0.f, ga, gx, gy);
-              else
-                core(loff, ((unsigned)c.o00 * ES) | c.valid, (unsigned)c.o01 * ES, (unsigned)c.o10 * ES,
-                     (unsigned)c.o11 * ES, c.lw, c.lh, 0u, 0u, w * c.w00, w * c.w01, w * c.w10,
-                     w * c.w11, ga, gx, gy);
-              ga = group_sum<TPH>(ga);
-              gx = group_sum<TPH>(gx);
-              gy = group_sum<TPH>(gy);
-              if (chunk == 0 && live) {
-                my_ga[s] += ga * dscale;
-                float2* go2 = reinterpret_cast<float2*>(my_go + 2 * s);
-                float2 cur = *go2;
-                const float ws = w * dscale;
-                cur.x += ws * gx;
-                cur.y += ws * gy;
-                *go2 = cur;
-              }
-            }
+            const float2 o = *reinterpret_cast<const float2*>(my_off + 2 * s);
+            lx = r.x + o.x;
+            ly = r.y + o.y;
+            wgt = live ? my_w[s] : 0.f;
+            map_off = (unsigned)j * (unsigned)batch_stride;
           }
+          run_block(coff, s, min(TPH, S - s0), in_row, in_row && live, l, lx, ly, wgt, map_off);
         }
       }
       __syncwarp();
@@ -915,6 +904,9 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   }
   a.num_tiles = (long long)f.bs * a.tiles_per_sample;
   if (a.num_tiles <= 0) return MSDA_OK;
+  // the sample records carry 32-bit byte offsets from the base of a sample's value maps
+  if ((unsigned long long)(MODE == MODE_TSA ? f.groups : 1) * f.Nk * f.M * f.Dh * sizeof(T) >= (1ull << 32))
+    return set_error(MSDA_ERR_UNSUPPORTED, "%s: value maps of %d pixels exceed the 4 GiB offset range", what, f.Nk);
   a.off_stride = f.off_stride ? f.off_stride : (long long)f.M * S * 2;
   a.log_stride = f.log_stride ? f.log_stride : (long long)f.M * S;
   if (a.off_stride % 2 != 0)

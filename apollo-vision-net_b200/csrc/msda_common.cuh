@@ -167,6 +167,17 @@ __device__ __forceinline__ uint4 ldg128(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
+// Predicated form: zeros where `on` is false (the load is not issued).  Keeps a loop of gathers
+// branch-free, so the compiler still batches the loads of several samples.
+__device__ __forceinline__ uint4 ldg128_if(const void* p, bool on) {
+  uint4 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t"
+      "mov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
+      "@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w) : "l"(p), "r"((uint32_t)on));
+  return v;
+}
+
 // Vector reduction: one 16-byte fp32x4 add at L2 (sm_90+), no return value.
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"

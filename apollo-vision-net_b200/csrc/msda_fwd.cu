@@ -94,14 +94,14 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float a = to_f32<CT>(my_att[s]);
       // clamped corners: unpredicated 128-bit loads, weight zero for corners outside the map.  An
       // invalid corner of a partly valid sample clamps onto the pixel of one of its valid corners;
-      // a sample entirely outside the map is skipped, so a non-finite value only reaches the samples
+      // a sample entirely outside the map reads nothing (predicated loads), so a non-finite value only reaches the samples
       // that touch it (the reference kernel never reads such corners)
       const Corners c = corner_setup(lx, ly, H, W, pix_stride);
-      if (c.valid == 0u) continue;
-      const uint4 u00 = ldg128(lbase + c.o00);
-      const uint4 u01 = ldg128(lbase + c.o01);
-      const uint4 u10 = ldg128(lbase + c.o10);
-      const uint4 u11 = ldg128(lbase + c.o11);
+      const bool touch = c.valid != 0u;
+      const uint4 u00 = ldg128_if(lbase + c.o00, touch);
+      const uint4 u01 = ldg128_if(lbase + c.o01, touch);
+      const uint4 u10 = ldg128_if(lbase + c.o10, touch);
+      const uint4 u11 = ldg128_if(lbase + c.o11, touch);
       const float2 w00 = splat2(a * c.w00), w01 = splat2(a * c.w01);
       const float2 w10 = splat2(a * c.w10), w11 = splat2(a * c.w11);
       float2 f[V2];
