@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 # APOLLO_B200_LIB: load another build of the same ABI (kernel experiments, tools/dev_variants.sh)
 LIB_PATH = os.environ.get('APOLLO_B200_LIB') or os.path.join(_HERE, 'libmsda_b200.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
-SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'rowops.cu', 'bev_prep.cu', 'wgrad.cu']
+SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'coarse_scatter.cu', 'rowops.cu', 'bev_prep.cu', 'wgrad.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -34,7 +34,10 @@ _SIGNATURES = {
     'msda_fwd_bwd_host': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_vp, _c_i64, _c_vp]),
     'bev_point_sampling': (_c_int, [_c_vp] * 3 + [_c_f, _c_f] + [_c_int] * 4 + [_c_vp] * 6),
     'sca_fwd': (_c_int, [_c_vp] * 10 + [_c_int] * 12 + [_c_i64, _c_i64, _c_vp]),
-    'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 12 + [_c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int, _c_vp]),
+    'sca_bwd': (_c_int, [_c_vp] * 12 + [_c_int] * 12 + [_c_i64, _c_i64, _c_int, _c_vp, _c_vp, _c_int, _c_int,
+                         _c_vp, _c_vp, _c_vp, _c_vp]),
+    'sca_coarse_workspace_bytes': (_c_i64, [_c_int] * 7),
+    'bev_hit_lists': (_c_int, [_c_vp, _c_int, _c_int, _c_vp, _c_vp, _c_vp]),
     'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_vp]),
     'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
     'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp]),
@@ -53,7 +56,7 @@ _SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 3          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
+ABI_VERSION = 4          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
 
 
 def _stale():

@@ -273,8 +273,18 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
             void* g_logits, int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
             int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride, int64_t logits_stride,
             int accum_dtype, const float* accum_scale, void* g_value_tail, int tail_copies, int tail_pixels,
-            void* stream) {
+            void* coarse_records, const int32_t* hit_index, const int32_t* hit_count, void* stream) {
   FusedProblem f;
+  if (coarse_records || hit_index || hit_count) {
+    if (!coarse_records || !hit_index || !hit_count)
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "sca_bwd: coarse_records, hit_index and hit_count go together");
+    if (!coarse_supported(Dh, P, value_dtype))
+      return set_error(MSDA_ERR_UNSUPPORTED, "sca_bwd: the tensor-core coarse pass needs a 16-bit value dtype, "
+                       "head_dim 32 and <= 8 points (sca_coarse_workspace_bytes() returns 0 otherwise)");
+    if (reinterpret_cast<uintptr_t>(coarse_records) % 16 != 0)
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "sca_bwd: coarse_records must be 16-byte aligned");
+    f.coarse_rec = coarse_records; f.hit_index = hit_index; f.hit_count = hit_count;
+  }
   f.off_stride = offsets_stride; f.log_stride = logits_stride;
   f.acc_half = accum_dtype == MSDA_F16; f.acc_scale = accum_scale;
   if (g_value_tail && tail_copies > 0) {
@@ -290,6 +300,18 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts, con
   if (int rc = validate_fused(f, true, true, "sca_bwd")) return rc;
   if ((long long)bs * HW == 0) return MSDA_OK;
   return launch_sca_bwd(f, static_cast<cudaStream_t>(stream));
+}
+
+int64_t sca_coarse_workspace_bytes(int bs, int num_cam, int HW, int M, int Dh, int P, int value_dtype) {
+  if (bs <= 0 || num_cam <= 0 || HW <= 0 || M <= 0 || !coarse_supported(Dh, P, value_dtype)) return 0;
+  return coarse_record_bytes(bs, num_cam, HW, M, P);
+}
+
+int bev_hit_lists(const uint32_t* hit_bits, int num_cam, int HW, int32_t* hit_index, int32_t* hit_count,
+                  void* stream) {
+  if (!hit_bits || !hit_index || !hit_count || num_cam <= 0 || num_cam > 32 || HW <= 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "bev_hit_lists: invalid arguments");
+  return launch_hit_lists(hit_bits, num_cam, HW, hit_index, hit_count, static_cast<cudaStream_t>(stream));
 }
 
 int tsa_fwd(const void* value, const int64_t* shapes, const int64_t* starts, const void* offsets,

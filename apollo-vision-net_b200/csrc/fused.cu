@@ -25,6 +25,7 @@
 // accumulator with 16-byte vector reductions (red.global.add.v4.f32) laid out so that one warp
 // instruction covers whole 32-byte sectors.
 #include <cstdlib>
+#include "coarse_common.cuh"
 #include "msda_common.cuh"
 #include "msda_host.h"
 
@@ -97,6 +98,9 @@ struct FusedArgs {
   int vec_ok;                  // rows can be written with 16-byte stores
   long long off_stride, log_stride;   // elements between the rows of consecutive queries
   int debug;                   // MSDA_DEBUG experiment switches (0 in production)
+  // SCA backward, 16-bit value: the samples of the coarse pyramid levels are not scattered here but
+  // written as records for the tensor-core pass (coarse_common.cuh); NULL = everything is scattered
+  uint4* coarse_rec;
 };
 
 // Sample `b` and query index of local slot `lq` in tile `t`; -1 when the slot is outside the grid.
@@ -469,6 +473,9 @@ fused_bwd_kernel(const FusedArgs a) {
   constexpr int REC_PITCH = REC_WORDS * TPH + 4;
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_ga + (size_t)ROWS * pw);
   uint32_t* s_meta = s_rec + (size_t)ROWS * REC_PITCH;   // per-sample level | anchor << 16
+  // coarse patch of the level table (first level, first pixel); first level == L: none
+  constexpr bool COARSE = MODE == MODE_SCA && sizeof(T) == 2;
+  __shared__ int s_coarse[2];
   const int tid = threadIdx.x;
   const int rows_tile = a.qpt * a.M;
 
@@ -478,7 +485,18 @@ fused_bwd_kernel(const FusedArgs a) {
     const int hi = (MODE == MODE_SCA) ? (sl - l * a.P) % a.D : i / LP;   // Z-anchor | queue entry
     s_meta[i] = (uint32_t)l | ((uint32_t)hi << 16);
   }
+  if (tid == 0) {
+    s_coarse[0] = a.L;
+    s_coarse[1] = 0;
+    if (COARSE && a.coarse_rec != nullptr) {
+      const CoarsePatch cp = coarse_patch(a.shapes, a.starts, a.L);
+      s_coarse[0] = cp.first_level;
+      s_coarse[1] = cp.start;
+    }
+  }
   __syncthreads();
+  const int coarse_first = COARSE ? s_coarse[0] : a.L;
+  const int coarse_start = COARSE ? s_coarse[1] : 0;
 
   const int chunk = tid % TPH;
   const int r_slot = tid / TPH;
@@ -699,8 +717,10 @@ fused_bwd_kernel(const FusedArgs a) {
       // part (it accumulates the totals); (l, lx, ly, wgt) level, location and attention weight (zero
       // for rows that do not take part: their gathers stay unpredicated, nothing is scattered);
       // `map_off`: element offset of its value map from `coff`, the base the block is walked with.
+      // `crow`: the row's records for the tensor-core pass of the coarse levels (indexed by the
+      // sample), or NULL
       auto run_block = [&](size_t coff, int s, int count, bool have, bool keep, int l, float lx, float ly,
-                           float wgt, unsigned map_off) {
+                           float wgt, unsigned map_off, uint4* crow) {
         float my_wgt = 0.f;
         {
           uint4 ro = make_uint4(0u, 0u, 0u, 0u);
@@ -708,12 +728,29 @@ fused_bwd_kernel(const FusedArgs a) {
 #pragma unroll
           for (int i = 0; i < REC_WORDS - 4; ++i) rw[i] = 0u;
           if (have) {
-            const Corners c = corner_setup(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride);
+            int px[4];
+            const Corners c = corner_setup_px(lx, ly, lv.t.h[l], lv.t.w[l], pix_stride, px);
             const unsigned base = map_off + (unsigned)(lv.t.start[l] * pix_stride);
             my_wgt = wgt;
             ro = make_uint4(((base + (unsigned)c.o00) * ES) | c.valid, (base + (unsigned)c.o01) * ES,
                             (base + (unsigned)c.o10) * ES, (base + (unsigned)c.o11) * ES);
             scatter_weights(c, my_wgt, rw);
+            if constexpr (COARSE) {
+              if (l >= coarse_first) {
+                // grad_value of this sample is accumulated by the tensor-core pass: no reductions
+                // here (zero scatter weights), one 16-byte record instead -- per corner the pixel
+                // inside the coarse patch and attention x bilinear / count as a 16-bit float
+                if (keep && crow != nullptr) {
+                  const int p0 = lv.t.start[l] - coarse_start;
+                  const float ws = my_wgt * dscale;
+                  using WT = typename std::conditional<ACC_HALF, __half, T>::type;
+                  crow[s] = make_uint4(coarse_corner<WT>(p0 + px[0], ws * c.w00), coarse_corner<WT>(p0 + px[1], ws * c.w01),
+                                       coarse_corner<WT>(p0 + px[2], ws * c.w10), coarse_corner<WT>(p0 + px[3], ws * c.w11));
+                }
+#pragma unroll
+                for (int i = 2; i < REC_WORDS - 4; ++i) rw[i] = 0u;
+              }
+            }
           }
           uint32_t* rec = my_rec + REC_WORDS * chunk;
           *reinterpret_cast<uint4*>(rec) = ro;
@@ -761,6 +798,10 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
           const float2* rc = reinterpret_cast<const float2*>(
               a.ref + (((size_t)cam * a.bs + b) * a.Nq + q) * a.D * 2);
           const size_t coff = ((size_t)b * a.groups + cam) * batch_stride;
+          uint4* crow = nullptr;
+          if (COARSE && coarse_first < a.L)
+            crow = a.coarse_rec + ((((size_t)b * a.groups + cam) * a.Nq + q) * a.M + m) * (kCoarseMaxLevels * a.P) -
+                   (size_t)coarse_first * a.P;
           if (replica > 0)
             acc_tail = reinterpret_cast<char*>(
                            tail16 + ((size_t)(replica - 1) * a.bs * a.groups + (size_t)b * a.groups + cam) * tail_map) -
@@ -779,7 +820,7 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
               ly = r.y + o.y;
               wgt = mine ? my_w[s] : 0.f;
             }
-            run_block(coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u);
+            run_block(coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u, crow);
           }
         }
       } else {
@@ -804,7 +845,7 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
             wgt = live ? my_w[s] : 0.f;
             map_off = (unsigned)j * (unsigned)batch_stride;
           }
-          run_block(coff, s, min(TPH, S - s0), in_row, in_row && live, l, lx, ly, wgt, map_off);
+          run_block(coff, s, min(TPH, S - s0), in_row, in_row && live, l, lx, ly, wgt, map_off, nullptr);
         }
       }
       __syncwarp();
@@ -883,6 +924,7 @@ static int launch_fused(const FusedProblem& f, bool bwd, cudaStream_t st, const 
   a.out = f.out; a.g_out = f.g_out; a.g_value = f.g_value; a.g_offsets = f.g_offsets;
   a.g_logits = f.g_logits; a.acc_scale = f.acc_scale; a.acc_half = f.acc_half;
   a.g_tail = f.g_tail; a.tail_copies = f.g_tail ? f.tail_copies : 0; a.tail_px = f.tail_px;
+  a.coarse_rec = (bwd && MODE == MODE_SCA && sca_coarse_active(f)) ? static_cast<uint4*>(f.coarse_rec) : nullptr;
   a.bs = f.bs; a.groups = f.groups; a.Nk = f.Nk; a.M = f.M; a.Dh = f.Dh; a.L = f.L; a.P = f.P;
   a.D = f.D; a.Nq = f.Nq; a.clamp = f.clamp;
   if (f.M > ROWS)
@@ -986,7 +1028,17 @@ static int dispatch_dtype(const FusedProblem& f, bool bwd, cudaStream_t st, cons
 }
 
 int launch_sca_fwd(const FusedProblem& f, cudaStream_t st) { return dispatch_dtype<MODE_SCA>(f, false, st, "sca_fwd"); }
-int launch_sca_bwd(const FusedProblem& f, cudaStream_t st) { return dispatch_dtype<MODE_SCA>(f, true, st, "sca_bwd"); }
+bool sca_coarse_active(const FusedProblem& f) {
+  return f.coarse_rec != nullptr && f.hit_index != nullptr && f.hit_count != nullptr &&
+         coarse_supported(f.Dh, f.P, f.value_dtype);
+}
+int launch_sca_bwd(const FusedProblem& f, cudaStream_t st) {
+  if (int rc = dispatch_dtype<MODE_SCA>(f, true, st, "sca_bwd")) return rc;
+  if (!sca_coarse_active(f)) return MSDA_OK;
+  // second pass: grad_value of the coarse levels from the records, on the tensor cores
+  return launch_coarse_scatter(f.coarse_rec, f.hit_index, f.hit_count, f.g_out, f.g_value, f.acc_scale, f.acc_half,
+                               f.shapes, f.starts, f.bs, f.groups, f.Nq, f.Nk, f.M, f.Dh, f.L, f.P, f.value_dtype, st);
+}
 int launch_tsa_fwd(const FusedProblem& f, cudaStream_t st) { return dispatch_dtype<MODE_TSA>(f, false, st, "tsa_fwd"); }
 int launch_tsa_bwd(const FusedProblem& f, cudaStream_t st) { return dispatch_dtype<MODE_TSA>(f, true, st, "tsa_bwd"); }
 

@@ -274,7 +274,9 @@ struct Corners {
   unsigned valid;              // bit0..3: corner 00, 01, 10, 11 contributes
 };
 
-__device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H, int W, int pix_stride) {
+// `px` receives the (clamped) pixel indices of the four corners inside the level (row-major).
+__device__ __forceinline__ Corners corner_setup_px(float loc_x, float loc_y, int H, int W, int pix_stride,
+                                                   int (&px)[4]) {
   Corners c;
   const float x = loc_x * (float)W - 0.5f;
   const float y = loc_y * (float)H - 0.5f;
@@ -290,10 +292,11 @@ __device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H,
   const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
   const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
   const int ra = ya * W, rb = yb * W;
-  c.o00 = (ra + xa) * pix_stride;
-  c.o01 = (ra + xb) * pix_stride;
-  c.o10 = (rb + xa) * pix_stride;
-  c.o11 = (rb + xb) * pix_stride;
+  px[0] = ra + xa; px[1] = ra + xb; px[2] = rb + xa; px[3] = rb + xb;
+  c.o00 = px[0] * pix_stride;
+  c.o01 = px[1] * pix_stride;
+  c.o10 = px[2] * pix_stride;
+  c.o11 = px[3] * pix_stride;
   c.w00 = (vy0 && vx0) ? c.hh * c.hw : 0.f;
   c.w01 = (vy0 && vx1) ? c.hh * c.lw : 0.f;
   c.w10 = (vy1 && vx0) ? c.lh * c.hw : 0.f;
@@ -301,6 +304,10 @@ __device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H,
   c.valid = (unsigned)(vy0 && vx0) | ((unsigned)(vy0 && vx1) << 1) | ((unsigned)(vy1 && vx0) << 2) |
             ((unsigned)(vy1 && vx1) << 3);
   return c;
+}
+__device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H, int W, int pix_stride) {
+  int px[4];
+  return corner_setup_px(loc_x, loc_y, H, W, pix_stride, px);
 }
 
 }  // namespace msda

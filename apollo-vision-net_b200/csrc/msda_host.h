@@ -50,6 +50,10 @@ struct FusedProblem {
   // elements between the offset / logit rows of consecutive queries (0 = dense); the gradient
   // buffers have the layout of their inputs
   long long off_stride = 0, log_stride = 0;
+  // SCA backward: tensor-core pass for the coarse pyramid levels (coarse_scatter.cu); all three or none
+  void* coarse_rec = nullptr;          // records, sca_coarse_workspace_bytes() bytes
+  const int32_t* hit_index = nullptr;  // (groups, Nq) per-camera hit lists of batch element 0
+  const int32_t* hit_count = nullptr;  // (groups,)
 };
 
 int set_error(int code, const char* fmt, ...);
@@ -64,6 +68,15 @@ int launch_point_sampling(const float* ref_3d, const float* lidar2img, const dou
                           int32_t* hit_count, cudaStream_t st);
 int launch_sca_fwd(const FusedProblem& fp, cudaStream_t st);
 int launch_sca_bwd(const FusedProblem& fp, cudaStream_t st);
+bool sca_coarse_active(const FusedProblem& fp);
+bool coarse_supported(int Dh, int P, int value_dtype);
+long long coarse_record_bytes(int bs, int cams, int Nq, int M, int P);
+int launch_coarse_scatter(const void* rec, const int32_t* hit_index, const int32_t* hit_count, const void* g_out,
+                          void* g_value, const float* acc_scale, int acc_half, const int64_t* shapes,
+                          const int64_t* starts, int bs, int cams, int Nq, int Nk, int M, int Dh, int L, int P,
+                          int value_dtype, cudaStream_t st);
+int launch_hit_lists(const uint32_t* hit_bits, int num_cam, int HW, int32_t* hit_index, int32_t* hit_count,
+                     cudaStream_t st);
 int launch_tsa_fwd(const FusedProblem& fp, cudaStream_t st);
 int launch_tsa_bwd(const FusedProblem& fp, cudaStream_t st);
 int rowops_partial_rows();

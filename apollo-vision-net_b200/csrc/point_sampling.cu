@@ -107,10 +107,15 @@ int launch_point_sampling(const float* ref_3d, const float* lidar2img, const dou
       num_cam, HW, D, ref_cam, bev_mask, hit_bits);
   count_launch();
   if (int rc = check_launch("bev_point_sampling")) return rc;
-  if (!hit_index || !hit_count) return MSDA_OK;      // the fused kernels only need the bit field
+  if (!hit_index || !hit_count) return MSDA_OK;      // the fused forward only needs the bit field
+  return launch_hit_lists(hit_bits, num_cam, HW, hit_index, hit_count, st);
+}
+
+int launch_hit_lists(const uint32_t* hit_bits, int num_cam, int HW, int32_t* hit_index, int32_t* hit_count,
+                     cudaStream_t st) {
   hit_compaction_kernel<<<num_cam, 1024, 0, st>>>(hit_bits, HW, hit_index, hit_count);
   count_launch();
-  return check_launch("bev_point_sampling(compaction)");
+  return check_launch("bev_hit_lists");
 }
 
 }  // namespace msda

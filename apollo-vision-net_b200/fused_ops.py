@@ -36,14 +36,20 @@ class BevGeometry:
         """(num_cam, bs, HW, D) bool, the reference's ``bev_mask``."""
         return self.mask_u8.view(torch.bool)
 
+    def lists(self):
+        """(hit_index, hit_count) of THIS geometry's queries, derived once from the bit field when
+        :func:`bev_point_sampling` was called without lists (or the geometry is a row slice)."""
+        if self.hit_index is None:
+            self.hit_index, self.hit_count = hit_lists(self.hit_bits, self.reference_points_cam.shape[0])
+        return self.hit_index, self.hit_count
+
     def rows(self, q0, q1):
         """Geometry of the query slice [q0, q1) (BEV row sharding).  The camera gating of the
         reference reads batch element 0 (quirk 1), so the slice keeps that convention; the
-        compacted hit lists are global and are not sliced."""
+        compacted hit lists of the slice are rebuilt on demand (:meth:`lists`)."""
         return BevGeometry(self.reference_points_cam[:, :, q0:q1].contiguous(),
                            self.mask_u8[:, :, q0:q1].contiguous(),
-                           self.hit_bits[:, q0:q1].contiguous(), self.hit_index, self.hit_count,
-                           self.D)
+                           self.hit_bits[:, q0:q1].contiguous(), None, None, self.D)
 
 
 def bev_point_sampling(ref_3d, pc_range, lidar2img, img_h, img_w, with_lists=True):
@@ -146,7 +152,52 @@ def grad_accumulator_overflowed(device=None, reset=True):
     return hit
 
 
-def _accumulator(value, g_out, num_levels=1, rows_per_slot=0):
+_coarse_mode = [__import__('os').environ.get('APOLLO_B200_COARSE', '1') != '0']
+_coarse_ws = {}
+
+
+def set_coarse_tensor_core_pass(on):
+    """Spatial cross-attention backward, 16-bit value dtypes with head_dim 32: accumulate grad_value of
+    the coarse pyramid levels on the tensor cores (records + tcgen05 contraction, see ``sca_bwd`` in
+    include/msda_b200.h) instead of one L2 reduction per corner.  Default on; returns the previous
+    setting.  (``APOLLO_B200_COARSE=0`` turns it off at import.)"""
+    prev, _coarse_mode[0] = _coarse_mode[0], bool(on)
+    return prev
+
+
+def hit_lists(hit_bits, num_cam):
+    """(bs, HW) int32 camera bit field -> (hit_index (num_cam, HW) int32, hit_count (num_cam,) int32):
+    the per-camera ordered query lists of batch element 0 (what :func:`bev_point_sampling` returns with
+    ``with_lists=True``), for callers that only hold the bit field."""
+    _require_cuda(hit_bits=hit_bits)
+    hit_bits = hit_bits.contiguous()
+    HW = hit_bits.shape[-1]
+    idx = torch.empty((num_cam, HW), dtype=torch.int32, device=hit_bits.device)
+    cnt = torch.empty((num_cam,), dtype=torch.int32, device=hit_bits.device)
+    with torch.cuda.device(hit_bits.device):
+        _lib.call('bev_hit_lists', hit_bits.data_ptr(), num_cam, HW, idx.data_ptr(), cnt.data_ptr(),
+                  _stream_ptr(hit_bits))
+    return idx, cnt
+
+
+def _coarse_records(value, bs, num_cam, HW, M, Dh, P):
+    """Record workspace of the tensor-core coarse pass (one buffer per device and stream, grown on
+    demand, contents undefined between calls), or None when the pass does not apply."""
+    if not _coarse_mode[0] or value.dtype == torch.float32:
+        return None
+    need = int(_lib.lib().sca_coarse_workspace_bytes(bs, num_cam, HW, M, Dh, P, _DTYPE_CODE[value.dtype]))
+    if need <= 0:
+        return None
+    dev = value.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _coarse_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _coarse_ws[key] = ws
+    return ws
+
+
+def _accumulator(value, g_out, num_levels=1, rows_per_slot=0, replicas=True):
     """grad_value accumulator for the fused backward kernels.
 
     fp32 value: fp32 accumulator (red.global.add.v4.f32).  16-bit value: fp16 accumulator scaled by
@@ -173,7 +224,7 @@ def _accumulator(value, g_out, num_levels=1, rows_per_slot=0):
                   float(limit), ws.data_ptr(), _stream_ptr(value))
     maps, Nk, M, Dh = value.shape
     tail, tail_px = None, 0
-    if num_levels > 1 and Nk >= 4 * _TAIL_FRACTION and (M * Dh) % 8 == 0 and \
+    if replicas and num_levels > 1 and Nk >= 4 * _TAIL_FRACTION and (M * Dh) % 8 == 0 and \
             os.environ.get('APOLLO_B200_TAIL_REPLICAS', '1') != '0':
         tail_px = Nk // _TAIL_FRACTION
         tail = torch.zeros((_TAIL_COPIES, maps, tail_px, M, Dh), dtype=torch.float16, device=dev)
@@ -271,7 +322,7 @@ class SpatialCrossAttnFunction(Function):
     @staticmethod
     @custom_fwd(cast_inputs=None)
     def forward(ctx, value, spatial_shapes, level_start_index, offsets, logits, ref_cam,
-                mask_u8, hit_bits, num_cam, bev_w=0):
+                mask_u8, hit_bits, num_cam, bev_w=0, hit_lists_=None):
         _require_cuda(value=value, offsets=offsets, logits=logits, ref_cam=ref_cam,
                       mask=mask_u8, hit_bits=hit_bits)
         value = _check_value(value)
@@ -298,6 +349,9 @@ class SpatialCrossAttnFunction(Function):
         ctx.merged, ctx.dims = co.merged, (bs, HW, M, Dh, L, P, D, Nk)
         ctx.coord = (co.code, co.off_stride, co.log_stride)
         ctx.num_cam = num_cam
+        # per-camera hit lists for the backward's tensor-core pass (non-differentiable int32 tensors
+        # from bev_point_sampling; derived from the bit field when the caller did not bring them)
+        ctx.hit_lists = hit_lists_
         ctx.bev_w = int(bev_w or 0)
         return slots
 
@@ -312,7 +366,16 @@ class SpatialCrossAttnFunction(Function):
         off_ptr = coords[0].data_ptr()
         log_ptr = off_ptr + 2 * (so // 3) * coords[0].element_size() if ctx.merged else coords[1].data_ptr()
         g_slots = g_slots.to(value.dtype).contiguous()
-        g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L, rows_per_slot=HW)
+        records = _coarse_records(value, bs, num_cam, HW, M, Dh, P)
+        lists = None
+        if records is not None:
+            lists = ctx.hit_lists
+            if lists is None or lists[0] is None:
+                lists = hit_lists(hit_bits, num_cam)
+            assert lists[0].shape == (num_cam, HW) and lists[0].dtype == torch.int32 and lists[0].is_contiguous()
+        # (with the tensor-core pass the coarse levels no longer need replicas of the accumulator tail)
+        g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L, rows_per_slot=HW,
+                                                                   replicas=records is None)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,
@@ -322,9 +385,11 @@ class SpatialCrossAttnFunction(Function):
                 code, so, sl, acc_code,
                 None if acc_scale is None else acc_scale.data_ptr(),
                 None if tail is None else tail.data_ptr(), 0 if tail is None else tail.shape[0],
-                tail_px, _stream_ptr(value))
+                tail_px, None if records is None else records.data_ptr(),
+                None if records is None else lists[0].data_ptr(),
+                None if records is None else lists[1].data_ptr(), _stream_ptr(value))
         g_value = _finish_accumulator(g_value, acc_code, acc_scale, value, tail, tail_px)
-        return (g_value, None, None, g_off, g_log, None, None, None, None, None)
+        return (g_value, None, None, g_off, g_log, None, None, None, None, None, None)
 
 
 class QueueDeformAttnFunction(Function):

@@ -135,9 +135,12 @@ class SpatialCrossAttention(BaseModule):
         da = self.deformable_attention
         if not isinstance(da, MSDeformableAttention3D):
             raise TypeError('the fused spatial cross-attention needs an MSDeformableAttention3D')
+        lists = None
         if bev_geometry is not None:
             hit_bits, mask_u8 = bev_geometry.hit_bits, bev_geometry.mask_u8
             reference_points_cam = bev_geometry.reference_points_cam
+            if torch.is_grad_enabled():
+                lists = bev_geometry.lists()       # the backward's tensor-core pass walks them
         else:
             mask_b = bev_mask.to(torch.bool)
             hit_bits = hit_bits_from_mask(mask_b)
@@ -148,7 +151,7 @@ class SpatialCrossAttention(BaseModule):
         coords = da.project_coords(query)          # offsets | logits of a query, one GEMM
         slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, coords, None,
                                                reference_points_cam, mask_u8, hit_bits,
-                                               self.num_cams, self._grid_w(bev_h, bev_w, num_query))
+                                               self.num_cams, self._grid_w(bev_h, bev_w, num_query), lists)
         # (the residual is added without a permute whatever batch_first says, reference :171-173)
         if post_norm is not None and not (self.training and self.dropout.p > 0):
             return linear_add_layernorm(slots.to(query.dtype), self.output_proj, inp_residual, post_norm)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 3
+#define MSDA_ABI_VERSION 4
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -177,13 +177,35 @@ int sca_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
             int bs, int num_cam, int Nk, int M, int Dh, int L, int P, int D, int HW,
             int bev_w, int value_dtype, int coord_dtype, int64_t offsets_stride,
             int64_t logits_stride, int accum_dtype, const float* accum_scale,
-            void* g_value_tail, int tail_copies, int tail_pixels, void* stream);
-/*   g_value_tail (optional, fp16 accumulator only): (tail_copies, bs*num_cam, tail_pixels, M, Dh) fp16,
+            void* g_value_tail, int tail_copies, int tail_pixels,
+            void* coarse_records, const int32_t* hit_index, const int32_t* hit_count, void* stream);
+/*   coarse_records, hit_index, hit_count (optional, all three or none; 16-bit value dtypes, Dh = 32,
+ *             P <= 8): grad_value of the COARSE pyramid levels -- the longest suffix of at most two levels
+ *             holding <= 2048 pixels together: 6 % of the pixels and 46 % of the updates at the base
+ *             config -- is not scattered with reductions (the reference-era design: one global atomicAdd
+ *             per corner and channel, ops_dcnv3/src/cuda/dcnv3_im2col_cuda.cuh:106-146 and mmcv's
+ *             ms_deform_attn_col2im_bilinear) but accumulated on the tensor cores: the kernel writes one
+ *             16-byte record per coarse sample into coarse_records (sca_coarse_workspace_bytes() bytes,
+ *             contents undefined on entry and exit) and a second kernel computes, per (camera, head),
+ *             patch[pixel][channel] += W^T[pixel][row] . g_slots[row][channel] with tcgen05.mma, the
+ *             fp32 patch living in tensor memory, walking hit_index / hit_count (bev_hit_lists() or
+ *             bev_point_sampling()).  The patch sums are added to g_value once per CTA.
+ *   g_value_tail (optional, fp16 accumulator only): (tail_copies, bs*num_cam, tail_pixels, M, Dh) fp16,
  *             zero-filled: replicas of the LAST tail_pixels pixels of every value map -- the coarse
  *             pyramid levels, whose slots receive hundreds of updates each.  A CTA adds into replica
  *             blockIdx % (tail_copies + 1) (0 = g_value itself), which divides the number of fp16
  *             roundings a slot's running sum sees; unscale_cast() adds the replicas back.  NULL / 0:
  *             everything goes to g_value.                                                          */
+
+/* Bytes of sca_bwd's coarse_records for these sizes; 0 when the tensor-core pass does not support them
+ * (then pass NULL and everything is scattered with reductions). */
+int64_t sca_coarse_workspace_bytes(int bs, int num_cam, int HW, int M, int Dh, int P, int value_dtype);
+
+/* Per-camera ordered hit lists from the camera bit field (what bev_point_sampling writes when given
+ * hit_index / hit_count): hit_bits (bs, HW) uint32 -- batch element 0 decides, the reference's quirk --
+ * -> hit_index (num_cam, HW) int32 ascending, -1 padded; hit_count (num_cam,) int32. */
+int bev_hit_lists(const uint32_t* hit_bits, int num_cam, int HW, int32_t* hit_index, int32_t* hit_count,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Fused temporal self-attention / decoder cross-attention core

@@ -39,6 +39,7 @@ def main():
     ap.add_argument('--which', default='sca,tsa')
     ap.add_argument('--accum', default='auto', help="'auto' (fp16 for 16-bit values) or 'fp32'")
     ap.add_argument('--no-tail', action='store_true', help='no replicas of the accumulator tail')
+    ap.add_argument('--no-coarse', action='store_true', help='coarse levels through L2 reductions (no tensor-core pass)')
     ap.add_argument('--coord', default='same', help="'same' = offsets/logits in the value dtype, 'fp32'")
     args = ap.parse_args()
     dev = torch.device('cuda:0')
@@ -74,7 +75,11 @@ def main():
         gv = torch.zeros(6, Nk, M, Dh, device=dev, dtype=torch.float16 if half_acc else torch.float32)
         sws = torch.zeros(64, device=dev)
         acode = 1 if half_acc else 0
-        tail = torch.zeros(7, 6, Nk // 16, M, Dh, device=dev, dtype=torch.float16) if (half_acc and not args.no_tail) else None
+        code = _DTYPE_CODE[dtype]
+        rec_bytes = 0 if args.no_coarse else int(_lib.lib().sca_coarse_workspace_bytes(1, 6, HW, M, Dh, P, code))
+        records = torch.empty(rec_bytes, dtype=torch.uint8, device=dev) if rec_bytes > 0 else None
+        tail = torch.zeros(7, 6, Nk // 16, M, Dh, device=dev, dtype=torch.float16) \
+            if (half_acc and not args.no_tail and records is None) else None
         goff = torch.empty_like(offsets)
         glog = torch.empty_like(logits)
         code = _DTYPE_CODE[dtype]
@@ -91,7 +96,10 @@ def main():
                       logits.data_ptr(), geo.reference_points_cam.data_ptr(), geo.mask_u8.data_ptr(),
                       geo.hit_bits.data_ptr(), gs.data_ptr(), gv.data_ptr(), goff.data_ptr(), glog.data_ptr(),
                       1, 6, Nk, M, Dh, L, P, D, HW, W, code, ccode, 0, 0, acode, sws[16:].data_ptr() if half_acc else None,
-                      tail.data_ptr() if tail is not None else None, 7 if tail is not None else 0, Nk // 16, st)
+                      tail.data_ptr() if tail is not None else None, 7 if tail is not None else 0, Nk // 16,
+                      records.data_ptr() if records is not None else None,
+                      geo.hit_index.data_ptr() if records is not None else None,
+                      geo.hit_count.data_ptr() if records is not None else None, st)
         res['sca_fwd_us'] = round(timeit(fwd, flush, args.iters), 1)
         res['sca_bwd_us'] = round(timeit(bwd, flush, args.iters), 1)
         res['sca_samples'] = pairs * M * L * P
@@ -128,7 +136,7 @@ def main():
                       sws[16:].data_ptr() if half_acc else None, st)
         res['tsa_fwd_us'] = round(timeit(tfwd, flush, args.iters), 1)
         res['tsa_bwd_us'] = round(timeit(tbwd, flush, args.iters), 1)
-    res.update(bev=args.bev, dtype=args.dtype, pairs=pairs)
+    res.update(bev=args.bev, dtype=args.dtype, pairs=pairs, coarse=not args.no_coarse)
     print(json.dumps(res), flush=True)
 
 
