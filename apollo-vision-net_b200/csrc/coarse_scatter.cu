@@ -16,8 +16,11 @@
 //
 // No atomics inside the accumulation, no same-address contention, fp32 sums (the fp16 accumulator of
 // the main pass only sees the few partial sums of the CTAs that share a (camera, head)).
-// Three stages (61-64 KB of W each), one builder warp per stage, one issuing warp; all waits are
+// Three stages (61-64 KB of W each), FOUR builder warps per stage (a lane owns one bilinear corner of one
+// level of one row and walks the level's samples: the corners of a sample are distinct pixels, samples
+// of one row may share pixels and follow each other in warp lockstep), one issuing warp; all waits are
 // bounded and trap instead of hanging.
+#include <cstdlib>
 #include <type_traits>
 
 #include "coarse_common.cuh"
@@ -26,7 +29,9 @@
 
 namespace msda {
 
-constexpr int CS_THREADS = 128;
+constexpr int CS_BUILDERS = 4;                                          // builder warps per stage (4 rows each)
+constexpr int CS_ISSUERS = 4;                                           // issuing warps (M-tiles t = w mod 4)
+constexpr int CS_THREADS = 32 * (CS_ISSUERS + 3 * CS_BUILDERS);
 constexpr int CS_STAGES = 3;
 constexpr int CS_KROWS = 16;
 constexpr int CS_TILE_BYTES = 128 / 8 * 128;                          // one M-tile of one k-group: 16 core matrices
@@ -47,6 +52,8 @@ struct CoarseArgs {
   const int64_t* starts;
   int bs, cams, Nq, Nk, M, L, P;
   uint32_t idesc;
+  int debug;                     // MSDA_COARSE_DEBUG experiment switches (0 in production): 1 = no build / erase,
+                                 // 2 = no MMAs, 4 = no record / gradient fetch
 };
 
 __device__ __forceinline__ uint64_t cs_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -138,10 +145,10 @@ coarse_scatter_kernel(const CoarseArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < CS_STAGES; ++s) {
-      mbar_init(&full_bar[s], 32);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], CS_BUILDERS);
+      mbar_init(&empty_bar[s], CS_ISSUERS);
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, CS_ISSUERS);
     fence_barrier_init();
   }
   for (int i = tid; i < CS_STAGES * CS_STAGE_BYTES / 16; i += CS_THREADS)
@@ -157,109 +164,125 @@ coarse_scatter_kernel(const CoarseArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp == 0) {
-    // ---------------- issuing warp: NT MMAs (M128 N32 K16) per K-step ----------------
+  if (warp < CS_ISSUERS) {
+    // ---------------- issuing warps: NT MMAs (M128 N32 K16) per K-step, M-tile t issued by warp t mod 4 ----
+    // One thread issues an MMA in ~50-90 cycles whatever its shape (descriptor arithmetic, five
+    // register-to-uniform moves, the election; tools/micro/umma_shape_bench.cu), several times the
+    // tensor-pipe time of these skinny tiles -- so four warps share the tiles.  A tile always belongs to
+    // the same warp (its accumulation stays in issue order); each warp walks the loop converged and one
+    // ELECTED lane issues (elect.sync names the same lane every time, so a warp's commits track its MMAs).
+    const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+    const uint32_t idesc_u = a.idesc;
+    const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);        // SBO = 128 bytes | descriptor version 1
+    const uint32_t lbo_field = ((lbo_a >> 4) & 0x3fffu) << 16;
+    const uint32_t b_lbo_field = (uint32_t)(((kCoarseDh / 8) * 128) >> 4) << 16;
     for (int k = 0; k < nsteps; ++k) {
       const int st = k % CS_STAGES;
       cs_wait(&full_bar[st], (uint32_t)((k / CS_STAGES) & 1));
-      if (lane == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_u32(smem + (size_t)st * CS_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + CS_A_BYTES;
-        const uint64_t bdesc = cs_desc(b_addr, (kCoarseDh / 8) * 128, 128);
-        const uint32_t accumulate = k > 0 ? 1u : 0u;
-        for (int t = 0; t < NT; ++t) {
-          const uint64_t adesc = cs_desc(a_addr + (uint32_t)t * CS_TILE_BYTES, lbo_a, 128);
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                       :: "r"(tmem_d + (uint32_t)t * kCoarseDh), "l"(adesc), "l"(bdesc), "r"(a.idesc), "r"(accumulate)
-                       : "memory");
-        }
-        // arrives when these MMAs (and all earlier ones) have completed: the stage may be rewritten
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     :: "r"(smem_u32(&empty_bar[st])) : "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_addr = smem_base + (uint32_t)st * CS_STAGE_BYTES;
+      const uint32_t b_lo = (((a_addr + CS_A_BYTES) & 0x3ffffu) >> 4) | b_lbo_field;
+      const uint32_t a_lo0 = ((a_addr & 0x3ffffu) >> 4) | lbo_field;
+      const uint32_t accumulate = k > 0 ? 1u : 0u;
+      const int nt = (a.debug & 2) ? 0 : NT;
+#pragma unroll 4
+      for (int t = warp; t < nt; t += CS_ISSUERS) {
+        // descriptor of M-tile t: the start address field advances by CS_TILE_BYTES / 16
+        asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+                     "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                     "elect.sync _|e, 0xffffffff;\n\t"
+                     "setp.ne.b32 p, %4, 0;\n\t"
+                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                     :: "r"(tmem_u + (uint32_t)t * kCoarseDh), "r"(a_lo0 + (uint32_t)t * (CS_TILE_BYTES >> 4)), "r"(b_lo),
+                        "r"(idesc_u), "r"(accumulate), "r"(desc_hi)
+                     : "memory");
       }
-      __syncwarp();
+      // arrives when these MMAs (and all earlier ones) have completed: the stage may be rewritten
+      asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                   "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                   :: "r"(smem_u32(&empty_bar[st])) : "memory");
     }
-    if (lane == 0)
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                   :: "r"(smem_u32(&done_bar)) : "memory");
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 :: "r"(smem_u32(&done_bar)) : "memory");
   } else {
-    // ---------------- builder warp: owns stage (warp - 1) ----------------
-    const int st = warp - 1;
+    // ---------------- builder warps: CS_BUILDERS per stage, 4 rows of the K-step each ----------------
+    const int st = (warp - CS_ISSUERS) / CS_BUILDERS, sub = (warp - CS_ISSUERS) % CS_BUILDERS;
     unsigned char* A = smem + (size_t)st * CS_STAGE_BYTES;
     unsigned char* B = A + CS_A_BYTES;
-    const int r = lane & 15, slot = lane >> 4;                       // row of the K-step, coarse level slot
+    // lane = (row of the warp's four, coarse level slot, bilinear corner)
+    const int r = sub * 4 + (lane >> 3), slot = (lane >> 2) & 1, cn = lane & 3;
     const bool lane_on = slot < nlev;
     const uint32_t row_off = (uint32_t)(r >> 3) * lbo_a + (uint32_t)(r & 7) * 16;
     const int recs_per_row = kCoarseMaxLevels * a.P;
     const T* gout = static_cast<const T*>(a.g_out);
     const float g_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
-    // one K-step of this lane: its (row, level)'s records and its two 16-byte chunks of the row's
-    // upstream gradient (all zero for rows past the slice)
+    // one K-step of this lane: word `cn` of the records of its (row, level) -- byte offset of the pixel
+    // inside the row's k-group : 16 | weight : 16 -- and, for the corner-0/1 lanes, one 16-byte chunk of
+    // the row's upstream gradient (all zero for rows past the slice)
     struct Step {
-      uint4 rec[kCoarseMaxP];
-      uint4 ga, gb;
+      uint32_t w[kCoarseMaxP];
+      uint4 g;
     };
     auto fetch = [&](int k, Step& d) {
       const int i = i0 + k * CS_KROWS + r;
-      const bool ok = k < nsteps && i < i1;
+      const bool ok = k < nsteps && i < i1 && !(a.debug & 4);
       const int q = ok ? __ldg(a.hit_index + (size_t)cam * a.Nq + i) : 0;
-      const uint4* src = a.rec + ((((size_t)b * a.cams + cam) * a.Nq + q) * a.M + m) * recs_per_row + (size_t)slot * a.P;
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(
+          a.rec + ((((size_t)b * a.cams + cam) * a.Nq + q) * a.M + m) * recs_per_row + (size_t)slot * a.P) + cn;
 #pragma unroll
-      for (int j = 0; j < kCoarseMaxP; ++j)
-        d.rec[j] = (ok && lane_on && j < a.P) ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
-      const uint4* gs = reinterpret_cast<const uint4*>(gout + (((size_t)b * a.Nq + q) * a.M + m) * kCoarseDh) + slot * 2;
-      d.ga = ok ? __ldg(gs) : make_uint4(0u, 0u, 0u, 0u);
-      d.gb = ok ? __ldg(gs + 1) : make_uint4(0u, 0u, 0u, 0u);
+      for (int j = 0; j < kCoarseMaxP; ++j) d.w[j] = (ok && lane_on && j < a.P) ? __ldg(src + 4 * j) : 0u;
+      const uint4* gs = reinterpret_cast<const uint4*>(gout + (((size_t)b * a.Nq + q) * a.M + m) * kCoarseDh) + slot * 2 + cn;
+      d.g = (ok && cn < 2) ? __ldg(gs) : make_uint4(0u, 0u, 0u, 0u);
     };
-    // non-zeros of one (row, level): the four corners of a sample are distinct pixels, different samples
-    // of the row may share one -- so samples go one after the other (read-modify-write), corners together.
-    // A record word = byte offset of the pixel inside the row's k-group : 16 | fp16 weight : 16.
     const uint32_t a_row = smem_u32(A) + row_off;
-    const uint32_t b_row = smem_u32(B) + (uint32_t)(r >> 3) * ((kCoarseDh / 8) * 128) + (uint32_t)(slot * 2) * 128 +
-                           (uint32_t)(r & 7) * 16;
-    auto scatter = [&](const Step& d, bool erase) {
+    const uint32_t b_at = smem_u32(B) + (uint32_t)(r >> 3) * ((kCoarseDh / 8) * 128) + (uint32_t)(slot * 2 + cn) * 128 +
+                          (uint32_t)(r & 7) * 16;
+    // samples one after the other: the warp's lanes update sample j together (distinct addresses, or
+    // nothing where the weight is zero), and the __syncwarp orders sample j's stores before sample
+    // j + 1's loads of a pixel that another corner lane of the same row wrote
+    auto build = [&](const Step& d) {
 #pragma unroll
       for (int j = 0; j < kCoarseMaxP; ++j) {
-        const uint32_t w[4] = {d.rec[j].x, d.rec[j].y, d.rec[j].z, d.rec[j].w};
-        uint16_t old[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          old[c] = (!erase && (w[c] & 0x7fff0000u)) ? cs_lds16(a_row + (w[c] & 0xffffu)) : (uint16_t)0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (w[c] & 0x7fff0000u)
-            cs_sts16(a_row + (w[c] & 0xffffu), erase ? (uint16_t)0 : cs_add_bits<WT>(old[c], (uint16_t)(w[c] >> 16)));
+        const uint32_t w = d.w[j];
+        if (w & 0x7fff0000u) {
+          const uint32_t at = a_row + (w & 0xffffu);
+          cs_sts16(at, cs_add_bits<WT>(cs_lds16(at), (uint16_t)(w >> 16)));
+        }
+        __syncwarp();
       }
+    };
+    auto erase = [&](const Step& d) {
+#pragma unroll
+      for (int j = 0; j < kCoarseMaxP; ++j)
+        if (d.w[j] & 0x7fff0000u) cs_sts16(a_row + (d.w[j] & 0xffffu), (uint16_t)0);
     };
 
     Step cur, nxt;
     fetch(st, cur);
     for (int k = st, n = 0; k < nsteps; k += CS_STAGES, ++n) {
       fetch(k + CS_STAGES, nxt);                                     // in flight while this step is built
-      scatter(cur, false);                                           // (the stage is all-zero here)
-      if constexpr (ACC_HALF) {
-        cs_sts128(b_row, cs_to_f16_scaled<T>(cur.ga, g_scale));
-        cs_sts128(b_row + 128, cs_to_f16_scaled<T>(cur.gb, g_scale));
-      } else {
-        cs_sts128(b_row, cur.ga);
-        cs_sts128(b_row + 128, cur.gb);
+      if (!(a.debug & 1)) build(cur);                                // (the stage is all-zero here)
+      if (cn < 2) {
+        if constexpr (ACC_HALF) cs_sts128(b_at, cs_to_f16_scaled<T>(cur.g, g_scale));
+        else cs_sts128(b_at, cur.g);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-      cs_arrive(&full_bar[st]);
+      __syncwarp();
+      if (lane == 0) cs_arrive(&full_bar[st]);
       if (k + CS_STAGES < nsteps) {
         cs_wait(&empty_bar[st], (uint32_t)(n & 1));                  // this step's MMAs have read the stage
-        scatter(cur, true);                                          // back to all-zero
+        if (!(a.debug & 1)) erase(cur);                              // back to all-zero
       }
       cur = nxt;
     }
   }
 
   // ---------------- epilogue: TMEM -> registers -> one reduction per (pixel, head) ----------------
-  cs_wait(&done_bar, 0u);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  {
+  if (warp < 4) {                                                    // (the issuers) warp i reads TMEM lanes [32 i, 32 i + 32)
+    cs_wait(&done_bar, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const size_t map = (size_t)b * a.cams + cam;
     for (int t = 0; t < NT; ++t) {
       uint32_t v[32];
@@ -354,6 +377,8 @@ int launch_coarse_scatter(const void* rec, const int32_t* hit_index, const int32
   a.rec = static_cast<const uint4*>(rec); a.hit_index = hit_index; a.hit_count = hit_count; a.g_out = g_out;
   a.g_value = g_value; a.acc_scale = acc_scale; a.shapes = shapes; a.starts = starts;
   a.bs = bs; a.cams = cams; a.Nq = Nq; a.Nk = Nk; a.M = M; a.L = L; a.P = P;
+  static const int dbg = [] { const char* v = getenv("MSDA_COARSE_DEBUG"); return v ? atoi(v) : 0; }();
+  a.debug = dbg;
   if (value_dtype == MSDA_BF16) return coarse_launch_t<__nv_bfloat16>(a, acc_half != 0, st);
   return coarse_launch_t<__half>(a, acc_half != 0, st);
 }

@@ -25,6 +25,7 @@
 // accumulator with 16-byte vector reductions (red.global.add.v4.f32) laid out so that one warp
 // instruction covers whole 32-byte sectors.
 #include <cstdlib>
+#include <type_traits>
 #include "coarse_common.cuh"
 #include "msda_common.cuh"
 #include "msda_host.h"
@@ -551,8 +552,11 @@ fused_bwd_kernel(const FusedArgs a) {
       // channels in their natural order, scaled by a power of two chosen from max|g_out|
       __half* ghead16 = static_cast<__half*>(a.g_value) + head_off + chunk * VEC;
       const float acc_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
-      // replica of the accumulator's coarse tail this CTA adds into (see FusedArgs::g_tail)
-      const int replica = (ACC_HALF && a.tail_copies > 0) ? (int)(blockIdx.x % (unsigned)(a.tail_copies + 1)) : 0;
+      // replica of the accumulator's coarse tail this CTA adds into (see FusedArgs::g_tail).  Not
+      // for TPH == 4 (head_dim 32 with a 16-bit value): those shapes have the tensor-core pass for
+      // the coarse levels, and the address selects cost 24 instructions per sample in the hot loop.
+      constexpr bool TAIL = ACC_HALF && MODE == MODE_SCA && TPH != 4;
+      const int replica = (TAIL && a.tail_copies > 0) ? (int)(blockIdx.x % (unsigned)(a.tail_copies + 1)) : 0;
       const unsigned tail_from = replica > 0 ? (unsigned)(a.Nk - a.tail_px) * (unsigned)pix_stride * ES_ACC
                                              : 0xffffffffu;      // byte offset inside a value map
       const size_t tail_map = (size_t)a.tail_px * pix_stride;    // elements per map in a replica
@@ -604,16 +608,19 @@ fused_bwd_kernel(const FusedArgs a) {
       // byte offset of corner 00 | validity bits; aw* = attention x bilinear weight per corner
       // (zero for invalid corners and for rows without work), as packed fp16 pairs (awa = 00|01,
       // awb = 10|11) for the fp16 accumulator or as floats.
-      auto core = [&](size_t boff, unsigned o00v, unsigned o01, unsigned o10, unsigned o11, float lw,
+      auto core = [&](auto scatter_tag, size_t boff, unsigned o00v, unsigned o01, unsigned o10, unsigned o11, float lw,
                       float lh, uint32_t awa, uint32_t awb, float aw00, float aw01, float aw10,
                       float aw11, float& ga, float& gx, float& gy) {
+        constexpr bool SCATTER = decltype(scatter_tag)::value;
         const unsigned o00 = o00v & ~15u;
         const char* vb = reinterpret_cast<const char*>(vhead + boff);
         const uint4 u00 = ldg128(vb + o00);
         const uint4 u01 = ldg128(vb + o01);
         const uint4 u10 = ldg128(vb + o10);
         const uint4 u11 = ldg128(vb + o11);
-        if constexpr (ACC_HALF) {
+        if constexpr (!SCATTER) {
+          // (a block of coarse-level samples: their grad_value goes through the records)
+        } else if constexpr (ACC_HALF) {
           // gh = fp16(g * scale) per row; one HMUL2 per channel pair, one predicated 16-byte
           // reduction per corner (skipped where the weight is zero); corners in the coarse tail
           // of the map go to this CTA's replica
@@ -626,7 +633,7 @@ fused_bwd_kernel(const FusedArgs a) {
               const __half2 hk = __hmul2(aw2, gh[k]);
               h[k] = *reinterpret_cast<const uint32_t*>(&hk);
             }
-            char* dst = (off >= tail_from ? gt : gb) + off;
+            char* dst = (TAIL ? (off >= tail_from ? gt : gb) : gb) + off;
             red_add_f16x8_if(reinterpret_cast<__half*>(dst), h[0], h[1], h[2], h[3], on);
           };
           const __half2 pa = *reinterpret_cast<const __half2*>(&awa);
@@ -719,8 +726,8 @@ fused_bwd_kernel(const FusedArgs a) {
       // `map_off`: element offset of its value map from `coff`, the base the block is walked with.
       // `crow`: the row's records for the tensor-core pass of the coarse levels (indexed by the
       // sample), or NULL
-      auto run_block = [&](size_t coff, int s, int count, bool have, bool keep, int l, float lx, float ly,
-                           float wgt, unsigned map_off, uint4* crow) {
+      auto run_block = [&](auto scatter_tag, size_t coff, int s, int count, bool have, bool keep, int l, float lx,
+                           float ly, float wgt, unsigned map_off, uint4* crow) {
         float my_wgt = 0.f;
         {
           uint4 ro = make_uint4(0u, 0u, 0u, 0u);
@@ -760,21 +767,56 @@ fused_bwd_kernel(const FusedArgs a) {
         }
         __syncwarp();
         float tga = 0.f, tgx = 0.f, tgy = 0.f;
+        if constexpr (TPH <= 8) {
+          // Fully unrolled walk (record addresses become immediates) with the lane sums done once per
+          // block: every lane keeps its partial (d weight, d x, d y) of each of the block's samples,
+          // and a halving exchange -- TPH - 1 shuffles per quantity instead of TPH log2 TPH -- leaves
+          // lane c with the totals of sample s0 + c.
+          float pa[TPH], px_[TPH], py[TPH];
+#pragma unroll
+          for (int j = 0; j < TPH; ++j) {
+            pa[j] = 0.f; px_[j] = 0.f; py[j] = 0.f;
+            if (j < count) {
+              const uint32_t* rec = my_rec + REC_WORDS * j;
+              const uint4 ro = *reinterpret_cast<const uint4*>(rec);
+              const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
+              float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
+              core(scatter_tag, coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
+                   ra.x, ra.y, ra.z, ra.w, pa[j], px_[j], py[j]);
+            }
+          }
+#pragma unroll
+          for (int w = TPH / 2; w >= 1; w >>= 1) {
+            const bool up = (chunk & w) != 0;          // keeps the upper half of the samples, sends the lower
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+              const float sa = up ? pa[i] : pa[i + w], ka = up ? pa[i + w] : pa[i];
+              const float sx = up ? px_[i] : px_[i + w], kx = up ? px_[i + w] : px_[i];
+              const float sy = up ? py[i] : py[i + w], ky = up ? py[i + w] : py[i];
+              pa[i] = ka + __shfl_xor_sync(0xffffffffu, sa, w);
+              px_[i] = kx + __shfl_xor_sync(0xffffffffu, sx, w);
+              py[i] = ky + __shfl_xor_sync(0xffffffffu, sy, w);
+            }
+          }
+          tga = pa[0]; tgx = px_[0]; tgy = py[0];
+        } else {
 FUSED_UNROLL(FUSED_BWD_UNROLL)
-        for (int j = 0; j < TPH; ++j) {
-          if (j < count) {
-            const uint32_t* rec = my_rec + REC_WORDS * j;
-            const uint4 ro = *reinterpret_cast<const uint4*>(rec);
-            const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
-            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
-            float ga, gx, gy;
-            core(coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
-                 ra.x, ra.y, ra.z, ra.w, ga, gx, gy);
-            ga = group_sum<TPH>(ga);
-            gx = group_sum<TPH>(gx);
-            gy = group_sum<TPH>(gy);
-            if (j == chunk) { tga = ga; tgx = gx; tgy = gy; }
+          for (int j = 0; j < TPH; ++j) {
+            if (j < count) {
+              const uint32_t* rec = my_rec + REC_WORDS * j;
+              const uint4 ro = *reinterpret_cast<const uint4*>(rec);
+              const uint4 rf = *reinterpret_cast<const uint4*>(rec + 4);
+              float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+              if constexpr (!ACC_HALF) ra = *reinterpret_cast<const float4*>(rec + 8);
+              float ga, gx, gy;
+              core(scatter_tag, coff, ro.x, ro.y, ro.z, ro.w, __uint_as_float(rf.x), __uint_as_float(rf.y), rf.z, rf.w,
+                   ra.x, ra.y, ra.z, ra.w, ga, gx, gy);
+              ga = group_sum<TPH>(ga);
+              gx = group_sum<TPH>(gx);
+              gy = group_sum<TPH>(gy);
+              if (j == chunk) { tga = ga; tgx = gx; tgy = gy; }
+            }
           }
         }
         if (keep) {
@@ -820,7 +862,12 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
               ly = r.y + o.y;
               wgt = mine ? my_w[s] : 0.f;
             }
-            run_block(coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u, crow);
+            // (the coarse levels are a suffix of the sample axis: a block that starts inside them has
+            // nothing to scatter -- a warp-uniform choice)
+            if (COARSE && s0 >= coarse_first * a.P)
+              run_block(std::false_type{}, coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u, crow);
+            else
+              run_block(std::true_type{}, coff, s, min(TPH, LP - s0), in_row, in_row && mine, l, lx, ly, wgt, 0u, crow);
           }
         }
       } else {
@@ -845,7 +892,7 @@ FUSED_UNROLL(FUSED_BWD_UNROLL)
             wgt = live ? my_w[s] : 0.f;
             map_off = (unsigned)j * (unsigned)batch_stride;
           }
-          run_block(coff, s, min(TPH, S - s0), in_row, in_row && live, l, lx, ly, wgt, map_off, nullptr);
+          run_block(std::true_type{}, coff, s, min(TPH, S - s0), in_row, in_row && live, l, lx, ly, wgt, map_off, nullptr);
         }
       }
       __syncwarp();

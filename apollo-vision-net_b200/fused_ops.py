@@ -373,9 +373,10 @@ class SpatialCrossAttnFunction(Function):
             if lists is None or lists[0] is None:
                 lists = hit_lists(hit_bits, num_cam)
             assert lists[0].shape == (num_cam, HW) and lists[0].dtype == torch.int32 and lists[0].is_contiguous()
-        # (with the tensor-core pass the coarse levels no longer need replicas of the accumulator tail)
+        # (with the tensor-core pass the coarse levels need no replicas of the accumulator tail, and the
+        # head_dim-32 kernels do not implement them)
         g_value, acc_code, acc_scale, tail, tail_px = _accumulator(value, g_slots, num_levels=L, rows_per_slot=HW,
-                                                                   replicas=records is None)
+                                                                   replicas=records is None and Dh != 32)
         (g_off, g_log), g_off_ptr, g_log_ptr = _Coords.grads(coords, ctx.merged)
         with torch.cuda.device(value.device):
             _lib.call('sca_bwd', value.data_ptr(), shapes.data_ptr(), starts.data_ptr(), off_ptr,

@@ -8,7 +8,7 @@ cd "$(dirname "$0")/.."
 mkdir -p build
 C=apollo-vision-net_b200/csrc
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude"
-for f in abi msda_fwd msda_bwd point_sampling rowops bev_prep wgrad; do       # cached objects of the other sources
+for f in abi msda_fwd msda_bwd point_sampling rowops bev_prep wgrad coarse_scatter; do       # cached objects of the other sources
   if [ ! -f build/$f.o ] || [ $C/$f.cu -nt build/$f.o ] || [ include/msda_b200.h -nt build/$f.o ]; then
     $NV -c $C/$f.cu -o build/$f.o &
   fi
@@ -19,7 +19,7 @@ while [ $# -ge 2 ]; do
   ( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -DFUSED_DEV_ONLY $flags \
       -Iinclude -c $C/fused.cu -o build/fused_$tag.o &&
     nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/libmsda_$tag.so \
-      build/abi.o build/msda_fwd.o build/msda_bwd.o build/point_sampling.o build/rowops.o build/bev_prep.o build/wgrad.o build/fused_$tag.o &&
+      build/abi.o build/msda_fwd.o build/msda_bwd.o build/point_sampling.o build/rowops.o build/bev_prep.o build/wgrad.o build/coarse_scatter.o build/fused_$tag.o &&
     echo "built build/libmsda_$tag.so" ) &
 done
 wait

@@ -78,7 +78,7 @@ def main():
         code = _DTYPE_CODE[dtype]
         rec_bytes = 0 if args.no_coarse else int(_lib.lib().sca_coarse_workspace_bytes(1, 6, HW, M, Dh, P, code))
         records = torch.empty(rec_bytes, dtype=torch.uint8, device=dev) if rec_bytes > 0 else None
-        tail = torch.zeros(7, 6, Nk // 16, M, Dh, device=dev, dtype=torch.float16) \
+        tail = None if True else torch.zeros(7, 6, Nk // 16, M, Dh, device=dev, dtype=torch.float16) \
             if (half_acc and not args.no_tail and records is None) else None
         goff = torch.empty_like(offsets)
         glog = torch.empty_like(logits)
