@@ -117,13 +117,15 @@ coarse_scatter_kernel(const CoarseArgs a) {
   __shared__ uint64_t done_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ int s_patch[3];
+  __shared__ uint32_t s_tiles[CS_STAGES][2];     // M-tiles a K-step touches (per stage, double-buffered by use count)
+  __shared__ uint32_t s_init[CS_ISSUERS];        // M-tiles each issuing warp has written in the current segment
   // Operand dtypes.  fp16 accumulator: the weights are fp16 (11 significant bits whatever the model
   // dtype) and g_out is staged as fp16(g * scale) -- what the reduction path adds, too -- so the patch
   // sums come out scaled.  fp32 accumulator: both operands in the model dtype, unscaled.
   // (kind::f16 wants A and B of ONE format: fp16 x bf16 raises an illegal-instruction fault.)
   using WT = typename std::conditional<ACC_HALF, __half, T>::type;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cam = blockIdx.y / a.M, m = blockIdx.y % a.M, b = blockIdx.z;
+  const int m = blockIdx.y, b = blockIdx.z;
 
   if (tid == 0) {
     const CoarsePatch cp = coarse_patch(a.shapes, a.starts, a.L);
@@ -131,15 +133,19 @@ coarse_scatter_kernel(const CoarseArgs a) {
     s_patch[1] = cp.npix;
     s_patch[2] = cp.start;
   }
+  if (tid < CS_STAGES * 2) s_tiles[tid >> 1][tid & 1] = 0u;
   __syncthreads();
   const int first_level = s_patch[0], npix = s_patch[1], patch_start = s_patch[2];
   if (first_level >= a.L || npix <= 0) return;                       // no coarse patch (whole grid: uniform)
   const int nlev = a.L - first_level;                                // 1 or 2
-  const int count = a.hit_count[cam];
-  const int i0 = (int)((long long)count * blockIdx.x / gridDim.x);
-  const int i1 = (int)((long long)count * (blockIdx.x + 1) / gridDim.x);
-  const int nsteps = (i1 - i0 + CS_KROWS - 1) / CS_KROWS;
-  if (nsteps <= 0) return;                                           // (whole CTA: uniform)
+  // This CTA's share of the (camera, hit query) rows of head m: an equal slice of the cameras' hit
+  // lists laid end to end, so the CTAs finish together however unevenly the cameras see the grid.  A
+  // slice that crosses a camera boundary is processed as one segment per camera (the patch in tensor
+  // memory belongs to one camera at a time).
+  long long total = 0;
+  for (int c = 0; c < a.cams; ++c) total += a.hit_count[c];
+  const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+  if (hi <= lo) return;                                              // (whole CTA: uniform)
   const int NT = (npix + 127) / 128;
   const uint32_t lbo_a = (uint32_t)NT * CS_TILE_BYTES;               // bytes between the two k-groups of 8 rows
 
@@ -164,163 +170,211 @@ coarse_scatter_kernel(const CoarseArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp < CS_ISSUERS) {
-    // ---------------- issuing warps: NT MMAs (M128 N32 K16) per K-step, M-tile t issued by warp t mod 4 ----
-    // One thread issues an MMA in ~50-90 cycles whatever its shape (descriptor arithmetic, five
-    // register-to-uniform moves, the election; tools/micro/umma_shape_bench.cu), several times the
-    // tensor-pipe time of these skinny tiles -- so four warps share the tiles.  A tile always belongs to
-    // the same warp (its accumulation stays in issue order); each warp walks the loop converged and one
-    // ELECTED lane issues (elect.sync names the same lane every time, so a warp's commits track its MMAs).
-    const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
-    const uint32_t idesc_u = a.idesc;
-    const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);        // SBO = 128 bytes | descriptor version 1
-    const uint32_t lbo_field = ((lbo_a >> 4) & 0x3fffu) << 16;
-    const uint32_t b_lbo_field = (uint32_t)(((kCoarseDh / 8) * 128) >> 4) << 16;
-    for (int k = 0; k < nsteps; ++k) {
-      const int st = k % CS_STAGES;
-      cs_wait(&full_bar[st], (uint32_t)((k / CS_STAGES) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_addr = smem_base + (uint32_t)st * CS_STAGE_BYTES;
-      const uint32_t b_lo = (((a_addr + CS_A_BYTES) & 0x3ffffu) >> 4) | b_lbo_field;
-      const uint32_t a_lo0 = ((a_addr & 0x3ffffu) >> 4) | lbo_field;
-      const uint32_t accumulate = k > 0 ? 1u : 0u;
-      const int nt = (a.debug & 2) ? 0 : NT;
-#pragma unroll 4
-      for (int t = warp; t < nt; t += CS_ISSUERS) {
-        // descriptor of M-tile t: the start address field advances by CS_TILE_BYTES / 16
-        asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-                     "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
-                     "elect.sync _|e, 0xffffffff;\n\t"
-                     "setp.ne.b32 p, %4, 0;\n\t"
-                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-                     :: "r"(tmem_u + (uint32_t)t * kCoarseDh), "r"(a_lo0 + (uint32_t)t * (CS_TILE_BYTES >> 4)), "r"(b_lo),
-                        "r"(idesc_u), "r"(accumulate), "r"(desc_hi)
-                     : "memory");
+  // K-steps are numbered through the whole kernel (`g`): step g uses stage g % CS_STAGES for the
+  // (g / CS_STAGES)-th time, which fixes the parities of the stage barriers across segments.
+  int g0 = 0, seg = 0;
+  long long prefix = 0;
+  for (int cam = 0; cam < a.cams; ++cam) {
+    const int count = a.hit_count[cam];
+    const long long s_lo = (lo > prefix ? lo : prefix) - prefix, s_hi = (hi < prefix + count ? hi : prefix + count) - prefix;
+    prefix += count;
+    if (s_lo >= s_hi) continue;                                      // (uniform)
+    const int i0 = (int)s_lo, i1 = (int)s_hi;
+    const int nsteps = (i1 - i0 + CS_KROWS - 1) / CS_KROWS;
+
+    if (warp < CS_ISSUERS) {
+      // ---------------- issuing warps: the touched M-tiles of a K-step (M128 N32 K16), tile t by warp t mod 4 ----
+      // One thread issues an MMA in ~50-90 cycles whatever its shape (descriptor arithmetic, five
+      // register-to-uniform moves, the election; tools/micro/umma_shape_bench.cu), several times the
+      // tensor-pipe time of these skinny tiles -- so four warps share the tiles.  A tile always belongs to
+      // the same warp (its accumulation stays in issue order); each warp walks the loop converged and one
+      // ELECTED lane issues (elect.sync names the same lane every time, so a warp's commits track its MMAs).
+      // A K-step's 16 neighbouring queries touch a few of the patch's tiles: the builders publish which.
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+      const uint32_t idesc_u = a.idesc;
+      const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);      // SBO = 128 bytes | descriptor version 1
+      const uint32_t lbo_field = ((lbo_a >> 4) & 0x3fffu) << 16;
+      const uint32_t b_lbo_field = (uint32_t)(((kCoarseDh / 8) * 128) >> 4) << 16;
+      uint32_t inited = 0u;
+      for (int k = 0; k < nsteps; ++k) {
+        const int g = g0 + k, st = g % CS_STAGES, use = g / CS_STAGES;
+        cs_wait(&full_bar[st], (uint32_t)(use & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t tiles = *reinterpret_cast<volatile uint32_t*>(&s_tiles[st][use & 1]);
+        if (a.debug & 8) tiles = 0xffffffffu;
+        if (a.debug & 2) tiles = 0u;
+        const uint32_t a_addr = smem_base + (uint32_t)st * CS_STAGE_BYTES;
+        const uint32_t b_lo = (((a_addr + CS_A_BYTES) & 0x3ffffu) >> 4) | b_lbo_field;
+        const uint32_t a_lo0 = ((a_addr & 0x3ffffu) >> 4) | lbo_field;
+        for (int t = warp; t < NT; t += CS_ISSUERS) {
+          if (!((tiles >> t) & 1u)) continue;
+          const uint32_t accumulate = (inited >> t) & 1u;
+          inited |= 1u << t;
+          // descriptor of M-tile t: the start address field advances by CS_TILE_BYTES / 16
+          asm volatile("{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+                       "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+                       "elect.sync _|e, 0xffffffff;\n\t"
+                       "setp.ne.b32 p, %4, 0;\n\t"
+                       "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+                       :: "r"(tmem_u + (uint32_t)t * kCoarseDh), "r"(a_lo0 + (uint32_t)t * (CS_TILE_BYTES >> 4)), "r"(b_lo),
+                          "r"(idesc_u), "r"(accumulate), "r"(desc_hi)
+                       : "memory");
+        }
+        // arrives when these MMAs (and all earlier ones) have completed: the stage may be rewritten
+        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                     "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                     :: "r"(smem_u32(&empty_bar[st])) : "memory");
       }
-      // arrives when these MMAs (and all earlier ones) have completed: the stage may be rewritten
       asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
                    "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-                   :: "r"(smem_u32(&empty_bar[st])) : "memory");
-    }
-    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-                 :: "r"(smem_u32(&done_bar)) : "memory");
-  } else {
-    // ---------------- builder warps: CS_BUILDERS per stage, 4 rows of the K-step each ----------------
-    const int st = (warp - CS_ISSUERS) / CS_BUILDERS, sub = (warp - CS_ISSUERS) % CS_BUILDERS;
-    unsigned char* A = smem + (size_t)st * CS_STAGE_BYTES;
-    unsigned char* B = A + CS_A_BYTES;
-    // lane = (row of the warp's four, coarse level slot, bilinear corner)
-    const int r = sub * 4 + (lane >> 3), slot = (lane >> 2) & 1, cn = lane & 3;
-    const bool lane_on = slot < nlev;
-    const uint32_t row_off = (uint32_t)(r >> 3) * lbo_a + (uint32_t)(r & 7) * 16;
-    const int recs_per_row = kCoarseMaxLevels * a.P;
-    const T* gout = static_cast<const T*>(a.g_out);
-    const float g_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
-    // one K-step of this lane: word `cn` of the records of its (row, level) -- byte offset of the pixel
-    // inside the row's k-group : 16 | weight : 16 -- and, for the corner-0/1 lanes, one 16-byte chunk of
-    // the row's upstream gradient (all zero for rows past the slice)
-    struct Step {
-      uint32_t w[kCoarseMaxP];
-      uint4 g;
-    };
-    auto fetch = [&](int k, Step& d) {
-      const int i = i0 + k * CS_KROWS + r;
-      const bool ok = k < nsteps && i < i1 && !(a.debug & 4);
-      const int q = ok ? __ldg(a.hit_index + (size_t)cam * a.Nq + i) : 0;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(
-          a.rec + ((((size_t)b * a.cams + cam) * a.Nq + q) * a.M + m) * recs_per_row + (size_t)slot * a.P) + cn;
-#pragma unroll
-      for (int j = 0; j < kCoarseMaxP; ++j) d.w[j] = (ok && lane_on && j < a.P) ? __ldg(src + 4 * j) : 0u;
-      const uint4* gs = reinterpret_cast<const uint4*>(gout + (((size_t)b * a.Nq + q) * a.M + m) * kCoarseDh) + slot * 2 + cn;
-      d.g = (ok && cn < 2) ? __ldg(gs) : make_uint4(0u, 0u, 0u, 0u);
-    };
-    const uint32_t a_row = smem_u32(A) + row_off;
-    const uint32_t b_at = smem_u32(B) + (uint32_t)(r >> 3) * ((kCoarseDh / 8) * 128) + (uint32_t)(slot * 2 + cn) * 128 +
-                          (uint32_t)(r & 7) * 16;
-    // samples one after the other: the warp's lanes update sample j together (distinct addresses, or
-    // nothing where the weight is zero), and the __syncwarp orders sample j's stores before sample
-    // j + 1's loads of a pixel that another corner lane of the same row wrote
-    auto build = [&](const Step& d) {
-#pragma unroll
-      for (int j = 0; j < kCoarseMaxP; ++j) {
-        const uint32_t w = d.w[j];
-        if (w & 0x7fff0000u) {
-          const uint32_t at = a_row + (w & 0xffffu);
-          cs_sts16(at, cs_add_bits<WT>(cs_lds16(at), (uint16_t)(w >> 16)));
-        }
-        __syncwarp();
-      }
-    };
-    auto erase = [&](const Step& d) {
-#pragma unroll
-      for (int j = 0; j < kCoarseMaxP; ++j)
-        if (d.w[j] & 0x7fff0000u) cs_sts16(a_row + (d.w[j] & 0xffffu), (uint16_t)0);
-    };
+                   :: "r"(smem_u32(&done_bar)) : "memory");
 
-    Step cur, nxt;
-    fetch(st, cur);
-    for (int k = st, n = 0; k < nsteps; k += CS_STAGES, ++n) {
-      fetch(k + CS_STAGES, nxt);                                     // in flight while this step is built
-      if (!(a.debug & 1)) build(cur);                                // (the stage is all-zero here)
-      if (cn < 2) {
-        if constexpr (ACC_HALF) cs_sts128(b_at, cs_to_f16_scaled<T>(cur.g, g_scale));
-        else cs_sts128(b_at, cur.g);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-      __syncwarp();
-      if (lane == 0) cs_arrive(&full_bar[st]);
-      if (k + CS_STAGES < nsteps) {
-        cs_wait(&empty_bar[st], (uint32_t)(n & 1));                  // this step's MMAs have read the stage
-        if (!(a.debug & 1)) erase(cur);                              // back to all-zero
-      }
-      cur = nxt;
-    }
-  }
-
-  // ---------------- epilogue: TMEM -> registers -> one reduction per (pixel, head) ----------------
-  if (warp < 4) {                                                    // (the issuers) warp i reads TMEM lanes [32 i, 32 i + 32)
-    cs_wait(&done_bar, 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const size_t map = (size_t)b * a.cams + cam;
-    for (int t = 0; t < NT; ++t) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * kCoarseDh;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int p = t * 128 + warp * 32 + lane;
-      if (p < npix) {
-        const size_t at = ((map * a.Nk + patch_start + p) * a.M + m) * kCoarseDh;
-        if constexpr (ACC_HALF) {
-          __half* dst = static_cast<__half*>(a.g_value) + at;
+      // ---------------- epilogue: TMEM -> registers -> one reduction per (pixel, head) ----------------
+      // (the issuers) warp i reads TMEM lanes [32 i, 32 i + 32); tiles no K-step touched hold nothing
+      if (lane == 0) s_init[warp] = inited;
+      cs_wait(&done_bar, (uint32_t)(seg & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * CS_ISSUERS) : "memory");
+      uint32_t written = 0u;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint32_t h[4];
+      for (int w = 0; w < CS_ISSUERS; ++w) written |= *reinterpret_cast<volatile uint32_t*>(&s_init[w]);
+      const size_t map = (size_t)b * a.cams + cam;
+      for (int t = 0; t < NT; ++t) {
+        if (!((written >> t) & 1u)) continue;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)t * kCoarseDh;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int p = t * 128 + warp * 32 + lane;
+        if (p < npix) {
+          const size_t at = ((map * a.Nk + patch_start + p) * a.M + m) * kCoarseDh;
+          if constexpr (ACC_HALF) {
+            __half* dst = static_cast<__half*>(a.g_value) + at;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 x = __floats2half2_rn(__uint_as_float(v[c + 2 * e]), __uint_as_float(v[c + 2 * e + 1]));
-              h[e] = *reinterpret_cast<const uint32_t*>(&x);
+            for (int c = 0; c < 32; c += 8) {
+              uint32_t h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 x = __floats2half2_rn(__uint_as_float(v[c + 2 * e]), __uint_as_float(v[c + 2 * e + 1]));
+                h[e] = *reinterpret_cast<const uint32_t*>(&x);
+              }
+              red_add_f16x8(dst + c, h[0], h[1], h[2], h[3]);
             }
-            red_add_f16x8(dst + c, h[0], h[1], h[2], h[3]);
-          }
-        } else {
-          float* dst = static_cast<float*>(a.g_value) + at;
+          } else {
+            float* dst = static_cast<float*>(a.g_value) + at;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            red_add_f32x4(dst + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
-                          __uint_as_float(v[c + 3]));
+            for (int c = 0; c < 32; c += 4)
+              red_add_f32x4(dst + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
+                            __uint_as_float(v[c + 3]));
+          }
         }
       }
+      // every issuer has read the patch before the next segment's first MMAs overwrite it
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" :: "n"(32 * CS_ISSUERS) : "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else {
+      // ---------------- builder warps: CS_BUILDERS per stage, 4 rows of the K-step each ----------------
+      const int st = (warp - CS_ISSUERS) / CS_BUILDERS, sub = (warp - CS_ISSUERS) % CS_BUILDERS;
+      unsigned char* A = smem + (size_t)st * CS_STAGE_BYTES;
+      unsigned char* B = A + CS_A_BYTES;
+      // lane = (row of the warp's four, coarse level slot, bilinear corner)
+      const int r = sub * 4 + (lane >> 3), slot = (lane >> 2) & 1, cn = lane & 3;
+      const bool lane_on = slot < nlev;
+      const uint32_t row_off = (uint32_t)(r >> 3) * lbo_a + (uint32_t)(r & 7) * 16;
+      const int recs_per_row = kCoarseMaxLevels * a.P;
+      const T* gout = static_cast<const T*>(a.g_out);
+      const float g_scale = ACC_HALF ? __ldg(a.acc_scale) : 1.f;
+      // one K-step of this lane: word `cn` of the records of its (row, level) -- byte offset of the pixel
+      // inside the row's k-group : 16 | weight : 16 -- and, for the corner-0/1 lanes, one 16-byte chunk of
+      // the row's upstream gradient (all zero for rows past the slice)
+      struct Step {
+        uint32_t w[kCoarseMaxP];
+        uint4 g;
+      };
+      // the row's query index is read one use of the stage ahead of its records (no dependent load
+      // on the critical path); k = step inside the segment
+      auto fetch_index = [&](int k) -> int {
+        const int i = i0 + k * CS_KROWS + r;
+        return (k < nsteps && i < i1 && !(a.debug & 4)) ? __ldg(a.hit_index + (size_t)cam * a.Nq + i) : -1;
+      };
+      auto fetch = [&](int q, Step& d) {
+        const bool ok = q >= 0;
+        const size_t qq = ok ? (size_t)q : 0;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(
+            a.rec + ((((size_t)b * a.cams + cam) * a.Nq + qq) * a.M + m) * recs_per_row + (size_t)slot * a.P) + cn;
+#pragma unroll
+        for (int j = 0; j < kCoarseMaxP; ++j) d.w[j] = (ok && lane_on && j < a.P) ? __ldg(src + 4 * j) : 0u;
+        const uint4* gs = reinterpret_cast<const uint4*>(gout + (((size_t)b * a.Nq + qq) * a.M + m) * kCoarseDh) + slot * 2 + cn;
+        d.g = (ok && cn < 2) ? __ldg(gs) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      const uint32_t a_row = smem_u32(A) + row_off;
+      const uint32_t b_at = smem_u32(B) + (uint32_t)(r >> 3) * ((kCoarseDh / 8) * 128) + (uint32_t)(slot * 2 + cn) * 128 +
+                            (uint32_t)(r & 7) * 16;
+      // samples one after the other: the warp's lanes update sample j together (distinct addresses, or
+      // nothing where the weight is zero), and the __syncwarp orders sample j's stores before sample
+      // j + 1's loads of a pixel that another corner lane of the same row wrote.  Returns the M-tiles
+      // this lane touched (position >> 11 = pixel / 128).
+      auto build = [&](const Step& d) -> uint32_t {
+        uint32_t tiles = 0u;
+#pragma unroll
+        for (int j = 0; j < kCoarseMaxP; ++j) {
+          const uint32_t w = d.w[j];
+          if (w & 0x7fff0000u) {
+            const uint32_t at = a_row + (w & 0xffffu);
+            cs_sts16(at, cs_add_bits<WT>(cs_lds16(at), (uint16_t)(w >> 16)));
+            tiles |= 1u << ((w & 0xffffu) >> 11);
+          }
+          __syncwarp();
+        }
+        return tiles;
+      };
+      auto erase = [&](const Step& d) {
+#pragma unroll
+        for (int j = 0; j < kCoarseMaxP; ++j)
+          if (d.w[j] & 0x7fff0000u) cs_sts16(a_row + (d.w[j] & 0xffffu), (uint16_t)0);
+      };
+
+      // first step of this segment that falls on this warp's stage
+      const int k_first = ((st - g0) % CS_STAGES + CS_STAGES) % CS_STAGES;
+      Step cur, nxt;
+      fetch(fetch_index(k_first), cur);
+      int q_next = fetch_index(k_first + CS_STAGES);
+      for (int k = k_first; k < nsteps; k += CS_STAGES) {
+        const int use = (g0 + k) / CS_STAGES;
+        fetch(q_next, nxt);                                            // in flight while this step is built
+        q_next = fetch_index(k + 2 * CS_STAGES);
+        uint32_t tiles = 0u;
+        if (!(a.debug & 1)) tiles = build(cur);                        // (the stage is all-zero here)
+        if (cn < 2) {
+          if constexpr (ACC_HALF) cs_sts128(b_at, cs_to_f16_scaled<T>(cur.g, g_scale));
+          else cs_sts128(b_at, cur.g);
+        }
+        tiles = __reduce_or_sync(0xffffffffu, tiles);
+        if (lane == 0) {
+          if (tiles) atomicOr(&s_tiles[st][use & 1], tiles);
+          if (sub == 0) s_tiles[st][(use + 1) & 1] = 0u;               // (read by the issuers one use ago)
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) cs_arrive(&full_bar[st]);
+        cs_wait(&empty_bar[st], (uint32_t)(use & 1));                  // this step's MMAs have read the stage
+        if (!(a.debug & 1)) erase(cur);                                // back to all-zero
+        cur = nxt;
+      }
     }
+    g0 += nsteps;
+    ++seg;
   }
+
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)
@@ -356,12 +410,12 @@ static int coarse_launch_t(const CoarseArgs& a0, bool acc_half, cudaStream_t st)
   auto kfn = acc_half ? coarse_scatter_kernel<T, true> : coarse_scatter_kernel<T, false>;
   if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM) != cudaSuccess)
     return set_error(MSDA_ERR_CUDA, "sca_coarse_scatter: cannot reserve %d bytes of shared memory", CS_SMEM);
-  // one CTA per SM (shared memory, all 512 TMEM columns): split every (batch, camera, head) patch over
-  // enough CTAs to fill the machine once
-  const int units = a.bs * a.cams * a.M;
+  // one CTA per SM (shared memory, all 512 TMEM columns): the (camera, hit query) rows of every
+  // (batch, head) are split evenly over enough CTAs to fill the machine once
+  const int units = a.bs * a.M;
   int split = cs_sm_count() / units;
   if (split < 1) split = 1;
-  const dim3 grid((unsigned)split, (unsigned)(a.cams * a.M), (unsigned)a.bs);
+  const dim3 grid((unsigned)split, (unsigned)a.M, (unsigned)a.bs);
   kfn<<<grid, CS_THREADS, CS_SMEM, st>>>(a);
   count_launch();
   return check_launch("sca_coarse_scatter");
