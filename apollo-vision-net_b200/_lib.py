@@ -50,13 +50,17 @@ _SIGNATURES = {
     'bev_rotate_nearest': (_c_int, [_c_vp] * 5 + [_c_int] * 5 + [_c_vp]),
     'linear_wgrad_workspace_floats': (_c_i64, [_c_int, _c_int]),
     'linear_wgrad': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
-    'relu_bwd_colsum': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_vp]),
+    'relu_bwd_colsum': (_c_int, [_c_vp] * 5 + [_c_i64, _c_int, _c_int, _c_int, _c_f, _c_vp]),
+    'ln_residual_dropout_fwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_f, _c_int, _c_vp, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
+    'ln_bwd_dxsum_dropout': (_c_int, [_c_vp] * 9 + [_c_i64, _c_int, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
+    'relu_dropout_fwd': (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
+    'dropout_keep_mask': (_c_int, [_c_vp, _c_i64, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
     'ln_residual_fwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd_dxsum': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),
 }
 
 _lib = None
-ABI_VERSION = 4          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
+ABI_VERSION = 5          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
 
 
 def _stale():

@@ -354,7 +354,7 @@ int ln_fwd(const void* x, const void* gamma, const void* beta, void* y, float* m
   if (rows == 0) return MSDA_OK;
   if (!x || !gamma || !beta || !y || !mean || !rstd) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_fwd: NULL pointer");
   return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
-                   dtype, nullptr, nullptr, false, static_cast<cudaStream_t>(stream));
+                   dtype, nullptr, nullptr, false, RowDropout{}, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int ln_residual_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* sum_out,
@@ -365,7 +365,20 @@ int ln_residual_fwd(const void* x, const void* residual, const void* gamma, cons
   if (!x || !residual || !gamma || !beta || !sum_out || !y || !mean || !rstd)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_residual_fwd: NULL pointer");
   return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
-                   dtype, residual, sum_out, false, static_cast<cudaStream_t>(stream));
+                   dtype, residual, sum_out, false, RowDropout{}, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int ln_residual_dropout_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* sum_out,
+                            void* y, float* mean, float* rstd, int64_t rows, int C, float eps, int dtype,
+                            const void* rng_state, void* key_save, uint32_t site, float p, void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_residual_dropout_fwd: invalid sizes");
+  if (rows == 0) return MSDA_OK;
+  if (!x || !residual || !gamma || !beta || !sum_out || !y || !mean || !rstd || !rng_state)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_residual_dropout_fwd: NULL pointer");
+  RowDropout rd;
+  rd.key = rng_state; rd.key_save = key_save; rd.site = site; rd.p = p;
+  return launch_ln(false, x, nullptr, gamma, beta, y, mean, rstd, nullptr, nullptr, nullptr, rows, C, eps,
+                   dtype, residual, sum_out, false, rd, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
@@ -374,7 +387,7 @@ int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, 
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma_dbeta || !partial)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd: NULL pointer");
   return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
-                   dx, dgamma_dbeta, partial, rows, C, 0.f, dtype, nullptr, nullptr, false,
+                   dx, dgamma_dbeta, partial, rows, C, 0.f, dtype, nullptr, nullptr, false, RowDropout{}, nullptr,
                    static_cast<cudaStream_t>(stream));
 }
 
@@ -385,22 +398,51 @@ int ln_bwd_dxsum(const void* x, const void* dy, const void* gamma, const float* 
   if (!x || !dy || !gamma || !mean || !rstd || !dx || !dgamma_dbeta_dxsum || !partial)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd_dxsum: NULL pointer");
   return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
-                   dx, dgamma_dbeta_dxsum, partial, rows, C, 0.f, dtype, nullptr, nullptr, true,
+                   dx, dgamma_dbeta_dxsum, partial, rows, C, 0.f, dtype, nullptr, nullptr, true, RowDropout{}, nullptr,
                    static_cast<cudaStream_t>(stream));
+}
+
+int ln_bwd_dxsum_dropout(const void* x, const void* dy, const void* gamma, const float* mean, const float* rstd,
+                         void* dx, void* dx_masked, void* dgamma_dbeta_dxsum, float* partial, int64_t rows, int C,
+                         int dtype, const void* key, uint32_t site, float p, void* stream) {
+  if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd_dxsum_dropout: invalid sizes");
+  if (!x || !dy || !gamma || !mean || !rstd || !dx || !dx_masked || !dgamma_dbeta_dxsum || !partial || !key)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "ln_bwd_dxsum_dropout: NULL pointer");
+  RowDropout rd;
+  rd.key = key; rd.site = site; rd.p = p;
+  return launch_ln(true, x, dy, gamma, nullptr, nullptr, const_cast<float*>(mean), const_cast<float*>(rstd),
+                   dx, dgamma_dbeta_dxsum, partial, rows, C, 0.f, dtype, nullptr, nullptr, true, rd, dx_masked,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int relu_dropout_fwd(void* x, int64_t n, int dtype, const void* rng_state, void* key_save, uint32_t site, float p,
+                     void* stream) {
+  if (n < 0 || (n > 0 && !x) || !rng_state) return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_dropout_fwd: bad argument");
+  RowDropout rd;
+  rd.key = rng_state; rd.key_save = key_save; rd.site = site; rd.p = p;
+  return launch_relu_dropout(x, nullptr, n, dtype, rd, static_cast<cudaStream_t>(stream));
+}
+
+int dropout_keep_mask(uint8_t* mask, int64_t n, int dtype, const void* key, uint32_t site, float p, void* stream) {
+  if (n < 0 || (n > 0 && !mask) || !key) return set_error(MSDA_ERR_BAD_ARGUMENT, "dropout_keep_mask: bad argument");
+  RowDropout rd;
+  rd.key = key; rd.site = site; rd.p = p;
+  return launch_relu_dropout(nullptr, mask, n, dtype, rd, static_cast<cudaStream_t>(stream));
 }
 
 int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dtype, int out_dtype,
            void* stream) {
   if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: invalid sizes");
   if (!x || !out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "colsum: NULL pointer");
-  return launch_colsum(x, nullptr, nullptr, out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+  return launch_colsum(x, nullptr, nullptr, out, partial, rows, C, dtype, out_dtype, 1.f, static_cast<cudaStream_t>(stream));
 }
 
 int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, float* partial, int64_t rows, int C,
-                    int dtype, int out_dtype, void* stream) {
+                    int dtype, int out_dtype, float scale, void* stream) {
   if (rows < 0 || C <= 0) return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_bwd_colsum: invalid sizes");
   if (!dy || !y || !dx || !colsum_out || !partial) return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_bwd_colsum: NULL pointer");
-  return launch_colsum(dy, y, dx, colsum_out, partial, rows, C, dtype, out_dtype, static_cast<cudaStream_t>(stream));
+  return launch_colsum(dy, y, dx, colsum_out, partial, rows, C, dtype, out_dtype, scale > 0.f ? scale : 1.f,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int grad_amax_scale(const void* g, int64_t n, int dtype, float limit, float* ws, void* stream) {

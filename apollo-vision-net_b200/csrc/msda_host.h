@@ -80,12 +80,20 @@ int launch_hit_lists(const uint32_t* hit_bits, int num_cam, int HW, int32_t* hit
 int launch_tsa_fwd(const FusedProblem& fp, cudaStream_t st);
 int launch_tsa_bwd(const FusedProblem& fp, cudaStream_t st);
 int rowops_partial_rows();
+// Dropout fused into the row kernels (rowops.cu): `key` = (seed, step) uint64 pair on the device, NULL = off.
+struct RowDropout {
+  const void* key = nullptr;
+  void* key_save = nullptr;            // forward: receives the pair used (for the backward)
+  uint32_t site = 0;
+  float p = 0.f;
+};
 int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
               long long rows, int C, float eps, int dtype, const void* residual, void* sum_out,
-              bool dxsum, cudaStream_t st);
+              bool dxsum, const RowDropout& rd, void* dx_masked, cudaStream_t st);
 int launch_colsum(const void* x, const void* y, void* dx, void* out, float* partial, long long rows, int C,
-                  int dtype, int out_dtype, cudaStream_t st);
+                  int dtype, int out_dtype, float relu_scale, cudaStream_t st);
+int launch_relu_dropout(void* x, void* mask_out, long long n, int dtype, const RowDropout& rd, cudaStream_t st);
 int launch_flatten_level(const void* feat, const void* cams, const void* lvl, void* out, int bs, int num_cam,
                          int C, int hw, long long Nk, long long start, int dtype, cudaStream_t st);
 int launch_rotate_nearest(const void* prev, void* out, const float* theta, const float* xs, const float* ys,

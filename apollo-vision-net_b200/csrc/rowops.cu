@@ -32,6 +32,51 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- dropout: counter-based masks, recomputed in the backward (no mask tensor) -------------------
+// The reference trains with dropout 0.1 after the output projections of TSA / SCA and twice inside the
+// FFN (temporal_self_attention.py:285-289, spatial_cross_attention.py:171-173, mmcv FFN).  Element e of
+// a tensor is kept when the 16-bit lane (e % 8) of Philox4x32-10(counter = (e / 8, call site, step),
+// key = seed) is >= round(p * 65536); kept values are scaled by 1 / (1 - p).  (seed, step) live in a
+// device buffer (the step advances on the device once per training step, so a replayed CUDA graph draws
+// new masks); the forward kernel copies the pair it used into `key_save`, which the backward reads.
+struct DropArgs {
+  const unsigned long long* key_src;   // (seed, step) on the device; NULL = no dropout
+  unsigned long long* key_save;        // forward: where block 0 stores the pair (may be NULL)
+  uint32_t site;                       // call site (distinct per dropout instance inside a step)
+  uint32_t thresh;                     // round(p * 65536)
+  float scale;                         // 1 / (1 - p)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// keep bits (bit j = element 8 * group + j is kept)
+__device__ __forceinline__ uint32_t drop_keep8(unsigned long long group, unsigned long long seed,
+                                               unsigned long long step, uint32_t site, uint32_t thresh) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), site, (uint32_t)step),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t keep = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) keep |= (((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thresh ? 1u : 0u) << j;
+  return keep;
+}
+// keep bits of the VEC (4 or 8) consecutive elements starting at element e0 (a multiple of VEC)
+template <int VEC>
+__device__ __forceinline__ uint32_t drop_keep(unsigned long long e0, unsigned long long seed, unsigned long long step,
+                                              const DropArgs& d) {
+  const uint32_t k = drop_keep8(e0 >> 3, seed, step, d.site, d.thresh);
+  return VEC == 8 ? k : (k >> (e0 & 4)) & 0xfu;
+}
+
 // Final stage of the column reductions.  Every CTA adds its partial sums into an fp32 strip in
 // the workspace with reductions at L2 (the strip is all zero on entry); the LAST CTA to finish
 // (ticket counter in the workspace header) converts the strip into the output and zeroes strip and
@@ -64,14 +109,24 @@ __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __r
 // One warp per row; every lane keeps its slice of the row (C / 32 elements, <= 32) in registers.
 // With `residual`: normalises s = x + residual, rounded to T first (bit-identical to a separate
 // add kernel followed by LayerNorm), and writes s to `sum_out` (may alias x) for the backward.
-template <typename T, int PER_LANE>
+// DROP: s = dropout(x) + residual (x = the output of the block's last Linear).
+template <typename T, int PER_LANE, bool DROP>
 __global__ void __launch_bounds__(kRowThreads)
 ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ gamma,
               const T* __restrict__ beta, T* sum_out, T* __restrict__ y, float* __restrict__ mean,
-              float* __restrict__ rstd, long long rows, int C, float eps) {
+              float* __restrict__ rstd, long long rows, int C, float eps, const DropArgs drop) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
   const int lane = threadIdx.x & 31;
+  unsigned long long seed = 0ull, step = 0ull;
+  if (DROP) {
+    seed = drop.key_src[0];
+    step = drop.key_src[1];
+    if (drop.key_save != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+      drop.key_save[0] = seed;
+      drop.key_save[1] = step;
+    }
+  }
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
   float g[PER_LANE], bb[PER_LANE];
@@ -110,6 +165,11 @@ ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ 
       if (residual != nullptr) {
         float rr[VEC];
         Vec16<T>::unpack(cr[v], rr);
+        if (DROP) {        // (rounded to T like a separate dropout kernel's output)
+          const uint32_t keep = drop_keep<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) t[i] = ((keep >> i) & 1u) ? to_f32<T>(from_f32<T>(t[i] * drop.scale)) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) t[i] = to_f32<T>(from_f32<T>(t[i] + rr[i]));
         Vec16IO<T>::store(sum_out + r * C + (v * 32 + lane) * VEC, t);
@@ -138,11 +198,14 @@ ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ 
 // DXSUM: additionally the column sums of dx (as rounded to T) -- the bias gradient of a Linear
 // layer whose output (plus a residual) this LayerNorm normalised; output rows: d gamma, d beta,
 // sum of dx.
-template <typename T, int PER_LANE, bool DXSUM>
+// DROP (with DXSUM): the normalised sum was dropout(lin) + residual, so the gradient of the Linear output
+// is dx masked and scaled -- written to `dx_masked` and summed over the rows instead of dx.
+template <typename T, int PER_LANE, bool DXSUM, bool DROP>
 __global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? LN_BWD_MINBLOCKS : 1)
 ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-              float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C) {
+              float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C,
+              T* __restrict__ dx_masked, const DropArgs drop) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
   constexpr int NOUT = DXSUM ? 3 : 2;
@@ -151,6 +214,11 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + wid;
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
   float dg[PER_LANE], db[PER_LANE], dsum[DXSUM ? PER_LANE : 1];
+  unsigned long long seed = 0ull, step = 0ull;
+  if (DROP) {
+    seed = drop.key_src[0];
+    step = drop.key_src[1];
+  }
   constexpr int NVG = NV > 0 ? NV : 1;
   uint4 gpk[NVG];                                     // gamma stays packed (registers), unpacked per row
 #pragma unroll
@@ -206,9 +274,19 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
       for (int i = 0; i < VEC; ++i) {
         const int k = v * VEC + i;
         t[i] = rs * (gd[k] - s1 - xh[k] * s2);
-        if (DXSUM) dsum[k] += to_f32<T>(from_f32<T>(t[i]));      // what a column sum of dx would read
+        if (DXSUM && !DROP) dsum[k] += to_f32<T>(from_f32<T>(t[i]));      // what a column sum of dx would read
       }
       Vec16IO<T>::store(dx + r * C + (v * 32 + lane) * VEC, t);
+      if (DXSUM && DROP) {
+        const uint32_t keep = drop_keep<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop);
+        float u[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          u[i] = ((keep >> i) & 1u) ? to_f32<T>(from_f32<T>(to_f32<T>(from_f32<T>(t[i])) * drop.scale)) : 0.f;
+          dsum[v * VEC + i] += u[i];
+        }
+        Vec16IO<T>::store(dx_masked + r * C + (v * 32 + lane) * VEC, u);
+      }
     }
   }
   // CTA reduction of the per-warp partials, then one row of partials per CTA
@@ -242,10 +320,12 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
 // RELU: the matrix summed is dx = (y > 0 ? x : 0) -- the backward of ReLU with upstream gradient x and
 // forward output y -- and dx is written out as well: one pass gives the activation's input gradient and
 // the bias gradient of the Linear layer in front of it.
+// `relu_scale`: factor on the kept entries (1 / (1 - p) when a dropout was fused into the activation: y is
+// then zero where the unit was dropped, too, so y > 0 selects exactly the surviving entries).
 template <typename T, typename TO, bool RELU>
 __global__ void __launch_bounds__(kRowThreads)
 colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ dx, float* __restrict__ ws,
-              TO* __restrict__ out, long long rows, int C) {
+              TO* __restrict__ out, long long rows, int C, float relu_scale) {
   constexpr int VEC = Vec16<T>::N;
   extern __shared__ __align__(16) float sm[];                       // [row_lanes][C]
   const int groups = C / VEC;                         // <= 256
@@ -260,7 +340,8 @@ colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
       float m[VEC];
       Vec16IO<T>::load(y + r * C + gidx * VEC, m);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) t[i] = m[i] > 0.f ? t[i] : 0.f;
+      for (int i = 0; i < VEC; ++i)
+        t[i] = m[i] > 0.f ? (relu_scale == 1.f ? t[i] : to_f32<T>(from_f32<T>(t[i] * relu_scale))) : 0.f;
       Vec16IO<T>::store(dx + r * C + gidx * VEC, t);
     }
   };
@@ -320,25 +401,37 @@ int rowops_partial_rows() { return row_grid(); }
 template <typename T, int PER_LANE>
 static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
                      float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
-                     float eps, const void* residual, void* sum_out, bool dxsum, cudaStream_t st) {
+                     float eps, const void* residual, void* sum_out, bool dxsum, const RowDropout& rd,
+                     void* dx_masked, cudaStream_t st) {
   const long long need = (rows + kRowThreads / 32 - 1) / (kRowThreads / 32);
   const int grid = (int)(need < row_grid() ? need : row_grid());
   if (grid <= 0) return MSDA_OK;
+  const bool dropping = rd.key != nullptr && rd.p > 0.f;
+  DropArgs da{};
+  if (dropping) {
+    da.key_src = static_cast<const unsigned long long*>(rd.key);
+    da.key_save = static_cast<unsigned long long*>(rd.key_save);
+    da.site = rd.site;
+    da.thresh = (uint32_t)(rd.p * 65536.f + 0.5f);
+    da.scale = 1.f / (1.f - rd.p);
+  }
   if (!bwd) {
-    ln_fwd_kernel<T, PER_LANE><<<grid, kRowThreads, 0, st>>>(
+    auto kfwd = dropping ? ln_fwd_kernel<T, PER_LANE, true> : ln_fwd_kernel<T, PER_LANE, false>;
+    kfwd<<<grid, kRowThreads, 0, st>>>(
         static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(gamma),
-        static_cast<const T*>(beta), static_cast<T*>(sum_out), static_cast<T*>(y), mean, rstd, rows, C, eps);
+        static_cast<const T*>(beta), static_cast<T*>(sum_out), static_cast<T*>(y), mean, rstd, rows, C, eps, da);
     count_launch();
     return check_launch("ln_fwd");
   }
   const size_t smem = (size_t)(kRowThreads / 32) * (dxsum ? 3 : 2) * C * sizeof(float);
-  auto kfn = dxsum ? ln_bwd_kernel<T, PER_LANE, true> : ln_bwd_kernel<T, PER_LANE, false>;
+  auto kfn = dxsum ? (dropping ? ln_bwd_kernel<T, PER_LANE, true, true> : ln_bwd_kernel<T, PER_LANE, true, false>)
+                   : ln_bwd_kernel<T, PER_LANE, false, false>;
   if (smem + 1024 > 48 * 1024 &&        // (+ the kernel's static shared memory)
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return set_error(MSDA_ERR_CUDA, "ln_bwd: cannot reserve %zu bytes of shared memory", smem);
   kfn<<<row_grid(), kRowThreads, smem, st>>>(
       static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<const T*>(gamma), mean, rstd,
-      static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C);
+      static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C, static_cast<T*>(dx_masked), da);
   count_launch();
   return check_launch("ln_bwd");
 }
@@ -346,12 +439,13 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
 template <typename T>
 static int ln_dispatch(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
                        float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
-                       float eps, const void* residual, void* sum_out, bool dxsum, cudaStream_t st) {
+                       float eps, const void* residual, void* sum_out, bool dxsum, const RowDropout& rd,
+                       void* dx_masked, cudaStream_t st) {
   constexpr int VEC = Vec16<T>::N;
   if (C % (32 * VEC) != 0 || C / 32 > 32)
     return set_error(MSDA_ERR_UNSUPPORTED, "layer_norm: C=%d must be a multiple of %d and <= 1024", C, 32 * VEC);
 #define LN_CASE(n) case n: return ln_launch<T, n>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgb, \
-                                                  rows, C, eps, residual, sum_out, dxsum, st)
+                                                  rows, C, eps, residual, sum_out, dxsum, rd, dx_masked, st)
   switch (C / 32) {
     LN_CASE(4);
     LN_CASE(8);
@@ -554,33 +648,92 @@ int launch_unscale_cast(const void* acc16, void* out, const float* scale, long l
 int launch_ln(bool bwd, const void* x, const void* dy, const void* gamma, const void* beta, void* y,
               float* mean, float* rstd, void* dx, void* dgamma_dbeta, float* partial,
               long long rows, int C, float eps, int dtype, const void* residual, void* sum_out,
-              bool dxsum, cudaStream_t st) {
+              bool dxsum, const RowDropout& rd, void* dx_masked, cudaStream_t st) {
+  if (rd.key != nullptr && rd.p > 0.f) {
+    if (!(rd.p < 1.f)) return set_error(MSDA_ERR_BAD_ARGUMENT, "layer_norm: dropout probability %g out of [0, 1)", rd.p);
+    if (!bwd && residual == nullptr)
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "layer_norm: the fused dropout acts on the residual form only");
+    if (bwd && (!dxsum || dx_masked == nullptr))
+      return set_error(MSDA_ERR_BAD_ARGUMENT, "layer_norm backward: dropout needs the dx-sum form and dx_masked");
+  }
   if (dtype == MSDA_F32)
     return ln_dispatch<float>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps,
-                              residual, sum_out, dxsum, st);
+                              residual, sum_out, dxsum, rd, dx_masked, st);
   if (dtype == MSDA_BF16)
     return ln_dispatch<__nv_bfloat16>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C,
-                                      eps, residual, sum_out, dxsum, st);
+                                      eps, residual, sum_out, dxsum, rd, dx_masked, st);
   return ln_dispatch<__half>(bwd, x, dy, gamma, beta, y, mean, rstd, dx, partial, dgamma_dbeta, rows, C, eps,
-                             residual, sum_out, dxsum, st);
+                             residual, sum_out, dxsum, rd, dx_masked, st);
+}
+
+// ---- ReLU + dropout in place (the FFN's first activation), and the mask itself (test hook) ----
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(256)
+relu_dropout_kernel(T* __restrict__ x, unsigned char* __restrict__ mask_out, long long n, const DropArgs drop) {
+  constexpr int VEC = Vec16<T>::N;
+  const unsigned long long seed = drop.key_src[0], step = drop.key_src[1];
+  if (drop.key_save != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    drop.key_save[0] = seed;
+    drop.key_save[1] = step;
+  }
+  const long long chunks = n / VEC, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += stride) {
+    const uint32_t keep = drop_keep<VEC>((unsigned long long)i * VEC, seed, step, drop);
+    if (mask_out != nullptr) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) mask_out[i * VEC + k] = (unsigned char)((keep >> k) & 1u);
+    } else {
+      float t[VEC];
+      Vec16<T>::unpack(*reinterpret_cast<const uint4*>(x + i * VEC), t);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float v = RELU ? fmaxf(t[k], 0.f) : t[k];
+        t[k] = ((keep >> k) & 1u) ? v * drop.scale : 0.f;
+      }
+      *reinterpret_cast<uint4*>(x + i * VEC) = Vec16<T>::pack(t);
+    }
+  }
+}
+
+int launch_relu_dropout(void* x, void* mask_out, long long n, int dtype, const RowDropout& rd, cudaStream_t st) {
+  if (!(rd.p > 0.f && rd.p < 1.f) || rd.key == nullptr)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "relu_dropout: needs 0 < p < 1 and a key");
+  const int vec = dtype == MSDA_F32 ? 4 : 8;
+  if (n % 8 != 0) return set_error(MSDA_ERR_UNSUPPORTED, "relu_dropout: the element count must be a multiple of 8");
+  DropArgs da{};
+  da.key_src = static_cast<const unsigned long long*>(rd.key);
+  da.key_save = static_cast<unsigned long long*>(rd.key_save);
+  da.site = rd.site;
+  da.thresh = (uint32_t)(rd.p * 65536.f + 0.5f);
+  da.scale = 1.f / (1.f - rd.p);
+  const long long chunks = n / vec;
+  if (chunks == 0) return MSDA_OK;
+  long long grid = (chunks + 255) / 256;
+  if (grid > (long long)row_grid() * 4) grid = (long long)row_grid() * 4;
+  unsigned char* mo = static_cast<unsigned char*>(mask_out);
+  if (dtype == MSDA_F32) relu_dropout_kernel<float, true><<<(unsigned)grid, 256, 0, st>>>(static_cast<float*>(x), mo, n, da);
+  else if (dtype == MSDA_BF16) relu_dropout_kernel<__nv_bfloat16, true><<<(unsigned)grid, 256, 0, st>>>(static_cast<__nv_bfloat16*>(x), mo, n, da);
+  else relu_dropout_kernel<__half, true><<<(unsigned)grid, 256, 0, st>>>(static_cast<__half*>(x), mo, n, da);
+  count_launch();
+  return check_launch("relu_dropout");
 }
 
 template <typename T, bool RELU>
 static int colsum_out(const void* x, const void* y, void* dx, void* out, float* ws, long long rows, int C,
-                      int out_dtype, int grid, size_t smem, cudaStream_t st) {
+                      int out_dtype, int grid, size_t smem, float relu_scale, cudaStream_t st) {
   const T* xi = static_cast<const T*>(x);
   const T* yi = static_cast<const T*>(y);
   T* di = static_cast<T*>(dx);
-  if (out_dtype == MSDA_F32) colsum_kernel<T, float, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<float*>(out), rows, C);
-  else if (out_dtype == MSDA_BF16) colsum_kernel<T, __nv_bfloat16, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__nv_bfloat16*>(out), rows, C);
-  else colsum_kernel<T, __half, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__half*>(out), rows, C);
+  if (out_dtype == MSDA_F32) colsum_kernel<T, float, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<float*>(out), rows, C, relu_scale);
+  else if (out_dtype == MSDA_BF16) colsum_kernel<T, __nv_bfloat16, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__nv_bfloat16*>(out), rows, C, relu_scale);
+  else colsum_kernel<T, __half, RELU><<<grid, kRowThreads, smem, st>>>(xi, yi, di, ws, static_cast<__half*>(out), rows, C, relu_scale);
   count_launch();
   return check_launch(RELU ? "relu_bwd_colsum" : "colsum");
 }
 
 // y == nullptr: plain column sums of x.  Otherwise dx = relu'(y) * x is written and summed.
 int launch_colsum(const void* x, const void* y, void* dx, void* out, float* partial, long long rows, int C,
-                  int dtype, int out_dtype, cudaStream_t st) {
+                  int dtype, int out_dtype, float relu_scale, cudaStream_t st) {
   const int vec = dtype == MSDA_F32 ? 4 : 8;
   if (C % vec != 0 || C / vec > kRowThreads)
     return set_error(MSDA_ERR_UNSUPPORTED, "colsum: C=%d must be a multiple of %d and <= %d", C, vec, vec * kRowThreads);
@@ -589,8 +742,8 @@ int launch_colsum(const void* x, const void* y, void* dx, void* out, float* part
   const int grid = (int)(need < row_grid() ? (need > 0 ? need : 1) : row_grid());
   const size_t smem = (size_t)row_lanes * C * sizeof(float);
   const bool relu = y != nullptr;
-#define COLSUM_CASE(T) (relu ? colsum_out<T, true>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, st) \
-                             : colsum_out<T, false>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, st))
+#define COLSUM_CASE(T) (relu ? colsum_out<T, true>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, relu_scale, st) \
+                             : colsum_out<T, false>(x, y, dx, out, partial, rows, C, out_dtype, grid, smem, 1.f, st))
   if (dtype == MSDA_F32) return COLSUM_CASE(float);
   if (dtype == MSDA_BF16) return COLSUM_CASE(__nv_bfloat16);
   return COLSUM_CASE(__half);

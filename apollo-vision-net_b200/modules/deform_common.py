@@ -89,13 +89,15 @@ class DeformAttnBase(BaseModule):
 def finish_block(mod, output, identity, post_norm=None):
     """Tail of an attention block: ``dropout(output_proj(output)) + identity`` (reference
     temporal_self_attention.py:285-289, spatial_cross_attention.py:171-173, decoder.py:353-358),
-    optionally followed by the layer's next LayerNorm (``post_norm``).  With the norm given and the
-    dropout inactive the projection, the residual add and the norm run as one fused autograd node
-    (:func:`rowops.linear_add_layernorm`); the result is then already normalised."""
+    optionally followed by the layer's next LayerNorm (``post_norm``).  With the norm given the
+    projection, the dropout (mask drawn in the kernel and recomputed in the backward), the residual add
+    and the norm run as one fused autograd node (:func:`rowops.linear_add_layernorm`); the result is then
+    already normalised."""
     batch_first = getattr(mod, 'batch_first', True)
     drop = mod.dropout
-    if post_norm is not None and batch_first and not (mod.training and drop.p > 0):
-        return linear_add_layernorm(output, mod.output_proj, identity, post_norm)
+    if post_norm is not None and batch_first:
+        return linear_add_layernorm(output, mod.output_proj, identity, post_norm,
+                                    p=drop.p if mod.training else 0.0)
     output = mod.output_proj(output)
     if not batch_first:
         output = output.permute(1, 0, 2)

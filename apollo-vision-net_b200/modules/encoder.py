@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..fused_ops import BevGeometry, bev_point_sampling
-from ..rowops import LayerNorm, Linear, ReLU, linear_add_layernorm
+from ..rowops import LayerNorm, Linear, ReLU, advance_dropout_step, linear_add_layernorm
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
                         build_transformer_layer)
 
@@ -57,13 +57,18 @@ class FFN(BaseModule):
         self.add_identity = add_identity
 
     def forward(self, x, identity=None, post_norm=None):
-        """``post_norm``: the layer's next LayerNorm; with it, two fcs and inactive dropout the last
-        Linear, the identity add and the norm run as one fused node (result already normalised)."""
+        """``post_norm``: the layer's next LayerNorm; with it and two fcs the last Linear, its dropout,
+        the identity add and the norm run as one fused node (result already normalised), and the first
+        activation's dropout is fused into the ReLU pass."""
         res = x if identity is None else identity
         last_drop = self.layers[-1]
-        if (post_norm is not None and self.add_identity and len(self.layers) == 3 and
-                not (self.training and last_drop.p > 0)):
-            return linear_add_layernorm(self.layers[0](x), self.layers[1], res, post_norm)
+        if post_norm is not None and self.add_identity and len(self.layers) == 3:
+            fc1, act, drop1 = self.layers[0]
+            p1 = drop1.p if self.training else 0.0
+            h = fc1(x)
+            h = act.forward_dropout(h, p1) if hasattr(act, 'forward_dropout') else drop1(act(h))
+            return linear_add_layernorm(h, self.layers[1], res, post_norm,
+                                        p=last_drop.p if self.training else 0.0)
         out = self.layers(x)
         if self.add_identity:
             out = res + out
@@ -259,6 +264,8 @@ class BEVFormerEncoder(BaseModule):
         intermediate = []
         bs = bev_query.size(1)
         dev, dt = bev_query.device, bev_query.dtype
+        if self.training and torch.is_grad_enabled() and bev_query.is_cuda:
+            advance_dropout_step(dev)          # new dropout masks for this step (device-side counter)
         ck = (bev_h, bev_w, bs, str(dev), self.num_points_in_pillar)
         if ck not in self._ref_cache:
             self._ref_cache = {ck: (

@@ -168,6 +168,9 @@ class MapTRv2Decoder(BaseModule):
                 key_padding_mask=None, **kwargs):
         """query (Nq, bs, C); reference_points (bs, Nq, 2) in [0, 1]; value=(HW, bs, C) in kwargs."""
         output = query
+        if self.training and torch.is_grad_enabled() and query.is_cuda:
+            from ..rowops import advance_dropout_step
+            advance_dropout_step(query.device)     # fresh masks for the fused dropouts of this step
         intermediate, intermediate_refs = [], []
         projected = hoisted_projections(self.layers, args, kwargs) if self.hoist_value_proj else None
         for lid, layer in enumerate(self.layers):

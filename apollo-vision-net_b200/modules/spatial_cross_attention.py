@@ -153,7 +153,8 @@ class SpatialCrossAttention(BaseModule):
                                                reference_points_cam, mask_u8, hit_bits,
                                                self.num_cams, self._grid_w(bev_h, bev_w, num_query), lists)
         # (the residual is added without a permute whatever batch_first says, reference :171-173)
-        if post_norm is not None and not (self.training and self.dropout.p > 0):
-            return linear_add_layernorm(slots.to(query.dtype), self.output_proj, inp_residual, post_norm)
+        if post_norm is not None:
+            return linear_add_layernorm(slots.to(query.dtype), self.output_proj, inp_residual, post_norm,
+                                        p=self.dropout.p if self.training else 0.0)
         out = self.dropout(self.output_proj(slots.to(query.dtype))) + inp_residual
         return out if post_norm is None else post_norm(out)

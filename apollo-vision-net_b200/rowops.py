@@ -36,6 +36,51 @@ def _workspace(device, floats):
 
 _LN_WIDTHS = (128, 256, 512, 1024)
 
+# ---- dropout state (masks are counter-based and recomputed in the backward, see msda_b200.h) -------
+_drop_state = {}
+_drop_site = [0]
+
+
+def dropout_state(device):
+    """uint64 pair (seed, step) on ``device`` (stored as int64); the seed is drawn from torch's CPU
+    generator at first use, so ``torch.manual_seed`` makes runs repeatable."""
+    st = _drop_state.get(device.index)
+    if st is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        st = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        _drop_state[device.index] = st
+    return st
+
+
+def advance_dropout_step(device):
+    """New masks for the next training step: increments the step counter ON THE DEVICE (a captured CUDA
+    graph replays the increment, so every replay draws fresh masks).  Called by the encoder / decoders at
+    the start of a training forward."""
+    dropout_state(device)[1:].add_(1)
+
+
+def reseed_dropout(device, seed):
+    st = dropout_state(device)
+    st.copy_(torch.tensor([int(seed), 0], dtype=torch.int64))
+
+
+def _next_site():
+    _drop_site[0] = (_drop_site[0] + 1) & 0x7fffffff
+    return _drop_site[0]
+
+
+def dropout_keep_mask(shape, dtype, key, site, p, device):
+    """The keep mask the fused kernels use for a tensor of ``shape`` / ``dtype`` under (key, site, p), as a
+    bool tensor (tests)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    m = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _lib.call('dropout_keep_mask', m.data_ptr(), n, _DTYPE_CODE[dtype], key.data_ptr(), int(site), float(p),
+                  torch.cuda.current_stream(device).cuda_stream)
+    return m.view(*shape).bool()
+
 
 def _ln_supported(x, weight, bias):
     if not x.is_cuda or weight is None or bias is None or x.dtype not in _DTYPE_CODE:
@@ -101,7 +146,8 @@ class LinearAddLayerNormFunction(Function):
 
     @staticmethod
     @custom_fwd(cast_inputs=None)
-    def forward(ctx, x, weight, bias, residual, gamma, beta, eps):
+    def forward(ctx, x, weight, bias, residual, gamma, beta, eps, p=0.0):
+        """``p`` > 0: y = LayerNorm(dropout(x W^T + b) + residual) with the mask drawn in the kernel."""
         C = weight.shape[0]
         x2 = x.reshape(-1, x.shape[-1])
         rows = x2.shape[0]
@@ -112,11 +158,20 @@ class LinearAddLayerNormFunction(Function):
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         g, b = gamma.contiguous(), beta.contiguous()
+        ctx.p, ctx.site, key = float(p), 0, None
         with torch.cuda.device(x.device):
-            _lib.call('ln_residual_fwd', lin.data_ptr(), res2.data_ptr(), g.data_ptr(), b.data_ptr(),
-                      lin.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
-                      float(eps), _DTYPE_CODE[x.dtype], _stream_ptr(x))
-        ctx.save_for_backward(x2, weight, lin, g, mean, rstd)
+            if p > 0:
+                ctx.site = _next_site()
+                key = torch.empty(2, dtype=torch.int64, device=x.device)
+                _lib.call('ln_residual_dropout_fwd', lin.data_ptr(), res2.data_ptr(), g.data_ptr(), b.data_ptr(),
+                          lin.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
+                          float(eps), _DTYPE_CODE[x.dtype], dropout_state(x.device).data_ptr(), key.data_ptr(),
+                          ctx.site, float(p), _stream_ptr(x))
+            else:
+                _lib.call('ln_residual_fwd', lin.data_ptr(), res2.data_ptr(), g.data_ptr(), b.data_ptr(),
+                          lin.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
+                          float(eps), _DTYPE_CODE[x.dtype], _stream_ptr(x))
+        ctx.save_for_backward(x2, weight, lin, g, mean, rstd, *([key] if key is not None else []))
         ctx.shapes = (x.shape, residual.shape)
         return y.view(residual.shape)
 
@@ -124,27 +179,35 @@ class LinearAddLayerNormFunction(Function):
     @once_differentiable
     @custom_bwd
     def backward(ctx, dy):
-        x2, weight, s, g, mean, rstd = ctx.saved_tensors
+        x2, weight, s, g, mean, rstd, *key = ctx.saved_tensors
         rows, C = s.shape
         dy2 = dy.reshape(rows, C).to(s.dtype).contiguous()
         ds = torch.empty_like(s)
         out3 = torch.empty((3, C), dtype=s.dtype, device=s.device)
         nrows = _lib.lib().rowops_workspace_rows()
         ws = _workspace(s.device, nrows * 3 * C)
+        dlin = ds                          # gradient of the Linear output (= d sum without dropout)
         with torch.cuda.device(s.device):
-            _lib.call('ln_bwd_dxsum', s.data_ptr(), dy2.data_ptr(), g.data_ptr(), mean.data_ptr(),
-                      rstd.data_ptr(), ds.data_ptr(), out3.data_ptr(), ws.data_ptr(), rows, C,
-                      _DTYPE_CODE[s.dtype], _stream_ptr(s))
+            if ctx.p > 0:
+                dlin = torch.empty_like(s)
+                _lib.call('ln_bwd_dxsum_dropout', s.data_ptr(), dy2.data_ptr(), g.data_ptr(), mean.data_ptr(),
+                          rstd.data_ptr(), ds.data_ptr(), dlin.data_ptr(), out3.data_ptr(), ws.data_ptr(), rows,
+                          C, _DTYPE_CODE[s.dtype], key[0].data_ptr(), ctx.site, ctx.p, _stream_ptr(s))
+            else:
+                _lib.call('ln_bwd_dxsum', s.data_ptr(), dy2.data_ptr(), g.data_ptr(), mean.data_ptr(),
+                          rstd.data_ptr(), ds.data_ptr(), out3.data_ptr(), ws.data_ptr(), rows, C,
+                          _DTYPE_CODE[s.dtype], _stream_ptr(s))
         x_shape, res_shape = ctx.shapes
-        dx = (ds @ weight).view(x_shape) if ctx.needs_input_grad[0] else None
-        dw = weight_bias_grad(ds, x2, weight, want_bias=False)[0] if ctx.needs_input_grad[1] else None
-        return dx, dw, out3[2], ds.view(res_shape), out3[0], out3[1], None
+        dx = (dlin @ weight).view(x_shape) if ctx.needs_input_grad[0] else None
+        dw = weight_bias_grad(dlin, x2, weight, want_bias=False)[0] if ctx.needs_input_grad[1] else None
+        return dx, dw, out3[2], ds.view(res_shape), out3[0], out3[1], None, None
 
 
-def linear_add_layernorm(x, linear_mod, residual, norm):
-    """``norm(linear_mod(x) + residual)`` through :class:`LinearAddLayerNormFunction` when the
-    tensors qualify (CUDA, one dtype, supported width, affine LayerNorm over the last dim with a
-    bias-carrying Linear); the plain composition otherwise."""
+def linear_add_layernorm(x, linear_mod, residual, norm, p=0.0):
+    """``norm(dropout_p(linear_mod(x)) + residual)`` through :class:`LinearAddLayerNormFunction` when
+    the tensors qualify (CUDA, one dtype, supported width, affine LayerNorm over the last dim with a
+    bias-carrying Linear); the plain composition otherwise.  ``p``: dropout probability of the training
+    step (0 = none)."""
     w, b = linear_mod.weight, linear_mod.bias
     ok = (isinstance(norm, nn.LayerNorm) and len(norm.normalized_shape) == 1 and b is not None and
           x.is_cuda and x.dtype == w.dtype == residual.dtype and
@@ -152,8 +215,9 @@ def linear_add_layernorm(x, linear_mod, residual, norm):
           norm.weight is not None and norm.bias is not None and
           _ln_supported(residual, norm.weight, norm.bias))
     if not ok:
-        return norm(linear_mod(x) + residual)
-    return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps)
+        out = linear_mod(x)
+        return norm((F.dropout(out, p, True) if p > 0 else out) + residual)
+    return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps, float(p))
 
 
 # ---- bias gradients that a producer kernel already has -----------------------------------------
@@ -192,8 +256,17 @@ class ReLUFunction(Function):
     layer in front of it (offered to that layer's backward through :func:`offer_bias_grad`)."""
 
     @staticmethod
-    def forward(ctx, x):
-        y = torch.relu_(x)
+    def forward(ctx, x, p=0.0):
+        """``p`` > 0: dropout(relu(x)) in one in-place pass (the FFN's Linear-ReLU-Dropout)."""
+        ctx.scale = 1.0
+        if p > 0:
+            with torch.cuda.device(x.device):
+                _lib.call('relu_dropout_fwd', x.data_ptr(), x.numel(), _DTYPE_CODE[x.dtype],
+                          dropout_state(x.device).data_ptr(), None, _next_site(), float(p), _stream_ptr(x))
+            ctx.scale = 1.0 / (1.0 - float(p))
+            y = x
+        else:
+            y = torch.relu_(x)
         ctx.mark_dirty(x)
         ctx.save_for_backward(y)
         return y
@@ -211,21 +284,30 @@ class ReLUFunction(Function):
         with torch.cuda.device(y.device):
             _lib.call('relu_bwd_colsum', dy2.data_ptr(), y2.data_ptr(), dx.data_ptr(), sums.data_ptr(),
                       ws.data_ptr(), dy2.shape[0], C, _DTYPE_CODE[y.dtype], _DTYPE_CODE[y.dtype],
-                      _stream_ptr(y))
+                      float(ctx.scale), _stream_ptr(y))
         dx = dx.view(y.shape)
         offer_bias_grad(dx, sums)
-        return dx
+        return dx, None
 
 
 class ReLU(nn.ReLU):
     """``nn.ReLU(inplace=True)`` after a Linear layer: same forward; on CUDA the backward is one kernel
     that also yields that Linear's bias gradient."""
 
+    def fused_ok(self, x):
+        return (self.inplace and x.is_cuda and x.requires_grad and torch.is_grad_enabled() and x.is_contiguous()
+                and x.dim() >= 2 and _colsum_supported(x.reshape(-1, x.shape[-1])))
+
     def forward(self, x):
-        if (self.inplace and x.is_cuda and x.requires_grad and torch.is_grad_enabled() and x.is_contiguous()
-                and x.dim() >= 2 and _colsum_supported(x.reshape(-1, x.shape[-1]))):
-            return ReLUFunction.apply(x)
+        if self.fused_ok(x):
+            return ReLUFunction.apply(x, 0.0)
         return super().forward(x)
+
+    def forward_dropout(self, x, p):
+        """dropout_p(relu(x)) -- one in-place kernel when the tensor qualifies."""
+        if p > 0 and self.fused_ok(x) and x.numel() % 8 == 0:
+            return ReLUFunction.apply(x, float(p))
+        return F.dropout(self.forward(x), p, True) if p > 0 else self.forward(x)
 
 
 def _wgrad_supported(dy2, x2, weight, want_bias=True):

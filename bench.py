@@ -49,18 +49,21 @@ def measured_peak():
 
 
 # --------------------------------------------------------------------------- workload ------
-def encoder_cfg(num_layers, num_levels, pc_range):
+def encoder_cfg(num_layers, num_levels, pc_range, dropout=0.1):
+    """The reference's training values: dropout 0.1 in TSA / SCA (temporal_self_attention.py:54-66,
+    spatial_cross_attention.py:43-61) and ffn_dropout 0.1 (bev_base_occ.py:127)."""
     return dict(
         type='BEVFormerEncoder', num_layers=num_layers, pc_range=pc_range,
         num_points_in_pillar=PILLAR, return_intermediate=False,
         transformerlayers=dict(
             type='BEVFormerLayer',
             attn_cfgs=[
-                dict(type='TemporalSelfAttention', embed_dims=C, num_points=TSA_POINTS, num_levels=1),
-                dict(type='SpatialCrossAttention', pc_range=pc_range, embed_dims=C,
+                dict(type='TemporalSelfAttention', embed_dims=C, num_points=TSA_POINTS, num_levels=1,
+                     dropout=dropout),
+                dict(type='SpatialCrossAttention', pc_range=pc_range, embed_dims=C, dropout=dropout,
                      deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
                                                num_points=SCA_POINTS, num_levels=num_levels))],
-            feedforward_channels=FFN_DIM, ffn_dropout=0.1,
+            feedforward_channels=FFN_DIM, ffn_dropout=dropout,
             operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm')))
 
 
@@ -164,12 +167,9 @@ def run_b200(args):
     dtype = torch.bfloat16
     bev_h = bev_w = args.bev
     levels = syn.LEVELS_BASE
-    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE))
+    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE, args.dropout))
     randomize(enc, 0)
-    enc.to(dev).to(dtype).train()
-    for m in enc.modules():                       # dropout off: deterministic, parity-checked config
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
+    enc.to(dev).to(dtype).train()                 # training mode: the reference's dropouts are active
     params = [p for p in enc.parameters() if p.requires_grad]
     l2i, img_shape = syn.camera_rig(1.0, bs=1)
     l2i_dev = torch.as_tensor(l2i).to(dev)
@@ -374,8 +374,8 @@ def run_b200(args):
     pipe['left'] = args.steps                      # ... and issues exactly `steps` H2D copies
     ms_e2e = timed(step_e2e, args.steps)
     # the loss the host read back from the last e2e step must be the loss the device computed
-    # (every step sees the same frame, so the device-timed steps produced the same number)
-    loss_dev = float(step_device()[1].detach().float().item())
+    # (with dropout every step draws new masks: compare with the device's copy of that same step's loss)
+    loss_dev = float(back['loss'].float().item()) if back['loss'] is not None else float('nan')
     loss_read = back['value']
     read_ok = loss_read is not None and abs(loss_read - loss_dev) <= 1e-3 * abs(loss_dev) + 1e-30
     if not read_ok:
@@ -447,6 +447,10 @@ def run_b200(args):
                 'l2': 'flushed every step (192 MiB write inside the timed region); the step\'s '
                       'working set (> 1 GB of activations) also exceeds the 126 MB L2',
                 'weights': 'random-init (reference init + N(0,0.02) offset/weight Linears)',
+                'dropout': args.dropout,
+                'dropout_note': 'training mode, the reference\'s dropout values (TSA / SCA 0.1, FFN 0.1 twice); masks '
+                                'are drawn inside the fused row kernels and recomputed in the backward; the step counter '
+                                'advances on the device, so every graph replay draws new masks',
                 'cuda_graph': graph is not None,
                 'cuda_graph_error': static_out.get('error'),
                 'eager_ms_per_step': ms_eager / args.steps,
@@ -666,6 +670,9 @@ def main():
     ap.add_argument('--shard-sim', type=int, default=0,
                     help='rowshard on ONE GPU: run rank 0 of this many row shards, no collective '
                          '(profiling aid: what one rank of an N-way run executes)')
+    ap.add_argument('--dropout', type=float, default=0.1,
+                    help="dropout of TSA / SCA / FFN (reference training value 0.1; 0 = the parity-checked "
+                         "deterministic configuration)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 4
+#define MSDA_ABI_VERSION 5
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -297,7 +297,42 @@ int colsum(const void* x, void* out, float* partial, int64_t rows, int C, int dt
  * forward output y, and colsum_out (C,) = column sums of dx; one pass instead of two.  dx must not
  * alias dy or y.                                                                                   */
 int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, float* partial,
-                    int64_t rows, int C, int dtype, int out_dtype, void* stream);
+                    int64_t rows, int C, int dtype, int out_dtype, float scale, void* stream);
+/*   scale: factor on the surviving entries -- 1, or 1 / (1 - p) when y came from relu_dropout_fwd (y is
+ *   zero where the unit was dropped, so y > 0 selects exactly the kept, active entries).           */
+
+/* ---------------------------------------------------------------------------------
+ * Dropout of the training configuration, fused into the row kernels.  The reference trains with
+ * dropout 0.1 after the output projections of TemporalSelfAttention / SpatialCrossAttention
+ * (temporal_self_attention.py:285-289, spatial_cross_attention.py:171-173) and ffn_drop 0.1 after the
+ * FFN's activation and after its last Linear (mmcv FFN; bev_base_occ.py:127).  Masks are counter-based
+ * (Philox4x32-10 over (element / 8, call site, step), keyed by a seed; 16 random bits per element) and
+ * are RECOMPUTED in the backward: no mask tensor exists.
+ *   rng_state  uint64[2] on the device: (seed, step); the caller advances `step` on the device once
+ *              per training step (so a replayed CUDA graph draws new masks)
+ *   key_save   uint64[2] on the device: the forward stores the (seed, step) it used; the matching
+ *              backward call takes it as `key`
+ *   site       distinguishes the dropout instances of one step;  p in (0, 1)
+ *   ln_residual_dropout_fwd: s = (dtype)(dropout(x) + residual), normalised (ln_residual_fwd with the
+ *              dropout of the block's last Linear output)
+ *   ln_bwd_dxsum_dropout: dx = d s (the residual's gradient) and dx_masked = d x = mask * d s / (1 - p)
+ *              (the Linear output's gradient); the third output row holds the column sums of dx_masked
+ *   relu_dropout_fwd: x <- dropout(relu(x)) in place (the FFN's Linear-ReLU-Dropout); n % 8 == 0
+ *   dropout_keep_mask: the keep mask itself as bytes, for tests (the i-th byte belongs to element i of
+ *              a tensor of the given dtype processed under (key, site, p))
+ * ------------------------------------------------------------------------------- */
+int ln_residual_dropout_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
+                            void* sum_out, void* y, float* mean, float* rstd, int64_t rows, int C, float eps,
+                            int dtype, const void* rng_state, void* key_save, uint32_t site, float p,
+                            void* stream);
+int ln_bwd_dxsum_dropout(const void* x, const void* dy, const void* gamma, const float* mean,
+                         const float* rstd, void* dx, void* dx_masked, void* dgamma_dbeta_dxsum,
+                         float* partial, int64_t rows, int C, int dtype, const void* key, uint32_t site,
+                         float p, void* stream);
+int relu_dropout_fwd(void* x, int64_t n, int dtype, const void* rng_state, void* key_save, uint32_t site,
+                     float p, void* stream);
+int dropout_keep_mask(uint8_t* mask, int64_t n, int dtype, const void* key, uint32_t site, float p,
+                      void* stream);
 
 /* Number of kernel launches this library has enqueued since load (all entry points);
  * bench.py reports the delta over its timed region as "gpu_launches". */
