@@ -173,33 +173,48 @@ def run_b200(args):
     params = [p for p in enc.parameters() if p.requires_grad]
     l2i, img_shape = syn.camera_rig(1.0, bs=1)
     l2i_dev = torch.as_tensor(l2i).to(dev)
+    # Batch-level data parallelism as DDP does it (bevformer/apis/mmdet_train.py:71-85): bucketed
+    # all-reduce of the parameter gradients launched from autograd hooks while the backward is still
+    # running; inside the captured step the NCCL launches are nodes of the CUDA graph.
+    from apollo_vision_net_b200.parallel import BucketedGradReducer
+    reducer = BucketedGradReducer(params, bucket_bytes=args.bucket_mb << 20) if world > 1 else None
+    ddp = {'mode': 'single GPU' if world == 1 else
+           f'bucketed all-reduce overlapped with the backward ({len(reducer.buckets)} buckets of '
+           f'~{args.bucket_mb} MiB, averaged gradients left in p.grad)'}
 
     host = host_inputs(bev_h, bev_w, levels, seed=1 + rank, dtype=dtype, pin=True)
     devin = {k: v.to(dev) for k, v in host.items()}
     shapes, starts = devin['shapes'], devin['starts']
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    use_reducer = [reducer is not None]
+
     def encoder_step(feat, bev_query, bev_pos, prev_bev, grad_w, shift):
         for p in params:
             p.grad = None
+        if reducer is not None:
+            reducer.reset()
+            reducer.enabled = use_reducer[0]
         feat.requires_grad_(True)
         out = enc(bev_query, feat, feat, bev_h=bev_h, bev_w=bev_w, bev_pos=bev_pos,
                   spatial_shapes=shapes, level_start_index=starts, prev_bev=prev_bev, shift=shift,
                   lidar2img=l2i_dev, img_shape=img_shape)
         loss = (out.float() * grad_w.float()).sum() * (1.0 / out.numel())
         loss.backward()
+        if reducer is not None and use_reducer[0]:
+            reducer.finish()
         return out, loss
 
-    def sync_grads():
-        if world > 1:                              # batch-level data parallelism: all-reduce of the
-            flat = torch.cat([p.grad.reshape(-1) for p in params])   # parameter gradients (NCCL)
+    def flat_allreduce():                          # fallback when NCCL cannot be captured into the graph
+        if world > 1 and not use_reducer[0]:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
             dist.all_reduce(flat)
 
     def step_eager():
         flush.zero_()                              # L2 flushed between iterations (inside the timed region)
         r = encoder_step(devin['feat'].detach(), devin['bev_query'], devin['bev_pos'],
                          devin['prev_bev'], devin['grad_w'], devin['shift'])
-        sync_grads()
+        flat_allreduce()
         return r
 
     def barrier():
@@ -237,9 +252,10 @@ def run_b200(args):
 
     # The encoder never synchronises with the host (no nonzero(), no max_len), so the whole
     # forward + backward step is captured once into a CUDA graph and replayed: the 540 launches
-    # of a step cost one graph launch on the host.  The parameter all-reduce stays outside.
+    # of a step cost one graph launch on the host.  At N > 1 the bucketed gradient all-reduces are
+    # captured with it (NCCL launches as graph nodes on a parallel branch).
     graph, static_out = None, {}
-    if not args.no_graph:
+    for attempt in range(2 if (world > 1 and not args.no_graph) else (0 if args.no_graph else 1)):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -251,26 +267,36 @@ def run_b200(args):
             for p in params:
                 p.grad = None
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # (thread-local capture mode: NCCL's watchdog thread may touch the device meanwhile)
+            with torch.cuda.graph(graph, capture_error_mode='thread_local' if world > 1 else 'global'):
                 o, l = encoder_step(devin['feat'].detach(), devin['bev_query'], devin['bev_pos'],
                                     devin['prev_bev'], devin['grad_w'], devin['shift'])
                 static_out['out'], static_out['loss'] = o.detach(), l.detach()
             torch.cuda.synchronize()
+            break
         except Exception as exc:                   # pragma: no cover - reported in the JSON line
             graph = None
             static_out['error'] = f'{type(exc).__name__}: {exc}'[:200]
             torch.cuda.synchronize()
+            if world > 1 and use_reducer[0]:       # second attempt: collectives outside the graph
+                use_reducer[0] = False
+                ddp['mode'] = ('flat all-reduce after the graph replay (capturing the bucketed NCCL launches '
+                               'failed: ' + static_out['error'][:80] + ')')
 
     def step_device():
         if graph is None:
             return step_eager()
         flush.zero_()
         graph.replay()
-        sync_grads()
+        flat_allreduce()
         return static_out['out'], static_out['loss']
 
     out_host = torch.empty((1, bev_h * bev_w, C), dtype=dtype).pin_memory()
-    h2d_keys = ('feat', 'bev_query', 'bev_pos', 'prev_bev', 'grad_w', 'shift')
+    # Per-frame inputs travel from the host: the six cameras' feature maps and the ego-motion shift.
+    # bev_query / bev_pos are parameters (bev_embedding, positional encoding), prev_bev is the previous
+    # frame's output and grad_w stands for the decoders' upstream gradient: all live on the device in
+    # the real model (dense_heads/bevformer_head.py:129-225) and stay resident here.
+    h2d_keys = ('feat', 'shift')
 
     # End-to-end pipeline: the frame's inputs travel from pinned host memory over PCIe on a copy
     # stream into a staging set of device buffers while the previous frame computes; the compute
@@ -310,7 +336,7 @@ def run_b200(args):
             pipe['primed'] = True
         main.wait_event(staged)
         if graph is None:
-            d = {k: staging[k].clone() for k in h2d_keys}
+            d = dict(devin, **{k: staging[k].clone() for k in h2d_keys})
         else:
             for k in h2d_keys:
                 devin[k].copy_(staging[k], non_blocking=True)
@@ -327,7 +353,7 @@ def run_b200(args):
         else:
             graph.replay()
             out, loss = static_out['out'], static_out['loss']
-        sync_grads()
+        flat_allreduce()
         # D2H of the step's results on its own stream, one step behind the compute: the BEV output
         # and the loss are first moved (device-to-device) into staging buffers, so the next replay
         # may overwrite the graph's static outputs while PCIe is still carrying these; the host
@@ -432,6 +458,23 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_reference_sample(steps=6, warmup=1)     # about 12 s of CPU work on the box
 
+    extras = {}
+    if world > 1 and not args.no_extras:
+        # the north_star's own partition (BASELINE configs[4]) and the det+map stand-in (configs[2]) ride on the
+        # same line as extra keys; the headline metric above is untouched
+        graph_ok = graph is not None
+        del graph
+        graph = True if graph_ok else None
+        torch.cuda.empty_cache()
+        for name, fn in (('rowshard', lambda: measure_rowshard(args, rank, world, dev, max(5, args.steps // 2), 3,
+                                                                bev=400, train_steps=3)),
+                         ('detmap', lambda: measure_detmap(args, rank, world, dev, max(5, args.steps // 2), 3))):
+            try:
+                extras[name] = fn()
+            except Exception as exc:               # pragma: no cover - reported in the JSON line
+                extras[name] = {'error': f'{type(exc).__name__}: {exc}'[:300]}
+                torch.cuda.synchronize()
+            torch.cuda.empty_cache()
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -444,6 +487,7 @@ def run_b200(args):
                 'points_per_step': points_per_step, 'sca_points_per_layer': sca_points,
                 'tsa_points_per_layer': tsa_points, 'camera_query_pairs': pairs,
                 'parallelism': f'dp{world}' if world > 1 else 'single',
+                'ddp': ddp['mode'],
                 'l2': 'flushed every step (192 MiB write inside the timed region); the step\'s '
                       'working set (> 1 GB of activations) also exceeds the 126 MB L2',
                 'weights': 'random-init (reference init + N(0,0.02) offset/weight Linears)',
@@ -458,6 +502,8 @@ def run_b200(args):
             'frames_per_s': world * args.steps / (ms / 1e3),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps,
+                    'h2d': 'per frame: 6-camera feature maps + ego-motion shift; device-resident: bev_query / '
+                           'bev_pos (parameters), prev_bev (previous output), upstream gradient',
                     'loss_read_back': loss_read, 'loss_read_back_matches_device': read_ok},
             'gpu_launches': launches,
             'kernels': kernels,
@@ -465,23 +511,185 @@ def run_b200(args):
             'cpu_baseline': cpu_baseline,
             'clocks': clocks.summary(),
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------ BEV row sharding ------
-def run_rowshard(args):
-    """BASELINE configs[4]: encoder FORWARD at a 400x400 BEV with the BEV query rows sharded over the
-    ranks (value maps replicated, one NCCL all-gather of the rows at encoder exit).  Strong
-    scaling: the frame is fixed, N ranks split its rows.  Not the contract line (that is the
-    default workload); run it with --workload rowshard."""
+def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps=0):
+    """BASELINE configs[4]: the encoder at a 400x400 BEV with the query rows sharded over the ranks.
+
+    Per frame and rank, inside the timed region: H2D of this rank's 1/N slice of the six cameras'
+    feature maps (pinned host memory), ONE NCCL all-gather that gives every rank the full maps over
+    NVLink (the "value features broadcast once per frame": no rank pulls more than 1/N of the frame over
+    PCIe), the shard's forward (a replayed CUDA graph), ONE all-gather of the BEV rows.  Also measured:
+    the same frame on one rank alone (unsharded, the strong-scaling reference) and, with
+    ``train_steps``, forward + backward with the gradients of the replicated tensors and of the
+    parameters summed over the row group (parallel.sharded_encoder_forward / allreduce_gradients)."""
     import torch.distributed as dist
     import apollo_vision_net_b200 as pkg
     import apollo_vision_net_b200.synthetic as syn
     from apollo_vision_net_b200 import _lib
-    from apollo_vision_net_b200.parallel import all_gather_bev_rows
+    from apollo_vision_net_b200.parallel import (all_gather_bev_rows, allreduce_gradients,
+                                                 sharded_encoder_forward)
+    dtype = torch.bfloat16
+    levels = syn.LEVELS_BASE
+    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE, 0.0))
+    randomize(enc, 0)
+    enc.to(dev).to(dtype).eval()
+    l2i, img_shape = syn.camera_rig(1.0, bs=1)
+    l2i_dev = torch.as_tensor(l2i).to(dev)
+    host = host_inputs(bev, bev, levels, seed=1, dtype=dtype, pin=False)   # the same frame on every rank
+    d = {k: v.to(dev) for k, v in host.items()}
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    shard = (rank, world) if world > 1 else ((0, args.shard_sim) if args.shard_sim > 1 else None)
+    # this rank's slice of the frame's features on the host (flat split: 6 cameras / N ranks)
+    feat_flat = d['feat'].view(-1)
+    n_feat = feat_flat.numel()
+    chunk = (n_feat + world - 1) // world
+    pad = torch.zeros(chunk * world, dtype=dtype)
+    pad[:n_feat] = host['feat'].view(-1)
+    my_host = pad[rank * chunk:(rank + 1) * chunk].clone().pin_memory()
+    my_dev = torch.empty(chunk, dtype=dtype, device=dev)
+    gathered = torch.empty(chunk * world, dtype=dtype, device=dev)
+    feat_static = d['feat']
 
+    def kwargs_of(feat):
+        return dict(bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'], spatial_shapes=d['shapes'],
+                    level_start_index=d['starts'], prev_bev=d['prev_bev'], shift=d['shift'],
+                    lidar2img=l2i_dev, img_shape=img_shape)
+
+    def shard_forward(row_shard):
+        with torch.no_grad():
+            return enc(d['bev_query'], feat_static, feat_static, row_shard=row_shard, **kwargs_of(feat_static))
+
+    def capture(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        torch.cuda.synchronize()
+        return g, out
+
+    graph, static_out, graph_error = None, None, None
+    if not args.no_graph:
+        try:
+            graph, static_out = capture(lambda: shard_forward(shard))
+        except Exception as exc:                   # pragma: no cover - reported in the JSON line
+            graph, graph_error = None, f'{type(exc).__name__}: {exc}'[:200]
+            torch.cuda.synchronize()
+
+    def distribute_frame():
+        if world == 1:
+            return
+        my_dev.copy_(my_host, non_blocking=True)                        # 1/N of the frame over PCIe
+        dist.all_gather_into_tensor(gathered, my_dev)                   # ... the rest over NVLink
+        feat_flat.copy_(gathered[:n_feat])                              # (into the graph's static input)
+
+    def step():
+        flush.zero_()
+        distribute_frame()
+        if graph is None:
+            out = shard_forward(shard)
+        else:
+            graph.replay()
+            out = static_out
+        if world > 1:
+            out = all_gather_bev_rows(out, bev, bev)
+        return out
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    for _ in range(max(warmup, 3)):
+        step()
+    n0 = _lib.launch_count()
+    if graph is not None:
+        shard_forward(shard)                       # our launches per frame, counted on an eager pass
+    launches = _lib.launch_count() - n0
+    ms_sharded = timed(step, steps)
+    res = {'bev': bev, 'ms_per_frame': ms_sharded, 'frames_per_s': 1e3 / ms_sharded,
+           'cuda_graph': graph is not None, 'cuda_graph_error': graph_error, 'launches_per_frame': launches,
+           'h2d_bytes_per_frame_per_rank': chunk * 2 if world > 1 else 0,
+           'collectives_per_frame': 'all-gather of the feature slices + all-gather of the BEV rows' if world > 1 else 'none'}
+    if world > 1:
+        # the same frame on one rank alone: every rank times its own unsharded forward (graph replay, no
+        # collective); efficiency = T(1) / (N * T(N)); the replicated share follows from T(N) = R + S / N
+        del graph
+        gfull, _ = capture(lambda: shard_forward(None)) if not args.no_graph else (None, None)
+
+        def full_step():
+            flush.zero_()
+            if gfull is None:
+                shard_forward(None)
+            else:
+                gfull.replay()
+        for _ in range(3):
+            full_step()
+        ms_full = timed(full_step, max(3, steps // 2))
+        res.update(ms_unsharded_one_gpu=ms_full, efficiency_vs_n1=ms_full / (world * ms_sharded),
+                   speedup_vs_n1=ms_full / ms_sharded,
+                   replicated_ms_estimate=max(0.0, (world * ms_sharded - ms_full) / (world - 1)),
+                   replicated_note='work that does not shrink with N (value projections over the full maps, '
+                                   'geometry, frame distribution, exit all-gather), from T(N) = R + S / N')
+        del gfull
+    if train_steps > 0:
+        enc.train()
+        params = [p for p in enc.parameters() if p.requires_grad]
+
+        def train_step(sharded):
+            flush.zero_()
+            for p in params:
+                p.grad = None
+            feat = d['feat'].detach().requires_grad_(True)
+            q = d['bev_query'].detach().requires_grad_(True)
+            kw = kwargs_of(feat)
+            if sharded and world > 1:
+                out = sharded_encoder_forward(enc, q, feat, feat, **kw)
+            else:
+                out = enc(q, feat, feat, **kw)
+            ((out.float() * d['grad_w'].float()).sum() * (1.0 / out.numel())).backward()
+            if sharded and world > 1:
+                allreduce_gradients(params)
+        for _ in range(2):
+            train_step(True)
+        ms_train = timed(lambda: train_step(True), train_steps)
+        res['train'] = {'ms_per_frame': ms_train, 'mode': 'eager forward + backward, gradients of the replicated '
+                        'tensors all-reduced in the backward, parameter gradients in one flat all-reduce'}
+        if world > 1:
+            for _ in range(2):
+                train_step(False)
+            ms_train_full = timed(lambda: train_step(False), max(2, train_steps // 2))
+            res['train'].update(ms_unsharded_one_gpu=ms_train_full,
+                                efficiency_vs_n1=ms_train_full / (world * ms_train))
+    return res
+
+
+def run_rowshard(args):
+    import torch.distributed as dist
+    import apollo_vision_net_b200 as pkg
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -490,74 +698,149 @@ def run_rowshard(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     pkg.build()
-    dtype = torch.bfloat16
     bev = args.bev if args.bev != 200 else 400
+    res = measure_rowshard(args, rank, world, dev, args.steps, args.warmup, bev=bev,
+                           train_steps=max(2, args.steps // 4))
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'BEVFormer encoder forward frames/s, BEV-query-row sharded', 'value': res['frames_per_s'],
+            'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': res['ms_per_frame'], 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': f'BEVFormer-base encoder forward, {bev}x{bev} BEV, 6 cams, 4 levels, '
+                                   f'{args.layers} layers, rows sharded over {world} rank(s), feature slices '
+                                   'all-gathered once per frame, one all-gather of the rows at exit '
+                                   '(BASELINE configs[4])',
+                       'l2': 'flushed every step (192 MiB write inside the timed region)'},
+            'rowshard': res, 'gpu_launches': res['launches_per_frame'] * args.steps}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------ det + map stand-in (BASELINE configs[2]) ------
+def measure_detmap(args, rank, world, dev, steps, warmup):
+    """BASELINE configs[2] as a synthetic stand-in: BEVFormer-base encoder ->
+    detection decoder (900 queries, 6 DetrTransformerDecoderLayers) + MapTRv2 decoder (350 vectors x 20
+    points, one-to-many mask, 6 decoupled layers) on the same BEV -> L2 loss on both decoders' stacked
+    outputs, forward + backward, one frame per rank, batch-level data parallelism (bucketed gradient
+    all-reduce), the whole step replayed as a CUDA graph.  Backbone, heads' losses and assigners are out of
+    scope; random-init weights, synthetic features.
+    Reference: projects/configs/bevformer/bev_tiny_det_mapv2.py:5-63, bevformer/apis/mmdet_train.py:71-85."""
+    import torch.distributed as dist
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    from apollo_vision_net_b200 import _lib
+    from apollo_vision_net_b200.parallel import BucketedGradReducer
+    dtype = torch.bfloat16
     levels = syn.LEVELS_BASE
-    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE))
-    randomize(enc, 0)
-    enc.to(dev).to(dtype).eval()
+    bev = 200
+    HW = bev * bev
+    NQ_DET, V, PN = 900, 350, 20
+    torch.manual_seed(0)
+    enc = pkg.build_transformer_layer_sequence(encoder_cfg(args.layers, len(levels), syn.PC_RANGE, args.dropout))
+    det = pkg.build_transformer_layer_sequence(dict(
+        type='DetectionTransformerDecoder', num_layers=6, return_intermediate=True,
+        transformerlayers=dict(
+            type='DetrTransformerDecoderLayer',
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=HEADS, dropout=args.dropout),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_levels=1, dropout=args.dropout)],
+            feedforward_channels=512, ffn_dropout=args.dropout,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    mapd = pkg.build_transformer_layer_sequence(dict(
+        type='MapTRv2Decoder', num_layers=6, return_intermediate=True,
+        transformerlayers=dict(
+            type='MapTRv2DecoupledDetrTransformerDecoderLayer', num_vec=V, num_pts_per_vec=PN,
+            attn_cfgs=[dict(type='MultiheadAttention', embed_dims=C, num_heads=HEADS, dropout=args.dropout),
+                       dict(type='MultiheadAttention', embed_dims=C, num_heads=HEADS, dropout=args.dropout),
+                       dict(type='CustomMSDeformableAttention', embed_dims=C, num_levels=1, dropout=args.dropout)],
+            feedforward_channels=512, ffn_dropout=args.dropout,
+            operation_order=('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    reg_det = torch.nn.ModuleList([torch.nn.Linear(C, 10) for _ in range(6)])
+    reg_map = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(6)])
+    model = torch.nn.ModuleList([enc, det, mapd, reg_det, reg_map])
+    randomize(model, 0)
+    model.to(dev).to(dtype).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    reducer = BucketedGradReducer(params, bucket_bytes=args.bucket_mb << 20) if world > 1 else None
     l2i, img_shape = syn.camera_rig(1.0, bs=1)
     l2i_dev = torch.as_tensor(l2i).to(dev)
-    host = host_inputs(bev, bev, levels, seed=1, dtype=dtype, pin=False)   # same frame on every rank
+    host = host_inputs(bev, bev, levels, seed=1 + rank, dtype=dtype, pin=False)
     d = {k: v.to(dev) for k, v in host.items()}
+    g = torch.Generator().manual_seed(7 + rank)
+    mk = lambda *sh: torch.randn(*sh, generator=g).to(dev, dtype)      # noqa: E731
+    q_det, p_det, q_map, p_map = mk(NQ_DET, 1, C), mk(NQ_DET, 1, C), mk(V * PN, 1, C), mk(V * PN, 1, C)
+    ref_det = torch.rand(1, NQ_DET, 3, generator=g).to(dev, dtype)
+    ref_map = torch.rand(1, V * PN, 2, generator=g).to(dev, dtype)
+    mask = torch.zeros(V, V, dtype=torch.bool, device=dev)
+    mask[50:, :50] = True
+    mask[:50, 50:] = True                              # one-to-one (50) / one-to-many (300) vectors
+    bshape, bstart = torch.tensor([[bev, bev]], device=dev), torch.tensor([0], device=dev)
     flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
-    def shard_forward():
-        with torch.no_grad():
-            return enc(d['bev_query'], d['feat'], d['feat'], bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
-                       spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
-                       shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape,
-                       row_shard=(rank, world) if world > 1 else
-                       ((0, args.shard_sim) if args.shard_sim > 1 else None))
+    def step():
+        for p in params:
+            p.grad = None
+        if reducer is not None:
+            reducer.reset()
+        feat = d['feat'].detach().requires_grad_(True)
+        bev_out = enc(d['bev_query'], feat, feat, bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
+                      spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
+                      shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape)          # (1, HW, C)
+        value = bev_out.permute(1, 0, 2)                                                  # (HW, 1, C)
+        det_out, _ = det(q_det, key=None, value=value, query_pos=p_det, reference_points=ref_det,
+                         reg_branches=reg_det, spatial_shapes=bshape, level_start_index=bstart)
+        map_out, _ = mapd(q_map, key=None, value=value, query_pos=p_map, reference_points=ref_map,
+                          reg_branches=reg_map, spatial_shapes=bshape, level_start_index=bstart,
+                          self_attn_mask=mask, num_vec=V, num_pts_per_vec=PN)
+        loss = det_out.float().square().mean() + map_out.float().square().mean()
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
 
-    # A rank's share of the frame is a few milliseconds of GPU work spread over ~150 launches: run
-    # eagerly the step is bound by the host's launch rate at N >= 4.  The shard forward never
-    # synchronises with the host, so it is captured once into a CUDA graph; the all-gather of the
-    # rows stays outside the graph (one NCCL launch per frame).
-    graph, static, graph_error = None, {}, None
+    def capture():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in params:
+            p.grad = None
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode='thread_local' if world > 1 else 'global'):
+            out = step()
+        torch.cuda.synchronize()
+        return gr, out
+
+    graph, graph_error = None, None
     if not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    shard_forward()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static['out'] = shard_forward()
-            torch.cuda.synchronize()
-        except Exception as exc:                   # pragma: no cover - reported in the JSON line
+            graph, _ = capture()
+        except Exception as exc:                       # pragma: no cover - reported in the JSON line
             graph, graph_error = None, f'{type(exc).__name__}: {exc}'[:200]
             torch.cuda.synchronize()
-    eager_launches = [0]
-    if graph is not None:                          # our launches per frame, counted on an eager pass
-        n0 = _lib.launch_count()
-        shard_forward()
-        eager_launches[0] = _lib.launch_count() - n0
 
-    def step():
+    def run():
         flush.zero_()
         if graph is None:
-            out = shard_forward()
+            step()
         else:
             graph.replay()
-            out = static['out']
-        if world > 1:
-            out = all_gather_bev_rows(out, bev, bev)
-        return out
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    n0 = _lib.launch_count()
+    step()
+    launches = _lib.launch_count() - n0
+    for _ in range(max(warmup, 3)):
+        run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
     s.record()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        run()
     e.record()
     if world > 1:
         dist.barrier()
@@ -565,19 +848,36 @@ def run_rowshard(args):
     ms = torch.tensor([s.elapsed_time(e)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms) / steps
+    if reducer is not None:
+        reducer.remove()
+    return {'workload': f'encoder ({args.layers} layers, 200x200) + detection decoder (900 queries x 6) + MapTRv2 '
+                        'decoder (350 x 20 queries x 6, one-to-many) -> L2 loss, fwd + bwd, one frame per rank',
+            'ms_per_step': ms, 'frames_per_s': world * 1e3 / ms, 'cuda_graph': graph is not None,
+            'cuda_graph_error': graph_error, 'our_launches_per_step': launches, 'dropout': args.dropout,
+            'parallelism': f'dp{world}' if world > 1 else 'single'}
+
+
+def run_detmap(args):
+    import torch.distributed as dist
+    import apollo_vision_net_b200 as pkg
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    pkg.build()
+    res = measure_detmap(args, rank, world, dev, args.steps, args.warmup)
     if rank == 0:
         print(json.dumps({
-            'metric': 'BEVFormer encoder forward frames/s, BEV-query-row sharded', 'value': args.steps / (float(ms) / 1e3),
-            'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': float(ms) / args.steps, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': f'BEVFormer-base encoder forward, {bev}x{bev} BEV, 6 cams, 4 levels, '
-                                   f'{args.layers} layers, rows sharded over {world} rank(s), value maps '
-                                   'replicated, one all-gather at exit (BASELINE configs[4])',
-                       'cuda_graph': graph is not None, 'cuda_graph_error': graph_error,
-                       'l2': 'flushed every step (192 MiB write inside the timed region)'},
-            'gpu_launches': (_lib.launch_count() - launches0) if graph is None
-            else eager_launches[0] * args.steps}), flush=True)
+            'metric': 'det+map stand-in frames/s (encoder + detection decoder + MapTRv2 decoder, fwd+bwd)',
+            'value': res['frames_per_s'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': res['workload'] + ' (BASELINE configs[2], synthetic stand-in)'},
+            'detmap': res, 'gpu_launches': res['our_launches_per_step'] * args.steps}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -665,7 +965,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--bev', type=int, default=200)
     ap.add_argument('--layers', type=int, default=6)
-    ap.add_argument('--workload', default='encoder', choices=['encoder', 'rowshard'],
+    ap.add_argument('--workload', default='encoder', choices=['encoder', 'rowshard', 'detmap'],
                     help="'encoder' (default, the contract line) or 'rowshard' (400x400 forward, strong scaling)")
     ap.add_argument('--shard-sim', type=int, default=0,
                     help='rowshard on ONE GPU: run rank 0 of this many row shards, no collective '
@@ -673,6 +973,9 @@ def main():
     ap.add_argument('--dropout', type=float, default=0.1,
                     help="dropout of TSA / SCA / FFN (reference training value 0.1; 0 = the parity-checked "
                          "deterministic configuration)")
+    ap.add_argument('--bucket-mb', type=int, default=2, help='gradient bucket size of the data-parallel arm (MiB)')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='N > 1: skip the row-shard / det+map measurements attached to the line')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
@@ -683,6 +986,8 @@ def main():
         run_reference(args)
     elif args.workload == 'rowshard':
         run_rowshard(args)
+    elif args.workload == 'detmap':
+        run_detmap(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_b200(args)

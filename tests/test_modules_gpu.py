@@ -497,6 +497,60 @@ def test_row_sharded_encoder_matches_full_on_one_gpu():
         enc(bevq, feat, feat, row_shard=(0, 2), **dict(kw, prev_bev=None))
 
 
+def test_row_sharded_encoder_backward_sums_to_the_full_gradients_on_one_gpu():
+    """Training with sharded BEV rows: the ranks of a 3-way split, run one after the
+    other on one GPU with their rows of the upstream gradient, produce partial gradients of the parameters,
+    the image features, the history and the BEV queries whose SUM equals the unsharded backward (the sum is
+    what parallel.replicated / allreduce_gradients compute over NCCL; gloo tests cover the collectives)."""
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.synthetic as syn
+    from apollo_vision_net_b200.parallel import bev_query_range
+    bs, H, W, C = 1, 24, 30, 256
+    levels = [(29, 50), (15, 25)]
+    shapes_l, starts_l, Nk = syn.level_tables(levels)
+    l2i, img_shape = syn.camera_rig(0.5, bs=bs)
+    enc = pkg.build_transformer_layer_sequence(dict(
+        type='BEVFormerEncoder', num_layers=2, pc_range=syn.PC_RANGE, num_points_in_pillar=4,
+        transformerlayers=dict(
+            type='BEVFormerLayer',
+            attn_cfgs=[dict(type='TemporalSelfAttention', embed_dims=C, num_levels=1, dropout=0.0),
+                       dict(type='SpatialCrossAttention', pc_range=syn.PC_RANGE, embed_dims=C, dropout=0.0,
+                            deformable_attention=dict(type='MSDeformableAttention3D', embed_dims=C,
+                                                      num_points=8, num_levels=len(levels)))],
+            feedforward_channels=512, ffn_dropout=0.0,
+            operation_order=('self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
+    _randomize(enc, 2)
+    enc.to(DEV).train()
+    g = torch.Generator().manual_seed(9)
+    bevq, pos, prev = (torch.randn(H * W, bs, C, generator=g).to(DEV) for _ in range(3))
+    feat = torch.randn(6, Nk, bs, C, generator=g).to(DEV)
+    go = torch.randn(bs, H * W, C, generator=g).to(DEV)
+    kw = dict(bev_h=H, bev_w=W, spatial_shapes=torch.tensor(shapes_l, device=DEV),
+              level_start_index=torch.tensor(starts_l, device=DEV),
+              shift=torch.tensor([[0.01, 0.02]], device=DEV), lidar2img=l2i, img_shape=img_shape)
+    params = [p for p in enc.parameters() if p.requires_grad]
+
+    def run(shard):
+        for p in params:
+            p.grad = None
+        q, ps, pv, f = (t.clone().requires_grad_(True) for t in (bevq, pos, prev, feat))
+        out = enc(q, f, f, bev_pos=ps, prev_bev=pv, row_shard=shard, **kw)
+        if shard is None:
+            out.backward(go)
+        else:
+            q0, q1 = bev_query_range(H, W, *shard)
+            out.backward(go[:, q0:q1])
+        return [q.grad, ps.grad, pv.grad, f.grad] + [p.grad.clone() for p in params]
+
+    full = run(None)
+    total = None
+    for r in range(3):
+        part = run((r, 3))
+        total = part if total is None else [a + b for a, b in zip(total, part)]
+    for i, (a, b) in enumerate(zip(total, full)):
+        assert rel_err(a, b) <= 2e-4, (i, rel_err(a, b))
+
+
 # ------------------------------------------------------------------ more shapes / paths ----
 @pytest.mark.parametrize('C,heads,D,P', [(128, 8, 4, 8), (64, 8, 2, 4), (256, 8, 1, 4)])
 def test_sca_generic_head_dims_and_anchor_counts(C, heads, D, P):
