@@ -202,7 +202,9 @@ class BucketedGradReducer:
 
     def _launch(self, b):
         ps = self.buckets[b]
-        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        # (parameters without a gradient this step -- unused in the graph -- contribute zeros, like DDP's
+        # find_unused_parameters; every rank runs the same model, so the collectives stay matched)
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in ps])
         if self.average and self.world > 1:
             flat.mul_(1.0 / self.world)
         self._flat[b] = flat
@@ -211,16 +213,18 @@ class BucketedGradReducer:
 
     def finish(self):
         """Wait for the collectives and point every ``p.grad`` at its slice of the reduced bucket."""
-        for b, ps in enumerate(self.buckets):          # (gradients that never arrived: unused parameters)
-            if self._pending[b] not in (0, len(ps)):
-                raise RuntimeError('a bucket received only part of its gradients')
+        for b, ps in enumerate(self.buckets):          # buckets that wait for a gradient that never came
+            if self._pending[b] > 0 and any(p.grad is not None for p in ps):
+                self._pending[b] = 0
+                self._launch(b)
         for b, work in self._works:
             if work is not None:
                 work.wait()
             off = 0
             for p in self.buckets[b]:
                 n = p.numel()
-                p.grad = self._flat[b][off:off + n].view_as(p)
+                if p.grad is not None:
+                    p.grad = self._flat[b][off:off + n].view_as(p)
                 off += n
         self._works = []
 

@@ -144,6 +144,20 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def leave(dist):
+    """End of a multi-rank run.  Captured CUDA graphs that contain NCCL launches keep the communicator busy:
+    destroy_process_group() after them was seen to hang (N = 2, driver 580.159) after the JSON line had been
+    printed.  Every rank has finished its work once the barrier returns, so the processes exit directly."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        os._exit(0)
+
+
 # --------------------------------------------------------------------------- B200 arm ------
 def run_b200(args):
     import torch.distributed as dist
@@ -161,7 +175,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     pkg.build()
 
     dtype = torch.bfloat16
@@ -514,7 +529,7 @@ def run_b200(args):
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        leave(dist)
 
 
 # ------------------------------------------------------------------ BEV row sharding ------
@@ -552,9 +567,13 @@ def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps
     pad = torch.zeros(chunk * world, dtype=dtype)
     pad[:n_feat] = host['feat'].view(-1)
     my_host = pad[rank * chunk:(rank + 1) * chunk].clone().pin_memory()
-    my_dev = torch.empty(chunk, dtype=dtype, device=dev)
+    my_dev = [torch.empty(chunk, dtype=dtype, device=dev) for _ in range(2)]   # double-buffered staging
     gathered = torch.empty(chunk * world, dtype=dtype, device=dev)
     feat_static = d['feat']
+    copy_stream = torch.cuda.Stream()
+    staged = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    frame = {'i': 0, 'primed': False}
 
     def kwargs_of(feat):
         return dict(bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'], spatial_shapes=d['shapes'],
@@ -587,12 +606,30 @@ def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps
             graph, graph_error = None, f'{type(exc).__name__}: {exc}'[:200]
             torch.cuda.synchronize()
 
+    def issue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            my_dev[slot].copy_(my_host, non_blocking=True)              # 1/N of the frame over PCIe
+            staged[slot].record(copy_stream)
+
     def distribute_frame():
+        """This frame's slice was put on the wire while the previous frame computed (copy stream, double
+        buffer); every frame's H2D still happens inside the timed region."""
         if world == 1:
             return
-        my_dev.copy_(my_host, non_blocking=True)                        # 1/N of the frame over PCIe
-        dist.all_gather_into_tensor(gathered, my_dev)                   # ... the rest over NVLink
+        main = torch.cuda.current_stream()
+        slot = frame['i'] & 1
+        if not frame['primed']:
+            for sl in (0, 1):
+                consumed[sl].record(main)
+            issue_h2d(slot)
+            frame['primed'] = True
+        main.wait_event(staged[slot])
+        dist.all_gather_into_tensor(gathered, my_dev[slot])             # ... the rest over NVLink
+        consumed[slot].record(main)
+        issue_h2d(slot ^ 1)                                             # next frame's slice
         feat_flat.copy_(gathered[:n_feat])                              # (into the graph's static input)
+        frame['i'] += 1
 
     def step():
         flush.zero_()
@@ -714,7 +751,7 @@ def run_rowshard(args):
                        'l2': 'flushed every step (192 MiB write inside the timed region)'},
             'rowshard': res, 'gpu_launches': res['launches_per_frame'] * args.steps}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        leave(dist)
 
 
 # ------------------------------------------------ det + map stand-in (BASELINE configs[2]) ------
@@ -879,7 +916,7 @@ def run_detmap(args):
             'config': {'workload': res['workload'] + ' (BASELINE configs[2], synthetic stand-in)'},
             'detmap': res, 'gpu_launches': res['our_launches_per_step'] * args.steps}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        leave(dist)
 
 
 # ---------------------------------------------------------------------- reference arm ------
@@ -978,7 +1015,12 @@ def main():
                     help='N > 1: skip the row-shard / det+map measurements attached to the line')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--watchdog-s', type=int, default=1500,
+                    help='abort the process (with a traceback of every thread on stderr) when the run takes longer')
     args = ap.parse_args()
+    import faulthandler
+    if args.watchdog_s > 0:          # a hung collective must end the run with a diagnosis, not sit on the GPUs
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)
     import torch
     torch.manual_seed(0)             # initial weights come from the global RNG: same model on every rank
     if args.impl == 'reference':
