@@ -171,9 +171,37 @@ def set_timer(timer):
     _timer = timer
 
 
+# Tracing: APOLLO_B200_NVTX=1 wraps every C-ABI launch and every encoder / decoder block
+# in an NVTX range, so a timeline (Nsight Systems, or ncu --nvtx filters) shows the reference's module
+# names above our kernels.  Off by default: a range costs two host calls per launch.
+NVTX = os.environ.get('APOLLO_B200_NVTX', '0') == '1'
+
+
+class nvtx_range:
+    """``with nvtx_range('BEVFormerLayer.cross_attn'): ...`` -- a no-op unless APOLLO_B200_NVTX=1."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
+
+
 def call(name, *args):
     """Invoke C entry point `name`; raises on a non-zero return code."""
     fn = getattr(lib(), name)
+    if NVTX:
+        with nvtx_range('msda::' + name):
+            rc = fn(*args)
+        check(rc, name)
+        return
     if _timer is None:
         rc = fn(*args)
     else:

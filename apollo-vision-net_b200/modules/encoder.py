@@ -18,6 +18,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .._lib import nvtx_range
 from ..fused_ops import BevGeometry, bev_point_sampling
 from ..rowops import LayerNorm, Linear, ReLU, advance_dropout_step, linear_add_layernorm
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
@@ -139,31 +140,34 @@ class BEVFormerLayer(BaseModule):
                 continue
             fused_norm = post is not None
             if op == 'self_attn':
-                query = self.attentions[attn_index](
-                    query, prev_bev, prev_bev, identity if self.pre_norm else None,
-                    query_pos=bev_pos, key_pos=bev_pos, key_padding_mask=query_key_padding_mask,
-                    reference_points=ref_2d, spatial_shapes=tsa_shapes[0],
-                    level_start_index=tsa_shapes[1], bev_h=bev_h, bev_w=bev_w, post_norm=post,
-                    **kwargs)
-                attn_index += 1
-                identity = query
+                with nvtx_range('BEVFormerLayer.self_attn'):
+                    query = self.attentions[attn_index](
+                        query, prev_bev, prev_bev, identity if self.pre_norm else None,
+                        query_pos=bev_pos, key_pos=bev_pos, key_padding_mask=query_key_padding_mask,
+                        reference_points=ref_2d, spatial_shapes=tsa_shapes[0],
+                        level_start_index=tsa_shapes[1], bev_h=bev_h, bev_w=bev_w, post_norm=post,
+                        **kwargs)
+                    attn_index += 1
+                    identity = query
             elif op == 'norm':
                 query = self.norms[norm_index](query)
                 norm_index += 1
             elif op == 'cross_attn':
-                query = self.attentions[attn_index](
-                    query, key, value, identity if self.pre_norm else None, query_pos=query_pos,
-                    key_pos=key_pos, reference_points=ref_3d,
-                    reference_points_cam=reference_points_cam, mask=mask,
-                    key_padding_mask=key_padding_mask, spatial_shapes=spatial_shapes,
-                    level_start_index=level_start_index, bev_h=bev_h, bev_w=bev_w, post_norm=post,
-                    **kwargs)
-                attn_index += 1
-                identity = query
+                with nvtx_range('BEVFormerLayer.cross_attn'):
+                    query = self.attentions[attn_index](
+                        query, key, value, identity if self.pre_norm else None, query_pos=query_pos,
+                        key_pos=key_pos, reference_points=ref_3d,
+                        reference_points_cam=reference_points_cam, mask=mask,
+                        key_padding_mask=key_padding_mask, spatial_shapes=spatial_shapes,
+                        level_start_index=level_start_index, bev_h=bev_h, bev_w=bev_w, post_norm=post,
+                        **kwargs)
+                    attn_index += 1
+                    identity = query
             elif op == 'ffn':
-                query = self.ffns[ffn_index](query, identity if self.pre_norm else None,
-                                             post_norm=post)
-                ffn_index += 1
+                with nvtx_range('BEVFormerLayer.ffn'):
+                    query = self.ffns[ffn_index](query, identity if self.pre_norm else None,
+                                                 post_norm=post)
+                    ffn_index += 1
         return query
 
 

@@ -474,16 +474,19 @@ def run_b200(args):
         cpu_baseline = run_reference_sample(steps=6, warmup=1)     # about 12 s of CPU work on the box
 
     extras = {}
-    if world > 1 and not args.no_extras:
-        # the north_star's own partition (BASELINE configs[4]) and the det+map stand-in (configs[2]) ride on the
-        # same line as extra keys; the headline metric above is untouched
+    if not args.no_extras:
+        # the north_star's own partition (BASELINE configs[4]: at N = 1 the unsharded frame, the reference of
+        # the strong-scaling sweep), the det+map stand-in (configs[2]) and the MapTRv2 decoder (configs[3]) ride
+        # on the same line as extra keys; the headline metric above is untouched
         graph_ok = graph is not None
         del graph
         graph = True if graph_ok else None
         torch.cuda.empty_cache()
         for name, fn in (('rowshard', lambda: measure_rowshard(args, rank, world, dev, max(5, args.steps // 2), 3,
                                                                 bev=400, train_steps=3)),
-                         ('detmap', lambda: measure_detmap(args, rank, world, dev, max(5, args.steps // 2), 3))):
+                         ('detmap', lambda: measure_detmap(args, rank, world, dev, max(5, args.steps // 2), 3)),
+                         ('maptrv2_decoder', lambda: measure_detmap(args, rank, world, dev, max(5, args.steps // 2), 3,
+                                                                    decoder_only=True))):
             try:
                 extras[name] = fn()
             except Exception as exc:               # pragma: no cover - reported in the JSON line
@@ -755,14 +758,17 @@ def run_rowshard(args):
 
 
 # ------------------------------------------------ det + map stand-in (BASELINE configs[2]) ------
-def measure_detmap(args, rank, world, dev, steps, warmup):
+def measure_detmap(args, rank, world, dev, steps, warmup, decoder_only=False):
     """BASELINE configs[2] as a synthetic stand-in: BEVFormer-base encoder ->
     detection decoder (900 queries, 6 DetrTransformerDecoderLayers) + MapTRv2 decoder (350 vectors x 20
     points, one-to-many mask, 6 decoupled layers) on the same BEV -> L2 loss on both decoders' stacked
     outputs, forward + backward, one frame per rank, batch-level data parallelism (bucketed gradient
     all-reduce), the whole step replayed as a CUDA graph.  Backbone, heads' losses and assigners are out of
     scope; random-init weights, synthetic features.
-    Reference: projects/configs/bevformer/bev_tiny_det_mapv2.py:5-63, bevformer/apis/mmdet_train.py:71-85."""
+    Reference: projects/configs/bevformer/bev_tiny_det_mapv2.py:5-63, bevformer/apis/mmdet_train.py:71-85.
+
+    ``decoder_only``: BASELINE configs[3] -- the MapTRv2 decoder alone (deformable cross-attention of 7000
+    queries on a given 200x200 BEV, 6 layers, one-to-many queries enabled), forward + backward."""
     import torch.distributed as dist
     import apollo_vision_net_b200 as pkg
     import apollo_vision_net_b200.synthetic as syn
@@ -794,7 +800,7 @@ def measure_detmap(args, rank, world, dev, steps, warmup):
             operation_order=('self_attn', 'norm', 'self_attn', 'norm', 'cross_attn', 'norm', 'ffn', 'norm'))))
     reg_det = torch.nn.ModuleList([torch.nn.Linear(C, 10) for _ in range(6)])
     reg_map = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(6)])
-    model = torch.nn.ModuleList([enc, det, mapd, reg_det, reg_map])
+    model = torch.nn.ModuleList([mapd, reg_map] if decoder_only else [enc, det, mapd, reg_det, reg_map])
     randomize(model, 0)
     model.to(dev).to(dtype).train()
     params = [p for p in model.parameters() if p.requires_grad]
@@ -819,17 +825,22 @@ def measure_detmap(args, rank, world, dev, steps, warmup):
             p.grad = None
         if reducer is not None:
             reducer.reset()
-        feat = d['feat'].detach().requires_grad_(True)
-        bev_out = enc(d['bev_query'], feat, feat, bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
-                      spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
-                      shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape)          # (1, HW, C)
-        value = bev_out.permute(1, 0, 2)                                                  # (HW, 1, C)
-        det_out, _ = det(q_det, key=None, value=value, query_pos=p_det, reference_points=ref_det,
-                         reg_branches=reg_det, spatial_shapes=bshape, level_start_index=bstart)
+        if decoder_only:
+            value = d['prev_bev'].detach().requires_grad_(True)                           # a BEV (HW, 1, C)
+        else:
+            feat = d['feat'].detach().requires_grad_(True)
+            bev_out = enc(d['bev_query'], feat, feat, bev_h=bev, bev_w=bev, bev_pos=d['bev_pos'],
+                          spatial_shapes=d['shapes'], level_start_index=d['starts'], prev_bev=d['prev_bev'],
+                          shift=d['shift'], lidar2img=l2i_dev, img_shape=img_shape)      # (1, HW, C)
+            value = bev_out.permute(1, 0, 2)                                              # (HW, 1, C)
         map_out, _ = mapd(q_map, key=None, value=value, query_pos=p_map, reference_points=ref_map,
                           reg_branches=reg_map, spatial_shapes=bshape, level_start_index=bstart,
                           self_attn_mask=mask, num_vec=V, num_pts_per_vec=PN)
-        loss = det_out.float().square().mean() + map_out.float().square().mean()
+        loss = map_out.float().square().mean()
+        if not decoder_only:
+            det_out, _ = det(q_det, key=None, value=value, query_pos=p_det, reference_points=ref_det,
+                             reg_branches=reg_det, spatial_shapes=bshape, level_start_index=bstart)
+            loss = loss + det_out.float().square().mean()
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -888,8 +899,11 @@ def measure_detmap(args, rank, world, dev, steps, warmup):
     ms = float(ms) / steps
     if reducer is not None:
         reducer.remove()
-    return {'workload': f'encoder ({args.layers} layers, 200x200) + detection decoder (900 queries x 6) + MapTRv2 '
-                        'decoder (350 x 20 queries x 6, one-to-many) -> L2 loss, fwd + bwd, one frame per rank',
+    what = ('MapTRv2 decoder alone (350 x 20 queries x 6 layers, one-to-many mask, deformable cross-attention on a '
+            '200x200 BEV) -> L2 loss, fwd + bwd (BASELINE configs[3])') if decoder_only else (
+        f'encoder ({args.layers} layers, 200x200) + detection decoder (900 queries x 6) + MapTRv2 '
+        'decoder (350 x 20 queries x 6, one-to-many) -> L2 loss, fwd + bwd, one frame per rank')
+    return {'workload': what,
             'ms_per_step': ms, 'frames_per_s': world * 1e3 / ms, 'cuda_graph': graph is not None,
             'cuda_graph_error': graph_error, 'our_launches_per_step': launches, 'dropout': args.dropout,
             'parallelism': f'dp{world}' if world > 1 else 'single'}
