@@ -615,38 +615,69 @@ def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps
             my_dev[slot].copy_(my_host, non_blocking=True)              # 1/N of the frame over PCIe
             staged[slot].record(copy_stream)
 
-    def distribute_frame():
-        """This frame's slice was put on the wire while the previous frame computed (copy stream, double
-        buffer); every frame's H2D still happens inside the timed region."""
-        if world == 1:
-            return
+    # Frame pipeline (N > 1).  Everything a frame needs from outside the GPU is on its way while the frame
+    # before it computes: its slice over PCIe (copy stream, double buffer), the other ranks' slices over
+    # NVLink (asynchronous all-gather on NCCL's stream); and the frame's own BEV rows leave through an
+    # asynchronous all-gather that overlaps the next frame.  Every frame still pays one H2D, one feature
+    # all-gather and one row all-gather inside the timed region; the run is drained before the clock stops.
+    pend = {'feat': None, 'rows': None}
+    rows_send = {'buf': None, 'recv': None}
+
+    def start_feat_gather():
         main = torch.cuda.current_stream()
         slot = frame['i'] & 1
+        main.wait_event(staged[slot])
+        pend['feat'] = (dist.all_gather_into_tensor(gathered, my_dev[slot], async_op=True), slot)
+        frame['i'] += 1
+
+    def take_features():
+        main = torch.cuda.current_stream()
         if not frame['primed']:
             for sl in (0, 1):
                 consumed[sl].record(main)
-            issue_h2d(slot)
+                issue_h2d(sl)
+            start_feat_gather()
             frame['primed'] = True
-        main.wait_event(staged[slot])
-        dist.all_gather_into_tensor(gathered, my_dev[slot])             # ... the rest over NVLink
-        consumed[slot].record(main)
-        issue_h2d(slot ^ 1)                                             # next frame's slice
+        work, slot = pend['feat']
+        work.wait()
         feat_flat.copy_(gathered[:n_feat])                              # (into the graph's static input)
-        frame['i'] += 1
+        consumed[slot].record(main)
+        issue_h2d(slot)                                                 # the slice of the frame after next
+        start_feat_gather()                                             # the next frame's slices, during this frame
+
+    def send_rows(out):
+        if rows_send['buf'] is None:
+            rows_send['buf'] = torch.empty_like(out)
+            rows_send['recv'] = out.new_empty((world,) + tuple(out.shape))
+        if pend['rows'] is not None:
+            pend['rows'].wait()                                         # the previous frame's rows have arrived
+        rows_send['buf'].copy_(out)                                     # the next replay may overwrite `out`
+        pend['rows'] = dist.all_gather_into_tensor(rows_send['recv'], rows_send['buf'], async_op=True)
+
+    def drain():
+        if pend['rows'] is not None:
+            pend['rows'].wait()
+            pend['rows'] = None
+
+    even = bev % world == 0
 
     def step():
         flush.zero_()
-        distribute_frame()
+        if world > 1:
+            take_features()
         if graph is None:
             out = shard_forward(shard)
         else:
             graph.replay()
             out = static_out
         if world > 1:
-            out = all_gather_bev_rows(out, bev, bev)
+            if even:
+                send_rows(out)
+            else:
+                out = all_gather_bev_rows(out, bev, bev)
         return out
 
-    def timed(fn, n):
+    def timed(fn, n, after=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -654,6 +685,8 @@ def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps
         s.record()
         for _ in range(n):
             fn()
+        if after is not None:
+            after()
         e.record()
         if world > 1:
             dist.barrier()
@@ -665,15 +698,19 @@ def measure_rowshard(args, rank, world, dev, steps, warmup, bev=400, train_steps
 
     for _ in range(max(warmup, 3)):
         step()
+    drain()
     n0 = _lib.launch_count()
     if graph is not None:
         shard_forward(shard)                       # our launches per frame, counted on an eager pass
     launches = _lib.launch_count() - n0
-    ms_sharded = timed(step, steps)
+    ms_sharded = timed(step, steps, after=drain)
+    if world > 1 and pend['feat'] is not None:
+        pend['feat'][0].wait()                     # (the gather issued for a frame that will not come)
     res = {'bev': bev, 'ms_per_frame': ms_sharded, 'frames_per_s': 1e3 / ms_sharded,
            'cuda_graph': graph is not None, 'cuda_graph_error': graph_error, 'launches_per_frame': launches,
            'h2d_bytes_per_frame_per_rank': chunk * 2 if world > 1 else 0,
-           'collectives_per_frame': 'all-gather of the feature slices + all-gather of the BEV rows' if world > 1 else 'none'}
+           'collectives_per_frame': 'all-gather of the feature slices + all-gather of the BEV rows, both asynchronous '
+                                    'and overlapped with the neighbouring frame' if world > 1 else 'none'}
     if world > 1:
         # the same frame on one rank alone: every rank times its own unsharded forward (graph replay, no
         # collective); efficiency = T(1) / (N * T(N)); the replicated share follows from T(N) = R + S / N
