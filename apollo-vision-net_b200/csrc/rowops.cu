@@ -10,6 +10,7 @@
 // eps inside the square root, affine weight / bias, statistics in fp32.
 #include "msda_common.cuh"
 #include "msda_host.h"
+#include "philox.cuh"
 
 namespace msda {
 
@@ -47,17 +48,6 @@ struct DropArgs {
   float scale;                         // 1 / (1 - p)
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
 // keep bits (bit j = element 8 * group + j is kept)
 __device__ __forceinline__ uint32_t drop_keep8(unsigned long long group, unsigned long long seed,
                                                unsigned long long step, uint32_t site, uint32_t thresh) {

@@ -60,6 +60,7 @@ def hoisted_projections(layers, args, kwargs):
 
 @ATTENTION.register_module()
 class CustomMSDeformableAttention(DeformAttnBase):
+    accepts_post_norm = True        # forward(post_norm=LayerNorm): the layer's next norm runs inside the block
 
     def __init__(self, embed_dims=256, num_heads=8, num_levels=4, num_points=4, im2col_step=64,
                  dropout=0.1, batch_first=False, norm_cfg=None, init_cfg=None,

@@ -98,6 +98,10 @@ def finish_block(mod, output, identity, post_norm=None):
     if post_norm is not None and batch_first:
         return linear_add_layernorm(output, mod.output_proj, identity, post_norm,
                                     p=drop.p if mod.training else 0.0)
+    if post_norm is not None and output.dim() == 3 and output.shape[0] == 1:
+        # sequence-first caller with one sample: (1, Nq, C) and (Nq, 1, C) hold the same rows in the same order
+        return linear_add_layernorm(output.permute(1, 0, 2), mod.output_proj, identity, post_norm,
+                                    p=drop.p if mod.training else 0.0)
     output = mod.output_proj(output)
     if not batch_first:
         output = output.permute(1, 0, 2)

@@ -5,8 +5,9 @@ decoder.py:50-126``): the layer sequence that calls ``CustomMSDeformableAttentio
 queries sampling the BEV) and refines 3-d reference points between the layers.  Its layers are
 mmdet's ``DetrTransformerDecoderLayer`` (self_attn, norm, cross_attn, norm, ffn, norm --
 ``configs/bevformer/bev_tiny_det_map_apollo.py`` decoder section); without mmcv / mmdet installed
-the same layer is provided here.  Only the cross-attention is on the hot path (fused sm_100a
-kernel); the dense self-attention uses ``torch.nn.MultiheadAttention``.
+the same layer is provided here.  The cross-attention runs on the fused sm_100a
+deformable-attention kernel, the dense self-attention over the object queries on the attention core of
+``csrc/mha.cu``, and every ``norm`` is folded into the block in front of it.
 """
 import copy
 
@@ -18,7 +19,7 @@ from ..registry import (HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE
 from ..rowops import LayerNorm
 from .decoder import hoisted_projections, inverse_sigmoid
 from .encoder import FFN
-from . import maptrv2_decoder  # noqa: F401  (registers the MultiheadAttention shim without mmcv)
+from .maptrv2_decoder import run_layer_ops      # also registers the MultiheadAttention shim without mmcv
 
 
 if not HAVE_MMCV:
@@ -62,36 +63,20 @@ if not HAVE_MMCV:
 
         def forward(self, query, key=None, value=None, query_pos=None, key_pos=None,
                     attn_masks=None, query_key_padding_mask=None, key_padding_mask=None, **kwargs):
-            norm_index = attn_index = ffn_index = 0
-            identity = query
             if attn_masks is None:
                 attn_masks = [None for _ in range(self.num_attn)]
             elif isinstance(attn_masks, torch.Tensor):
                 attn_masks = [copy.deepcopy(attn_masks) for _ in range(self.num_attn)]
             else:
                 assert len(attn_masks) == self.num_attn
-            for op in self.operation_order:
-                if op == 'self_attn':
-                    query = self.attentions[attn_index](
-                        query, query, query, identity if self.pre_norm else None,
-                        query_pos=query_pos, key_pos=query_pos, attn_mask=attn_masks[attn_index],
-                        key_padding_mask=query_key_padding_mask)
-                    attn_index += 1
-                    identity = query
-                elif op == 'norm':
-                    query = self.norms[norm_index](query)
-                    norm_index += 1
-                elif op == 'cross_attn':
-                    query = self.attentions[attn_index](
-                        query, key, value, identity if self.pre_norm else None,
-                        query_pos=query_pos, key_pos=key_pos, attn_mask=attn_masks[attn_index],
-                        key_padding_mask=key_padding_mask, **kwargs)
-                    attn_index += 1
-                    identity = query
-                elif op == 'ffn':
-                    query = self.ffns[ffn_index](query, identity if self.pre_norm else None)
-                    ffn_index += 1
-            return query
+
+            def self_attention(attn, attn_index, query, identity, post_norm):
+                extra = {} if post_norm is None else {'post_norm': post_norm}
+                return attn(query, query, query, identity, query_pos=query_pos, key_pos=query_pos,
+                            attn_mask=attn_masks[attn_index], key_padding_mask=query_key_padding_mask, **extra)
+
+            return run_layer_ops(self, query, key, value, query_pos, key_pos, attn_masks,
+                                 query_key_padding_mask, key_padding_mask, self_attention, kwargs)
 
 
 @TRANSFORMER_LAYER_SEQUENCE.register_module()

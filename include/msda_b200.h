@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 5
+#define MSDA_ABI_VERSION 6
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -373,6 +373,47 @@ int bev_rotate_nearest(const void* prev_bev, void* out, const float* theta, cons
 int64_t linear_wgrad_workspace_floats(int O, int I);
 int linear_wgrad(const void* dy, const void* x, void* dW, void* db, float* workspace, int64_t N,
                  int O, int I, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Small-sequence multi-head self-attention of the decoders: replaces the
+ * torch.nn.MultiheadAttention core behind mmcv's MultiheadAttention in
+ *   projects/mmdet3d_plugin/maptrv2/modules/decoder.py:129-188 (inter-vector attention over the vectors with
+ *   the one-to-one / one-to-many block mask, intra-vector attention over a vector's points) and in the
+ *   detection decoder's DetrTransformerDecoderLayer (bevformer/modules/decoder.py:50-126 builds it).
+ *
+ *   out = dropout_p(softmax(scale * q k^T + mask)) v        per (group, head)
+ *
+ * A problem is one (group g, head h): S tokens x Dh.  Token s of group g is row
+ *     s * seq_stride + (g / n_lo) * hi_stride + (g % n_lo) * lo_stride
+ * of the matrices q / k / v / out (dtype; element (row, h * Dh + d) at row * ld + h * Dh + d), so the
+ * (num_query, bs, C) activations of a decoder layer are attended in place under either grouping of
+ * decoder.py:131-185 without the permute + contiguous copies.  ld* in elements; pointers and row strides
+ * 16-byte aligned; Dh in {32, 64} takes the tensor-core kernels for 16-bit dtypes (mma.sync, fp32
+ * accumulate, K / V of a problem staged once per CTA), any other supported case (fp32; Dh in {8, 16, 32, 64},
+ * S <= 3072) a one-warp-per-row FMA kernel.  impl: 0 = choose, 1 = force the FMA path, 2 = require the
+ * tensor-core path.  mha_impl() returns what 0 would choose (0 = unsupported).
+ *   mask_bits / mask_bits_t  (S, ceil(S / 32)) uint32 from mha_pack_mask(): bit k of row q set = query q may
+ *              not attend to key k (the reference's boolean attn_mask, shared by all groups and heads);
+ *              the second matrix is the transpose; NULL = no mask.  A row with no admissible key yields 0.
+ *   lse        (G * H, S) fp32, written by the forward: log sum exp of the row's scaled scores.
+ *   delta      (G * H, S) fp32 scratch of the backward (rowsum(grad_out * out)).
+ *   dq, dk, dv have the layout (and ld) of q, k, v; every element of a token row's head slice is written.
+ *   dropout    on the attention weights, counter-based and recomputed in the backward (rng_state,
+ *              key_save / key, site, p: as in ln_residual_dropout_fwd).  mha_keep_mask() writes the keep
+ *              mask ((G * H, S, S) bytes) for tests.
+ * ------------------------------------------------------------------------------- */
+int mha_impl(int G, int H, int S, int Dh, int dtype);
+int mha_pack_mask(const uint8_t* mask, int S, uint32_t* bits, uint32_t* bits_t, void* stream);
+int mha_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int64_t ldq, int64_t ldk,
+            int64_t ldv, int64_t ldo, const uint32_t* mask_bits, int G, int H, int S, int Dh,
+            int64_t seq_stride, int64_t hi_stride, int64_t lo_stride, int n_lo, float scale, int dtype,
+            int impl, const void* rng_state, void* key_save, uint32_t site, float p, void* stream);
+int mha_bwd(const void* q, const void* k, const void* v, const void* out, const void* grad_out,
+            const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk,
+            int64_t ldv, int64_t ldo, const uint32_t* mask_bits, const uint32_t* mask_bits_t, int G, int H,
+            int S, int Dh, int64_t seq_stride, int64_t hi_stride, int64_t lo_stride, int n_lo, float scale,
+            int dtype, int impl, const void* key, uint32_t site, float p, void* stream);
+int mha_keep_mask(uint8_t* keep, int P, int S, const void* key, uint32_t site, float p, void* stream);
 
 #ifdef __cplusplus
 }
