@@ -18,6 +18,9 @@ def main():
     ap.add_argument('--bev', type=int, default=50)
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--train', action='store_true', help='training mode (dropout 0.1 everywhere)')
+    ap.add_argument('--torch-self-attn', action='store_true',
+                    help='self-attentions on torch.nn.MultiheadAttention with the permute copies (the round-1 path)')
     args = ap.parse_args()
     dev = torch.device('cuda:0')
     dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[args.dtype]
@@ -36,7 +39,11 @@ def main():
     for n, p in dec.named_parameters():
         if n.endswith('sampling_offsets.weight') or n.endswith('attention_weights.weight'):
             p.data = torch.randn(p.shape, generator=g) * 0.02
-    dec.to(dev).to(dtype).eval()
+    dec.to(dev).to(dtype).train(args.train)
+    if args.torch_self_attn:
+        for layer in dec.layers:
+            for a in layer.attentions[:2]:
+                a.use_fused_core = False
     reg = torch.nn.ModuleList([torch.nn.Linear(C, 2) for _ in range(6)]).to(dev).to(dtype)
     query = torch.randn(V * Pn, bs, C, device=dev, dtype=dtype, requires_grad=True)
     qpos = torch.randn(V * Pn, bs, C, device=dev, dtype=dtype)
@@ -57,7 +64,7 @@ def main():
         query.grad = None
         bev.grad = None
 
-    res = {'bev': H, 'dtype': args.dtype, 'queries': V * Pn, 'xattn_samples_per_layer': V * Pn * 8 * 4}
+    res = {'bev': H, 'dtype': args.dtype, 'train': args.train, 'torch_self_attn': args.torch_self_attn, 'queries': V * Pn, 'xattn_samples_per_layer': V * Pn * 8 * 4}
     for hoist in (True, False):
         dec.hoist_value_proj = hoist
         for _ in range(5):
