@@ -940,7 +940,31 @@ def measure_detmap(args, rank, world, dev, steps, warmup, decoder_only=False):
             '200x200 BEV) -> L2 loss, fwd + bwd (BASELINE configs[3])') if decoder_only else (
         f'encoder ({args.layers} layers, 200x200) + detection decoder (900 queries x 6) + MapTRv2 '
         'decoder (350 x 20 queries x 6, one-to-many) -> L2 loss, fwd + bwd, one frame per rank')
-    return {'workload': what,
+    torch_ms = None
+    if decoder_only and world == 1:
+        # the same step with the self-attentions on torch.nn.MultiheadAttention + the reference's permute copies
+        # (what this repository ran before csrc/mha.cu): the gain of the attention core, measured side by side
+        for layer in mapd.layers:
+            for att in layer.attentions[:2]:
+                att.use_fused_core = False
+        try:
+            graph = None
+            if not args.no_graph:
+                graph, _ = capture()
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(steps):
+                run()
+            e.record()
+            torch.cuda.synchronize()
+            torch_ms = s.elapsed_time(e) / steps
+        except Exception:                              # pragma: no cover
+            torch.cuda.synchronize()
+    return {'workload': what, 'self_attention': 'csrc/mha.cu (mma.sync tensor-core core, tokens attended in place, '
+                                                'LayerNorms folded into the blocks)',
+            'ms_per_step_torch_self_attention': torch_ms,
             'ms_per_step': ms, 'frames_per_s': world * 1e3 / ms, 'cuda_graph': graph is not None,
             'cuda_graph_error': graph_error, 'our_launches_per_step': launches, 'dropout': args.dropout,
             'parallelism': f'dp{world}' if world > 1 else 'single'}
