@@ -61,7 +61,7 @@ _SIGNATURES = {
     'mha_pack_mask': (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp]),
     'mha_fwd': (_c_int, [_c_vp] * 5 + [_c_i64] * 4 + [_c_vp] + [_c_int] * 4 + [_c_i64] * 3 + [_c_int, _c_f, _c_int, _c_int,
                          _c_vp, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
-    'mha_bwd': (_c_int, [_c_vp] * 10 + [_c_i64] * 4 + [_c_vp, _c_vp] + [_c_int] * 4 + [_c_i64] * 3 +
+    'mha_bwd': (_c_int, [_c_vp] * 10 + [_c_i64] * 7 + [_c_vp, _c_vp] + [_c_int] * 4 + [_c_i64] * 3 +
                 [_c_int, _c_f, _c_int, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
     'mha_keep_mask': (_c_int, [_c_vp, _c_int, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
 }

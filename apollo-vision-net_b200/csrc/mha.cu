@@ -46,6 +46,7 @@ struct MhaArgs {
   const void *q, *k, *v, *o, *dout;
   void *out, *dq, *dk, *dv;
   long long ldq, ldk, ldv, ldo;
+  long long lddq, lddk, lddv;      // row strides of the gradient matrices dq / dk / dv
   float* lse;                      // (G * H, S) natural-log sum of exp of the scaled scores (+inf: empty row)
   float* delta;                    // (G * H, S) rowsum(dO . O), written by pass A, read by pass B
   const uint32_t* mask_bits;       // (S, mask_words): bit k of row q set = q may not attend to k; or NULL
@@ -566,10 +567,10 @@ mha_bwd_tc_kernel(const MhaArgs a, int npc, int tpc, int ntiles, int S_pad) {
   if (TR) frags_to_tile<T, DH>(st1, acc2, lane);
   __syncwarp();
   if (!TR) {
-    store_tile<T, DH>(st0, a.dq, a.ldq, a, gbase, h, r0, lane);
+    store_tile<T, DH>(st0, a.dq, a.lddq, a, gbase, h, r0, lane);
   } else {
-    store_tile<T, DH>(st0, a.dk, a.ldk, a, gbase, h, r0, lane);
-    store_tile<T, DH>(st1, a.dv, a.ldv, a, gbase, h, r0, lane);
+    store_tile<T, DH>(st0, a.dk, a.lddk, a, gbase, h, r0, lane);
+    store_tile<T, DH>(st1, a.dv, a.lddv, a, gbase, h, r0, lane);
   }
   __syncwarp();
   }
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(kMhaThreads) mha_bwd_dq_simt_kernel(const MhaA
   __syncwarp();
   float acc[(DH + 31) / 32];
   weighted_rows<T, DH>(acc, sc, a.k, gbase, a.seq_stride, a.ldk, h, a.S, lane);
-  store_dims<T, DH>(a.dq, qrow, a.ldq, h, acc, lane);
+  store_dims<T, DH>(a.dq, qrow, a.lddq, h, acc, lane);
 }
 
 // pass B: one warp per key -> dK and dV rows
@@ -766,9 +767,9 @@ __global__ void __launch_bounds__(kMhaThreads) mha_bwd_dkv_simt_kernel(const Mha
   __syncwarp();
   float acc[(DH + 31) / 32];
   weighted_rows<T, DH>(acc, scp, a.dout, gbase, a.seq_stride, a.ldo, h, a.S, lane);
-  store_dims<T, DH>(a.dv, krow, a.ldv, h, acc, lane);
+  store_dims<T, DH>(a.dv, krow, a.lddv, h, acc, lane);
   weighted_rows<T, DH>(acc, scs, a.q, gbase, a.seq_stride, a.ldq, h, a.S, lane);
-  store_dims<T, DH>(a.dk, krow, a.ldk, h, acc, lane);
+  store_dims<T, DH>(a.dk, krow, a.lddk, h, acc, lane);
 }
 
 __global__ void mha_pack_mask_kernel(const uint8_t* __restrict__ mask, int S, int W, uint32_t* __restrict__ bits,
@@ -930,7 +931,8 @@ int check_common(const char* what, const MhaArgs& a, int Dh, int dtype, float p)
     return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: unknown dtype %d", what, dtype);
   if (!a.q || !a.k || !a.v || !a.lse) return set_error(MSDA_ERR_BAD_ARGUMENT, "%s: NULL pointer", what);
   const int vec = dtype == MSDA_F32 ? 4 : 8;
-  if (Dh % vec != 0 || a.ldq % vec != 0 || a.ldk % vec != 0 || a.ldv % vec != 0 || a.ldo % vec != 0)
+  if (Dh % vec != 0 || a.ldq % vec != 0 || a.ldk % vec != 0 || a.ldv % vec != 0 || a.ldo % vec != 0 ||
+      a.lddq % vec != 0 || a.lddk % vec != 0 || a.lddv % vec != 0)
     return set_error(MSDA_ERR_UNSUPPORTED, "%s: head_dim and the row strides must be multiples of %d elements", what, vec);
   const uintptr_t bits = (uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.out | (uintptr_t)a.o |
                          (uintptr_t)a.dout | (uintptr_t)a.dq | (uintptr_t)a.dk | (uintptr_t)a.dv;
@@ -993,6 +995,7 @@ int mha_fwd(const void* q, const void* k, const void* v, void* out, float* lse, 
 
 int mha_bwd(const void* q, const void* k, const void* v, const void* out, const void* grad_out, const float* lse,
             float* delta, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+            int64_t ld_dq, int64_t ld_dk, int64_t ld_dv,
             const uint32_t* mask_bits, const uint32_t* mask_bits_t, int G, int H, int S, int Dh,
             int64_t seq_stride, int64_t hi_stride, int64_t lo_stride, int n_lo, float scale, int dtype, int impl,
             const void* key, uint32_t site, float p, void* stream) {
@@ -1000,6 +1003,7 @@ int mha_bwd(const void* q, const void* k, const void* v, const void* out, const 
   a.q = q; a.k = k; a.v = v; a.o = out; a.dout = grad_out; a.lse = const_cast<float*>(lse); a.delta = delta;
   a.dq = dq; a.dk = dk; a.dv = dv;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.lddq = ld_dq > 0 ? ld_dq : ldq; a.lddk = ld_dk > 0 ? ld_dk : ldk; a.lddv = ld_dv > 0 ? ld_dv : ldv;
   a.mask_bits = mask_bits; a.mask_bits_t = mask_bits_t; a.mask_words = (S + 31) / 32;
   a.G = G; a.H = H; a.S = S;
   a.seq_stride = seq_stride; a.hi_stride = hi_stride; a.lo_stride = lo_stride; a.n_lo = n_lo;

@@ -17,7 +17,7 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .multi_scale_deformable_attn_function import _DTYPE_CODE, _stream_ptr, custom_bwd, custom_fwd
-from .rowops import _next_site, dropout_state
+from .rowops import _colsum_supported, _next_site, column_sum, dropout_state
 
 # Token s of group g is row  s * seq_stride + (g // n_lo) * hi_stride + (g % n_lo) * lo_stride  of the
 # (rows, C) activation matrix; G groups of S tokens cover every row exactly once.
@@ -140,12 +140,107 @@ class SelfAttentionCoreFunction(Function):
         with torch.cuda.device(v.device):
             _lib.call('mha_bwd', qk.data_ptr(), qk.data_ptr() + C * esz, v.data_ptr(), out.data_ptr(),
                       dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqk.data_ptr(),
-                      dqk.data_ptr() + C * esz, dv.data_ptr(), 2 * C, 2 * C, C, C,
+                      dqk.data_ptr() + C * esz, dv.data_ptr(), 2 * C, 2 * C, C, C, 0, 0, 0,
                       None if bits is None else bits.data_ptr(), None if bits_t is None else bits_t.data_ptr(),
                       layout.G, heads, layout.S, Dh, layout.seq_stride, layout.hi_stride, layout.lo_stride,
                       layout.n_lo, scale, _DTYPE_CODE[v.dtype], impl,
                       None if key is None else key.data_ptr(), ctx.site, ctx.p, _stream_ptr(v))
         return dqk, dv, None, None, None, None, None
+
+
+class SelfAttentionFunction(Function):
+    """In-projection + attention core of an mmcv-convention self-attention as ONE autograd node:
+
+        q | k = (x + pos) W[:2C]^T + b[:2C],   v = x W[2C:]^T + b[2C:],   o = core(q, k, v)
+
+    (``torch.nn.MultiheadAttention``'s packed ``in_proj_weight`` / ``in_proj_bias``).  Against the composition
+    of ``linear`` nodes and :class:`SelfAttentionCoreFunction` the backward has no parameter slices to zero-fill
+    and accumulate, no gradient-accumulation adds on x, and one bias reduction: the core's backward writes
+    dq | dk | dv into one (rows, 3C) buffer, whose column sums are the bias gradient, whose two column blocks
+    give the two halves of dW (written straight into one (3C, C) tensor) and dx = dqk W[:2C] + dv W[2C:]
+    (the second GEMM accumulates onto the first)."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, x, pos, weight, bias, layout, heads, packed_mask, p, impl):
+        if not x.is_cuda:
+            raise RuntimeError('self_attention has no CPU path')
+        C = x.shape[-1]
+        x2 = x.reshape(-1, C)
+        rows = x2.shape[0]
+        if layout.G * layout.S != rows or weight.shape != (3 * C, C) or C % heads != 0:
+            raise ValueError(f'x {tuple(x.shape)}, in_proj_weight {tuple(weight.shape)}, {layout} do not fit')
+        xp = x2 if pos is None else x2 + pos.reshape(-1, C)
+        qk = torch.addmm(bias[:2 * C], xp, weight[:2 * C].t())
+        v = torch.addmm(bias[2 * C:], x2, weight[2 * C:].t())
+        Dh = C // heads
+        bits, bits_t = packed_mask if packed_mask is not None else (None, None)
+        out = torch.empty_like(v)
+        lse = torch.empty((layout.G * heads, layout.S), dtype=torch.float32, device=x.device)
+        ctx.p, ctx.site, key = float(p), 0, None
+        if p > 0:
+            ctx.site = _next_site()
+            key = torch.empty(2, dtype=torch.int64, device=x.device)
+        esz = qk.element_size()
+        ctx.geom = (layout, heads, Dh, 1.0 / float(Dh) ** 0.5, int(impl))
+        with torch.cuda.device(x.device):
+            _lib.call('mha_fwd', qk.data_ptr(), qk.data_ptr() + C * esz, v.data_ptr(), out.data_ptr(),
+                      lse.data_ptr(), 2 * C, 2 * C, C, C, None if bits is None else bits.data_ptr(),
+                      layout.G, heads, layout.S, Dh, layout.seq_stride, layout.hi_stride, layout.lo_stride,
+                      layout.n_lo, ctx.geom[3], _DTYPE_CODE[v.dtype], int(impl),
+                      dropout_state(x.device).data_ptr() if p > 0 else None,
+                      None if key is None else key.data_ptr(), ctx.site, float(p), _stream_ptr(x))
+        ctx.masks = (bits, bits_t)
+        ctx.has_pos = pos is not None
+        ctx.x_shape = x.shape
+        ctx.pos_shape = None if pos is None else pos.shape
+        ctx.save_for_backward(x2, xp, weight, qk, v, out, lse, *([key] if key is not None else []))
+        return out.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, dout):
+        x2, xp, weight, qk, v, out, lse = ctx.saved_tensors[:7]
+        key = ctx.saved_tensors[7] if len(ctx.saved_tensors) > 7 else None
+        layout, heads, Dh, scale, impl = ctx.geom
+        bits, bits_t = ctx.masks
+        rows, C = v.shape
+        dout = dout.reshape(rows, C).contiguous()
+        dqkv = torch.empty((rows, 3 * C), dtype=v.dtype, device=v.device)
+        delta = torch.empty_like(lse)
+        esz = qk.element_size()
+        with torch.cuda.device(v.device):
+            _lib.call('mha_bwd', qk.data_ptr(), qk.data_ptr() + C * esz, v.data_ptr(), out.data_ptr(),
+                      dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), dqkv.data_ptr(),
+                      dqkv.data_ptr() + C * esz, dqkv.data_ptr() + 2 * C * esz, 2 * C, 2 * C, C, C,
+                      3 * C, 3 * C, 3 * C, None if bits is None else bits.data_ptr(), None if bits_t is None else bits_t.data_ptr(),
+                      layout.G, heads, layout.S, Dh, layout.seq_stride, layout.hi_stride, layout.lo_stride,
+                      layout.n_lo, scale, _DTYPE_CODE[v.dtype], impl,
+                      None if key is None else key.data_ptr(), ctx.site, ctx.p, _stream_ptr(v))
+        dqk, dv = dqkv[:, :2 * C], dqkv[:, 2 * C:]
+        dx = dpos = dw = db = None
+        need_x, need_pos, need_w, need_b = ctx.needs_input_grad[:4]
+        if need_x or (need_pos and ctx.has_pos):
+            dxp = dqk @ weight[:2 * C]
+            if need_pos and ctx.has_pos:
+                dpos = dxp.view(ctx.pos_shape)
+            if need_x:
+                dx = torch.addmm(dxp, dv, weight[2 * C:]).view(ctx.x_shape)
+        if need_w:
+            dw = torch.empty_like(weight)
+            torch.mm(dqk.t(), xp, out=dw[:2 * C])
+            torch.mm(dv.t(), x2, out=dw[2 * C:])
+        if need_b:
+            db = column_sum(dqkv, weight.dtype) if _colsum_supported(dqkv) else dqkv.sum(0).to(weight.dtype)
+        return dx, dpos, dw, db, None, None, None, None, None
+
+
+def self_attention(x, pos, in_proj_weight, in_proj_bias, layout, heads, attn_mask=None, p=0.0, impl=IMPL_AUTO):
+    """``core(q, k, v)`` with q | k = (x + pos) Wqk^T + bqk and v = x Wv^T + bv from the packed in-projection
+    parameters of ``torch.nn.MultiheadAttention``; x, pos: (..., C) activations whose rows the layout describes."""
+    return SelfAttentionFunction.apply(x, pos, in_proj_weight, in_proj_bias, layout, int(heads),
+                                       pack_mask(attn_mask), float(p), int(impl))
 
 
 def self_attention_core(qk, v, layout, heads, attn_mask=None, p=0.0, impl=IMPL_AUTO):

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..mha import (batch_first_layout, inter_vector_layout, intra_vector_layout, self_attention_core,
+from ..mha import (batch_first_layout, inter_vector_layout, intra_vector_layout, self_attention,
                    sequence_first_layout, supported_impl)
 from ..registry import (ATTENTION, HAVE_MMCV, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE,
                         BaseModule, build_attention, build_transformer_layer)
@@ -30,7 +30,7 @@ def _mask_ok(attn_mask, S):
 class FusedSelfAttentionMixin:
     """The self-attention of an mmcv-convention ``MultiheadAttention`` (``self.attn`` = a
     ``torch.nn.MultiheadAttention``, ``self.dropout_layer``, ``self.proj_drop``) on the sm_100a kernels of
-    ``csrc/mha.cu``: in-projection GEMMs (q | k from x + pos, v from x), the fused attention core over the
+    ``csrc/mha.cu``: in-projection GEMMs (q | k from x + pos, v from x) and the fused attention core over the
     token layout, then ``identity + dropout(out_proj(.))`` -- with the layer's next LayerNorm folded into
     the same node when the caller hands it over (``post_norm``).  Parameters and their names are those of
     ``torch.nn.MultiheadAttention`` (checkpoints load unchanged)."""
@@ -51,15 +51,11 @@ class FusedSelfAttentionMixin:
     def fused_self_attention(self, x, pos, layout, attn_mask=None, identity=None, post_norm=None):
         """x, pos, identity: (..., C) activations whose flattened rows the layout describes."""
         a = self.attn
-        C = a.embed_dim
         if identity is None:
             identity = x
-        xp = x if pos is None else x + pos
-        w, b = a.in_proj_weight, a.in_proj_bias
-        qk = linear(xp, w[:2 * C], b[:2 * C])
-        v = linear(x, w[2 * C:], b[2 * C:])
         p_attn = float(a.dropout) if self.training else 0.0
-        o = self_attention_core(qk.view(-1, 2 * C), v.view(-1, C), layout, a.num_heads, attn_mask, p_attn)
+        # in-projection + attention core as one autograd node (mha.SelfAttentionFunction)
+        o = self_attention(x, pos, a.in_proj_weight, a.in_proj_bias, layout, a.num_heads, attn_mask, p_attn)
         p_out = float(getattr(self.dropout_layer, 'p', 0.0)) if self.training else 0.0
         if post_norm is not None:
             return linear_add_layernorm(o.view(identity.shape), a.out_proj, identity, post_norm, p_out)

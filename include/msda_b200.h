@@ -397,7 +397,9 @@ int linear_wgrad(const void* dy, const void* x, void* dW, void* db, float* works
  *              the second matrix is the transpose; NULL = no mask.  A row with no admissible key yields 0.
  *   lse        (G * H, S) fp32, written by the forward: log sum exp of the row's scaled scores.
  *   delta      (G * H, S) fp32 scratch of the backward (rowsum(grad_out * out)).
- *   dq, dk, dv have the layout (and ld) of q, k, v; every element of a token row's head slice is written.
+ *   dq, dk, dv have the token layout of q, k, v and their own row strides ld_dq / ld_dk / ld_dv (0 = those of
+ *              q / k / v; one (rows, 3C) buffer can receive dq | dk | dv); every element of a token row's head
+ *              slice is written.
  *   dropout    on the attention weights, counter-based and recomputed in the backward (rng_state,
  *              key_save / key, site, p: as in ln_residual_dropout_fwd).  mha_keep_mask() writes the keep
  *              mask ((G * H, S, S) bytes) for tests.
@@ -410,7 +412,8 @@ int mha_fwd(const void* q, const void* k, const void* v, void* out, float* lse, 
             int impl, const void* rng_state, void* key_save, uint32_t site, float p, void* stream);
 int mha_bwd(const void* q, const void* k, const void* v, const void* out, const void* grad_out,
             const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t ldq, int64_t ldk,
-            int64_t ldv, int64_t ldo, const uint32_t* mask_bits, const uint32_t* mask_bits_t, int G, int H,
+            int64_t ldv, int64_t ldo, int64_t ld_dq, int64_t ld_dk, int64_t ld_dv,
+            const uint32_t* mask_bits, const uint32_t* mask_bits_t, int G, int H,
             int S, int Dh, int64_t seq_stride, int64_t hi_stride, int64_t lo_stride, int n_lo, float scale,
             int dtype, int impl, const void* key, uint32_t site, float p, void* stream);
 int mha_keep_mask(uint8_t* keep, int P, int S, const void* key, uint32_t site, float p, void* stream);
