@@ -9,7 +9,7 @@ when that library is missing.
 """
 from . import _lib
 from ._lib import build, launch_count
-from . import bev_prep, fused_ops, mha, modules, parallel, registry, rowops, synthetic
+from . import bev_prep, dcnv3, fused_ops, mha, modules, parallel, registry, rowops, synthetic
 from .fused_ops import (QueueDeformAttnFunction, SpatialCrossAttnFunction, bev_point_sampling)
 from .registry import (ATTENTION, TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, build_attention,
                        build_transformer_layer, build_transformer_layer_sequence)

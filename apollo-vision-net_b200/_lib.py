@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 # APOLLO_B200_LIB: load another build of the same ABI (kernel experiments, tools/dev_variants.sh)
 LIB_PATH = os.environ.get('APOLLO_B200_LIB') or os.path.join(_HERE, 'libmsda_b200.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'msda_b200.h')
-SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'coarse_scatter.cu', 'rowops.cu', 'bev_prep.cu', 'wgrad.cu', 'mha.cu']
+SOURCES = ['abi.cu', 'msda_fwd.cu', 'msda_bwd.cu', 'point_sampling.cu', 'fused.cu', 'coarse_scatter.cu', 'rowops.cu', 'bev_prep.cu', 'wgrad.cu', 'mha.cu', 'dcnv3.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -63,11 +63,14 @@ _SIGNATURES = {
                          _c_vp, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
     'mha_bwd': (_c_int, [_c_vp] * 10 + [_c_i64] * 7 + [_c_vp, _c_vp] + [_c_int] * 4 + [_c_i64] * 3 +
                 [_c_int, _c_f, _c_int, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
+    'dcnv3_scratch_floats': (_c_i64, [_c_int] * 7),
+    'dcnv3_fwd': (_c_int, [_c_vp] * 5 + [_c_int] * 15 + [_c_f, _c_int, _c_vp]),
+    'dcnv3_bwd': (_c_int, [_c_vp] * 8 + [_c_int] * 15 + [_c_f, _c_int, _c_vp]),
     'mha_keep_mask': (_c_int, [_c_vp, _c_int, _c_int, _c_vp, ctypes.c_uint32, _c_f, _c_vp]),
 }
 
 _lib = None
-ABI_VERSION = 6          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
+ABI_VERSION = 7          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
 
 
 def _stale():

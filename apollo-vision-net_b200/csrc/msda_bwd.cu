@@ -30,7 +30,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     const CT* __restrict__ attn, const T* __restrict__ grad_out,
                     float* __restrict__ g_value, float* __restrict__ g_loc,
                     float* __restrict__ g_attn,
-                    int Nk, int M, int Dh, int L, int Nq, int P, long long total_rows) {
+                    int Nk, int M, int Dh, int L, int Nq, int P, long long total_rows, float pixel_scale) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int ROWS = kBwdThreads / TPH;
   __shared__ LevelTable lv;
@@ -124,7 +124,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float lx = to_f32<CT>(my_loc[2 * s]);
       const float ly = to_f32<CT>(my_loc[2 * s + 1]);
       const float a = active ? to_f32<CT>(my_att[s]) : 0.f;
-      const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      const Corners c = corner_setup(lx, ly, H, W, pix_stride, pixel_scale > 0.f);
       const T* vb = vhead + loff;
       float* gb = ghead + loff;
       const uint4 u00 = ldg128(vb + c.o00);
@@ -177,7 +177,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       if (active && chunk == 0) {
         g_attn[row * LP + s] = ga;
         *reinterpret_cast<float2*>(g_loc + (row * LP + s) * 2) =
-            make_float2((float)W * a * gx, (float)H * a * gy);
+            make_float2((pixel_scale > 0.f ? pixel_scale : (float)W) * a * gx,
+                        (pixel_scale > 0.f ? pixel_scale : (float)H) * a * gy);
       }
     }
   }
@@ -191,7 +192,7 @@ msda_bwd_scalar_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
                        const CT* __restrict__ attn, const T* __restrict__ grad_out,
                        float* __restrict__ g_value, float* __restrict__ g_loc,
                        float* __restrict__ g_attn,
-                       int Nk, int M, int Dh, int L, int Nq, int P, long long total) {
+                       int Nk, int M, int Dh, int L, int Nq, int P, long long total, float pixel_scale) {
   __shared__ LevelTable lv;
   load_level_table(lv, shapes, starts, L);
   __syncthreads();
@@ -207,7 +208,8 @@ msda_bwd_scalar_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
   const int pix_stride = M * Dh;
   const size_t voff = ((size_t)b * Nk * M + m) * Dh + (size_t)lv.start[l] * pix_stride;
   const float a = to_f32<CT>(attn[idx]);
-  const Bilinear bl = bilinear_setup(to_f32<CT>(loc[2 * idx]), to_f32<CT>(loc[2 * idx + 1]), H, W);
+  const Bilinear bl = bilinear_setup(to_f32<CT>(loc[2 * idx]), to_f32<CT>(loc[2 * idx + 1]), H, W,
+                                     pixel_scale > 0.f);
   const float hw = 1.f - bl.lw, hh = 1.f - bl.lh;
   const long long o00 = (long long)voff + ((long long)bl.y0 * W + bl.x0) * pix_stride;
   const long long o01 = o00 + pix_stride, o10 = o00 + (long long)W * pix_stride, o11 = o10 + pix_stride;
@@ -223,8 +225,8 @@ msda_bwd_scalar_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     if (c11) { d11 = fmaf(to_f32<T>(value[o11 + c]), g, d11); atomicAdd(g_value + o11 + c, a * w11 * g); }
   }
   g_attn[idx] = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
-  g_loc[2 * idx] = (float)W * a * (hh * (d01 - d00) + bl.lh * (d11 - d10));
-  g_loc[2 * idx + 1] = (float)H * a * (hw * (d10 - d00) + bl.lw * (d11 - d01));
+  g_loc[2 * idx] = (pixel_scale > 0.f ? pixel_scale : (float)W) * a * (hh * (d01 - d00) + bl.lh * (d11 - d10));
+  g_loc[2 * idx + 1] = (pixel_scale > 0.f ? pixel_scale : (float)H) * a * (hw * (d10 - d00) + bl.lw * (d11 - d01));
 }
 
 template <typename T, typename CT, int TPH>
@@ -242,11 +244,11 @@ static int launch_vec(const Problem& pr, cudaStream_t st) {
   if (smem <= 40 * 1024) {
     msda_bwd_vec_kernel<T, CT, TPH, true><<<(unsigned)grid, kBwdThreads, smem, st>>>(
         v, pr.shapes, pr.starts, lo, at, go, pr.g_value, pr.g_loc, pr.g_attn,
-        pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows);
+        pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows, pr.pixel_scale);
   } else {
     msda_bwd_vec_kernel<T, CT, TPH, false><<<(unsigned)grid, kBwdThreads, 0, st>>>(
         v, pr.shapes, pr.starts, lo, at, go, pr.g_value, pr.g_loc, pr.g_attn,
-        pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows);
+        pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows, pr.pixel_scale);
   }
   count_launch();
   return check_launch("msda_bwd");
@@ -276,7 +278,7 @@ static int launch_bwd_typed(const Problem& pr, cudaStream_t st) {
   msda_bwd_scalar_kernel<T, CT><<<(unsigned)grid, 256, 0, st>>>(
       static_cast<const T*>(pr.value), pr.shapes, pr.starts, static_cast<const CT*>(pr.loc),
       static_cast<const CT*>(pr.attn), static_cast<const T*>(pr.grad_out), pr.g_value, pr.g_loc,
-      pr.g_attn, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, total);
+      pr.g_attn, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, total, pr.pixel_scale);
   count_launch();
   return check_launch("msda_bwd(scalar)");
 }

@@ -247,10 +247,12 @@ struct Bilinear {
   bool vx0, vx1, vy0, vy1;
 };
 
-__device__ __forceinline__ Bilinear bilinear_setup(float loc_x, float loc_y, int H, int W) {
+// `pixel`: the location already is the pixel coordinate (the DCNv3 entry points, which state their sampling
+// positions in pixels of the input map: no normalise / de-normalise round trip).
+__device__ __forceinline__ Bilinear bilinear_setup(float loc_x, float loc_y, int H, int W, bool pixel = false) {
   Bilinear b;
-  const float x = loc_x * (float)W - 0.5f;
-  const float y = loc_y * (float)H - 0.5f;
+  const float x = pixel ? loc_x : loc_x * (float)W - 0.5f;
+  const float y = pixel ? loc_y : loc_y * (float)H - 0.5f;
   b.in_range = (y > -1.0f) && (x > -1.0f) && (y < (float)H) && (x < (float)W);
   const float xf = floorf(x), yf = floorf(y);
   b.x0 = (int)xf;
@@ -276,10 +278,10 @@ struct Corners {
 
 // `px` receives the (clamped) pixel indices of the four corners inside the level (row-major).
 __device__ __forceinline__ Corners corner_setup_px(float loc_x, float loc_y, int H, int W, int pix_stride,
-                                                   int (&px)[4]) {
+                                                   int (&px)[4], bool pixel = false) {
   Corners c;
-  const float x = loc_x * (float)W - 0.5f;
-  const float y = loc_y * (float)H - 0.5f;
+  const float x = pixel ? loc_x : loc_x * (float)W - 0.5f;
+  const float y = pixel ? loc_y : loc_y * (float)H - 0.5f;
   const bool in = (y > -1.0f) && (x > -1.0f) && (y < (float)H) && (x < (float)W);
   const float xf = floorf(x), yf = floorf(y);
   const int x0 = (int)xf, y0 = (int)yf;             // cvt saturates; NaN -> 0
@@ -305,9 +307,10 @@ __device__ __forceinline__ Corners corner_setup_px(float loc_x, float loc_y, int
             ((unsigned)(vy1 && vx1) << 3);
   return c;
 }
-__device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H, int W, int pix_stride) {
+__device__ __forceinline__ Corners corner_setup(float loc_x, float loc_y, int H, int W, int pix_stride,
+                                                bool pixel = false) {
   int px[4];
-  return corner_setup_px(loc_x, loc_y, H, W, pix_stride, px);
+  return corner_setup_px(loc_x, loc_y, H, W, pix_stride, px, pixel);
 }
 
 }  // namespace msda

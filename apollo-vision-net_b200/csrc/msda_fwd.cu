@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ starts, const CT* __restrict__ loc,
                     const CT* __restrict__ attn, T* __restrict__ out,
-                    int Nk, int M, int Dh, int L, int Nq, int P, long long total_rows) {
+                    int Nk, int M, int Dh, int L, int Nq, int P, long long total_rows, float pixel_scale) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int ROWS = kFwdThreads / TPH;      // (b, q, m) rows per CTA
   __shared__ LevelTable lv;
@@ -96,7 +96,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       // invalid corner of a partly valid sample clamps onto the pixel of one of its valid corners;
       // a sample entirely outside the map reads nothing (predicated loads), so a non-finite value only reaches the samples
       // that touch it (the reference kernel never reads such corners)
-      const Corners c = corner_setup(lx, ly, H, W, pix_stride);
+      const Corners c = corner_setup(lx, ly, H, W, pix_stride, pixel_scale > 0.f);
       const bool touch = c.valid != 0u;
       const uint4 u00 = ldg128_if(lbase + c.o00, touch);
       const uint4 u01 = ldg128_if(lbase + c.o01, touch);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256)
 msda_fwd_scalar_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                        const int64_t* __restrict__ starts, const CT* __restrict__ loc,
                        const CT* __restrict__ attn, T* __restrict__ out,
-                       int Nk, int M, int Dh, int L, int Nq, int P, long long total) {
+                       int Nk, int M, int Dh, int L, int Nq, int P, long long total, float pixel_scale) {
   __shared__ LevelTable lv;
   load_level_table(lv, shapes, starts, L);
   __syncthreads();
@@ -156,7 +156,8 @@ msda_fwd_scalar_kernel(const T* __restrict__ value, const int64_t* __restrict__ 
     const T* lbase = vbase + (size_t)lv.start[l] * pix_stride;
     for (int p = 0; p < P; ++p) {
       const int s = l * P + p;
-      const Bilinear bl = bilinear_setup(to_f32<CT>(my_loc[2 * s]), to_f32<CT>(my_loc[2 * s + 1]), H, W);
+      const Bilinear bl = bilinear_setup(to_f32<CT>(my_loc[2 * s]), to_f32<CT>(my_loc[2 * s + 1]), H, W,
+                                         pixel_scale > 0.f);
       const float a = to_f32<CT>(my_att[s]);
       const float hw = 1.f - bl.lw, hh = 1.f - bl.lh;
       const T* p00 = lbase + ((long long)bl.y0 * W + bl.x0) * pix_stride;
@@ -185,10 +186,10 @@ static int launch_vec(const Problem& pr, cudaStream_t st) {
   T* o = static_cast<T*>(pr.out);
   if (smem <= 40 * 1024) {
     msda_fwd_vec_kernel<T, CT, TPH, true><<<(unsigned)grid, kFwdThreads, smem, st>>>(
-        v, pr.shapes, pr.starts, lo, at, o, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows);
+        v, pr.shapes, pr.starts, lo, at, o, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows, pr.pixel_scale);
   } else {
     msda_fwd_vec_kernel<T, CT, TPH, false><<<(unsigned)grid, kFwdThreads, 0, st>>>(
-        v, pr.shapes, pr.starts, lo, at, o, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows);
+        v, pr.shapes, pr.starts, lo, at, o, pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq, pr.P, rows, pr.pixel_scale);
   }
   count_launch();
   return check_launch("msda_fwd");
@@ -216,7 +217,7 @@ static int launch_fwd_typed(const Problem& pr, cudaStream_t st) {
   msda_fwd_scalar_kernel<T, CT><<<(unsigned)grid, 256, 0, st>>>(
       static_cast<const T*>(pr.value), pr.shapes, pr.starts, static_cast<const CT*>(pr.loc),
       static_cast<const CT*>(pr.attn), static_cast<T*>(pr.out), pr.Nk, pr.M, pr.Dh, pr.L, pr.Nq,
-      pr.P, total);
+      pr.P, total, pr.pixel_scale);
   count_launch();
   return check_launch("msda_fwd(scalar)");
 }

@@ -20,6 +20,9 @@ struct Problem {
   float* g_attn = nullptr;
   int B = 0, Nk = 0, M = 0, Dh = 0, L = 0, Nq = 0, P = 0;
   int value_dtype = MSDA_F32, coord_dtype = MSDA_F32;
+  // > 0: `loc` holds PIXEL coordinates of the (single) level and the location gradient is multiplied by this
+  // factor instead of the level size (the DCNv3 entry points: factor = offset_scale)
+  float pixel_scale = 0.f;
 };
 
 // Arguments of the fused attention cores (sca_* / tsa_*).

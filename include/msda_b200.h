@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 6
+#define MSDA_ABI_VERSION 7
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -417,6 +417,33 @@ int mha_bwd(const void* q, const void* k, const void* v, const void* out, const 
             int S, int Dh, int64_t seq_stride, int64_t hi_stride, int64_t lo_stride, int n_lo, float scale,
             int dtype, int impl, const void* key, uint32_t site, float p, void* stream);
 int mha_keep_mask(uint8_t* keep, int P, int S, const void* key, uint32_t site, float p, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * DCNv3: replaces the compiled `DCNv3` extension of the reference,
+ *   dcnv3_forward / dcnv3_backward (projects/mmdet3d_plugin/bevformer/backbones/ops_dcnv3/src/dcnv3.h:21-59,
+ *   src/cuda/dcnv3_cuda.cu:28-173), bound by functions/dcnv3_func.py:16, :41-46, :55-60.
+ *
+ *   input   (N, H_in, W_in, group * group_channels)              dtype, channels-last, contiguous
+ *   offset  (N, H_out, W_out, group * kernel_h * kernel_w * 2)   dtype, (w, h) pairs, kernel_w outer loop
+ *   mask    (N, H_out, W_out, group * kernel_h * kernel_w)       dtype
+ *   output  (N, H_out, W_out, group * group_channels)            dtype, fully overwritten
+ *   H_out = (H_in + 2 pad_h - (dilation_h (kernel_h - 1) + 1)) / stride_h + 1 (validated, as the reference does)
+ *   scratch dcnv3_scratch_floats() fp32 values (sampling positions in pixels; an fp32 copy of the mask for
+ *           16-bit dtypes; the level table), caller-owned, rewritten by every call
+ * Backward: grad_input is an fp32 ACCUMULATOR the caller zero-fills (the reference allocates it with
+ *   at::zeros_like, dcnv3_cuda.cu:112); grad_offset / grad_mask fp32, every element written once.
+ * The reference's im2col_step batching has no meaning here and is not an argument.  offset_scale > 0.
+ * ------------------------------------------------------------------------------- */
+int64_t dcnv3_scratch_floats(int N, int H_out, int W_out, int group, int kernel_h, int kernel_w, int dtype);
+int dcnv3_fwd(const void* input, const void* offset, const void* mask, void* output, float* scratch, int N,
+              int H_in, int W_in, int H_out, int W_out, int kernel_h, int kernel_w, int stride_h, int stride_w,
+              int pad_h, int pad_w, int dilation_h, int dilation_w, int group, int group_channels,
+              float offset_scale, int dtype, void* stream);
+int dcnv3_bwd(const void* input, const void* offset, const void* mask, const void* grad_output,
+              float* grad_input, float* grad_offset, float* grad_mask, float* scratch, int N, int H_in, int W_in,
+              int H_out, int W_out, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+              int dilation_h, int dilation_w, int group, int group_channels, float offset_scale, int dtype,
+              void* stream);
 
 #ifdef __cplusplus
 }

@@ -397,3 +397,28 @@ def load_reference():
         ATTENTION=ATTENTION, LAYER=LAYER, LAYER_SEQ=LAYER_SEQ, build_attention=build_attention,
         modules=dict(tsa=tsa, sca=sca, enc=enc, dec=dec, fn=fn_mod, trf=trf, mapdec=mapdec))
     return _loaded
+
+
+def load_reference_dcnv3():
+    """The reference's ``ops_dcnv3/functions/dcnv3_func.py`` (unmodified, executed from /root/reference) with a
+    stand-in for its compiled ``DCNv3`` extension, which cannot be built here: only the pure-PyTorch
+    ``dcnv3_core_pytorch`` (:119-188, "for debug and test only") is usable, and that is what the DCNv3 golden
+    vectors are generated with."""
+    import importlib.util
+    import types
+    path = os.path.join(REFERENCE_ROOT, 'projects', 'mmdet3d_plugin', 'bevformer', 'backbones', 'ops_dcnv3',
+                        'functions', 'dcnv3_func.py')
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
+    saved = sys.modules.get('DCNv3')
+    sys.modules['DCNv3'] = types.ModuleType('DCNv3')
+    try:
+        spec = importlib.util.spec_from_file_location('_reference_dcnv3_func', path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop('DCNv3', None)
+        else:
+            sys.modules['DCNv3'] = saved
+    return mod

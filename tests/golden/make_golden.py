@@ -397,6 +397,33 @@ def bev_features_case(ref, gen):
     return res
 
 
+def dcnv3_case(gen):
+    """DCNv3 through the reference's own pure-PyTorch ``dcnv3_core_pytorch`` (ops_dcnv3/functions/dcnv3_func.py:
+    119-188), forward and autograd gradients: a 3x3 kernel with padding (the backbone's configuration,
+    modules/dcnv3.py:216-345) and a strided, dilated, rectangular-kernel case without padding."""
+    from oracle.refshim import load_reference_dcnv3
+    fn = load_reference_dcnv3().dcnv3_core_pytorch
+    res = {}
+    for tag, (N, H, W, G, Cg, kh, kw, sh, sw, ph, pw, dh, dw, scale) in {
+            'a': (2, 9, 11, 4, 8, 3, 3, 1, 1, 1, 1, 1, 1, 1.0),
+            'b': (1, 13, 10, 2, 16, 3, 2, 2, 1, 0, 0, 2, 1, 0.7)}.items():
+        Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+        Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+        K = kh * kw
+        x = torch.randn(N, H, W, G * Cg, generator=gen, requires_grad=True)
+        off = (torch.randn(N, Ho, Wo, G * K * 2, generator=gen) * 1.5).requires_grad_(True)
+        msk = torch.softmax(torch.randn(N, Ho, Wo, G, K, generator=gen), -1).reshape(N, Ho, Wo, G * K).requires_grad_(True)
+        go = torch.randn(N, Ho, Wo, G * Cg, generator=gen)
+        out = fn(x, off, msk, kh, kw, sh, sw, ph, pw, dh, dw, G, Cg, scale)
+        out.backward(go)
+        res.update({f'{tag}.cfg': np.array([kh, kw, sh, sw, ph, pw, dh, dw, G, Cg], dtype=np.int64),
+                    f'{tag}.offset_scale': np.array(scale, dtype=np.float64),
+                    f'{tag}.input': _np(x), f'{tag}.offset': _np(off), f'{tag}.mask': _np(msk),
+                    f'{tag}.grad_output': _np(go), f'{tag}.output': _np(out), f'{tag}.grad_input': _np(x.grad),
+                    f'{tag}.grad_offset': _np(off.grad), f'{tag}.grad_mask': _np(msk.grad)})
+    return res
+
+
 def main():
     ref = load_reference()
     gen = torch.Generator().manual_seed(20261018)
@@ -411,6 +438,7 @@ def main():
         'det_decoder_small': det_decoder_case(ref, gen),
         'maptrv2_decoder_small': maptrv2_decoder_case(ref, gen),
         'encoder_small': encoder_case(ref, gen),
+        'dcnv3_small': dcnv3_case(torch.Generator().manual_seed(20261019)),
     }
     only = sys.argv[1:]                                # optional: names of the cases to (re)write
     for name, arrays in cases.items():
