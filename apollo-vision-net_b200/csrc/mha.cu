@@ -592,10 +592,10 @@ __device__ __forceinline__ void load_row(float (&f)[DH], const void* base, long 
   }
 }
 template <int DH> __device__ __forceinline__ float dot_row(const float (&x)[DH], const float (&y)[DH]) {
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};             // four independent chains instead of DH dependent FMAs
 #pragma unroll
-  for (int i = 0; i < DH; ++i) s = fmaf(x[i], y[i], s);
-  return s;
+  for (int i = 0; i < DH; ++i) s[i & 3] = fmaf(x[i], y[i], s[i & 3]);
+  return (s[0] + s[1]) + (s[2] + s[3]);
 }
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll
@@ -613,18 +613,37 @@ __device__ __forceinline__ void weighted_rows(float (&acc)[(DH + 31) / 32], cons
                                               long long gbase, long long seq_stride, long long ld, int h, int S,
                                               int lane) {
   constexpr int NJ = (DH + 31) / 32;
+  float part[4][NJ];                             // four tokens per iteration, four independent chains
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) part[u][j] = 0.f;
   const T* p = static_cast<const T*>(base) + gbase * ld + h * DH;
-  for (int t = 0; t < S; ++t) {
+  const long long step = seq_stride * ld;
+  int t = 0;
+  for (; t + 4 <= S; t += 4) {
+    const float4 wt = *reinterpret_cast<const float4*>(w + t);       // w is 16-byte aligned, t a multiple of 4
+    const T* row = p + (long long)t * step;
+    const float wv[4] = {wt.x, wt.y, wt.z, wt.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int d = lane + 32 * j;
+        if (d < DH) part[u][j] = fmaf(wv[u], to_f32(row[u * step + d]), part[u][j]);
+      }
+  }
+  for (; t < S; ++t) {
     const float wt = w[t];
-    const T* row = p + (long long)t * seq_stride * ld;
+    const T* row = p + (long long)t * step;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int d = lane + 32 * j;
-      if (d < DH) acc[j] = fmaf(wt, to_f32(row[d]), acc[j]);
+      if (d < DH) part[0][j] = fmaf(wt, to_f32(row[d]), part[0][j]);
     }
   }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) acc[j] = (part[0][j] + part[1][j]) + (part[2][j] + part[3][j]);
 }
 template <typename T, int DH>
 __device__ __forceinline__ void store_dims(void* base, long long row, long long ld, int h,

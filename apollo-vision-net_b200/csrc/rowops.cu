@@ -419,7 +419,11 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
   if (smem + 1024 > 48 * 1024 &&        // (+ the kernel's static shared memory)
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return set_error(MSDA_ERR_CUDA, "ln_bwd: cannot reserve %zu bytes of shared memory", smem);
-  kfn<<<row_grid(), kRowThreads, smem, st>>>(
+  // every CTA ends with a reduction of its column partials into the L2 strip: with few rows (the decoders'
+  // 7 000 queries) fewer CTAs, four rows per warp, keep that fixed cost from dominating
+  const long long want = (rows + 4 * (kRowThreads / 32) - 1) / (4 * (kRowThreads / 32));
+  const int bgrid = (int)(want < row_grid() ? (want > 0 ? want : 1) : row_grid());
+  kfn<<<bgrid, kRowThreads, smem, st>>>(
       static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<const T*>(gamma), mean, rstd,
       static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C, static_cast<T*>(dx_masked), da);
   count_launch();
