@@ -656,6 +656,43 @@ __device__ __forceinline__ void store_dims(void* base, long long row, long long 
   }
 }
 
+// 32 token rows [t0, t0 + 32) of one (group, head) -> a shared tile [32][DH + 1] fp32 (coalesced loads; the
+// padded row stride makes "lane = token" reads conflict-free); rows beyond S are zero
+template <typename T, int DH>
+__device__ __forceinline__ void stage_rows(float* dst, const void* base, long long ld, long long gbase,
+                                           long long seq_stride, int h, int t0, int S) {
+  const T* p = static_cast<const T*>(base) + gbase * ld + h * DH;
+  for (int i = threadIdx.x; i < 32 * DH; i += kMhaThreads) {
+    const int row = i / DH, d = i % DH, t = t0 + row;
+    dst[row * (DH + 1) + d] = t < S ? to_f32(p[(long long)t * seq_stride * ld + d]) : 0.f;
+  }
+}
+template <int DH> __device__ __forceinline__ float dot_tile(const float (&x)[DH], const float* row) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < DH; ++i) s[i & 3] = fmaf(x[i], row[i], s[i & 3]);
+  return (s[0] + s[1]) + (s[2] + s[3]);
+}
+
+// A CTA owns 8 consecutive rows of one problem (one warp per row); the other side of the score matrix
+// streams through shared memory in tiles of 32 tokens shared by the 8 warps.
+struct SimtItem {
+  int p, r, g, h;
+  bool valid;
+  long long gbase;
+};
+__device__ __forceinline__ SimtItem simt_item(const MhaArgs& a) {
+  const int nblk = (a.S + kMhaWarps - 1) / kMhaWarps;
+  SimtItem it;
+  it.p = blockIdx.x / nblk;
+  it.r = (blockIdx.x % nblk) * kMhaWarps + (threadIdx.x >> 5);
+  it.valid = it.r < a.S;
+  it.g = it.p / a.H;
+  it.h = it.p % a.H;
+  it.gbase = group_base(a, it.g);
+  return it;
+}
+
 template <typename T, int DH, bool DROP>
 __global__ void __launch_bounds__(kMhaThreads) mha_fwd_simt_kernel(const MhaArgs a, int S_round) {
   extern __shared__ __align__(16) unsigned char mha_smem[];
@@ -669,23 +706,29 @@ __global__ void __launch_bounds__(kMhaThreads) mha_fwd_simt_kernel(const MhaArgs
     }
     rkey = mha_stream_key(seed, step, a.site);
   }
-  const long long item = (long long)blockIdx.x * kMhaWarps + warp;
-  if (item >= (long long)a.G * a.H * a.S) return;
-  const int p = (int)(item / a.S), q = (int)(item % a.S), g = p / a.H, h = p % a.H;
-  const long long gbase = group_base(a, g);
-  float* sc = reinterpret_cast<float*>(mha_smem) + (size_t)warp * S_round;
+  const SimtItem it = simt_item(a);
+  const int p = it.p, q = it.r, h = it.h;
+  float* tile = reinterpret_cast<float*>(mha_smem);
+  float* sc = tile + 32 * (DH + 1) + (size_t)warp * S_round;
   float qr[DH];
-  load_row<T, DH>(qr, a.q, gbase + (long long)q * a.seq_stride, a.ldq, h);
-  const uint32_t* mrow = a.mask_bits ? a.mask_bits + (long long)q * a.mask_words : nullptr;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) qr[i] = 0.f;
+  if (it.valid) load_row<T, DH>(qr, a.q, it.gbase + (long long)q * a.seq_stride, a.ldq, h);
+  const uint32_t* mrow = (a.mask_bits && it.valid) ? a.mask_bits + (long long)q * a.mask_words : nullptr;
   float mx = -INFINITY;
-  for (int k = lane; k < a.S; k += 32) {
-    float kr[DH];
-    load_row<T, DH>(kr, a.k, gbase + (long long)k * a.seq_stride, a.ldk, h);
-    float s = dot_row<DH>(qr, kr) * a.scale;
-    if (mrow != nullptr && ((__ldg(mrow + (k >> 5)) >> (k & 31)) & 1u)) s = -INFINITY;
-    sc[k] = s;
-    mx = fmaxf(mx, s);
+  for (int t0 = 0; t0 < a.S; t0 += 32) {
+    __syncthreads();
+    stage_rows<T, DH>(tile, a.k, a.ldk, it.gbase, a.seq_stride, h, t0, a.S);
+    __syncthreads();
+    const int k = t0 + lane;
+    if (it.valid && k < a.S) {
+      float s = dot_tile<DH>(qr, tile + lane * (DH + 1)) * a.scale;
+      if (mrow != nullptr && ((__ldg(mrow + (k >> 5)) >> (k & 31)) & 1u)) s = -INFINITY;
+      sc[k] = s;
+      mx = fmaxf(mx, s);
+    }
   }
+  if (!it.valid) return;                       // no block-wide barrier below
   mx = warp_max_f(mx);
   const float mu = mx == -INFINITY ? 0.f : mx;
   float l = 0.f;
@@ -704,8 +747,8 @@ __global__ void __launch_bounds__(kMhaThreads) mha_fwd_simt_kernel(const MhaArgs
   }
   __syncwarp();
   float acc[(DH + 31) / 32];
-  weighted_rows<T, DH>(acc, sc, a.v, gbase, a.seq_stride, a.ldv, h, a.S, lane);
-  store_dims<T, DH>(a.out, gbase + (long long)q * a.seq_stride, a.ldo, h, acc, lane);
+  weighted_rows<T, DH>(acc, sc, a.v, it.gbase, a.seq_stride, a.ldv, h, a.S, lane);
+  store_dims<T, DH>(a.out, it.gbase + (long long)q * a.seq_stride, a.ldo, h, acc, lane);
 }
 
 // pass A: one warp per query -> dQ row and delta
@@ -715,37 +758,45 @@ __global__ void __launch_bounds__(kMhaThreads) mha_bwd_dq_simt_kernel(const MhaA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t rkey = 0u;
   if (DROP) rkey = mha_stream_key(a.key[0], a.key[1], a.site);
-  const long long item = (long long)blockIdx.x * kMhaWarps + warp;
-  if (item >= (long long)a.G * a.H * a.S) return;
-  const int p = (int)(item / a.S), q = (int)(item % a.S), g = p / a.H, h = p % a.H;
-  const long long gbase = group_base(a, g), qrow = gbase + (long long)q * a.seq_stride;
-  float* sc = reinterpret_cast<float*>(mha_smem) + (size_t)warp * S_round;
+  const SimtItem it = simt_item(a);
+  const int p = it.p, q = it.r, h = it.h;
+  const long long qrow = it.gbase + (long long)q * a.seq_stride;
+  float* tk = reinterpret_cast<float*>(mha_smem);
+  float* tv = tk + 32 * (DH + 1);
+  float* sc = tv + 32 * (DH + 1) + (size_t)warp * S_round;
   float qr[DH], dor[DH];
-  load_row<T, DH>(qr, a.q, qrow, a.ldq, h);
-  load_row<T, DH>(dor, a.dout, qrow, a.ldo, h);
-  float delta;
-  {
+#pragma unroll
+  for (int i = 0; i < DH; ++i) qr[i] = dor[i] = 0.f;
+  float delta = 0.f, lse = INFINITY;
+  if (it.valid) {
+    load_row<T, DH>(qr, a.q, qrow, a.ldq, h);
+    load_row<T, DH>(dor, a.dout, qrow, a.ldo, h);
     float orow[DH];
     load_row<T, DH>(orow, a.o, qrow, a.ldo, h);
     delta = dot_row<DH>(dor, orow);
+    lse = a.lse[(long long)p * a.S + q];
+    if (lane == 0) a.delta[(long long)p * a.S + q] = delta;
   }
-  const float lse = a.lse[(long long)p * a.S + q];
-  if (lane == 0) a.delta[(long long)p * a.S + q] = delta;
-  const uint32_t* mrow = a.mask_bits ? a.mask_bits + (long long)q * a.mask_words : nullptr;
-  for (int k = lane; k < a.S; k += 32) {
-    float kr[DH];
-    load_row<T, DH>(kr, a.k, gbase + (long long)k * a.seq_stride, a.ldk, h);
-    const float s = dot_row<DH>(qr, kr) * a.scale;
-    const bool masked = mrow != nullptr && ((__ldg(mrow + (k >> 5)) >> (k & 31)) & 1u);
-    const float pv = masked ? 0.f : expf(s - lse);
-    load_row<T, DH>(kr, a.v, gbase + (long long)k * a.seq_stride, a.ldv, h);
-    float dp = dot_row<DH>(dor, kr);
-    if (DROP) dp = mha_keep((uint32_t)p, q, k, rkey, a.thresh) ? dp * a.inv_keep : 0.f;
-    sc[k] = pv * (dp - delta) * a.scale;
+  const uint32_t* mrow = (a.mask_bits && it.valid) ? a.mask_bits + (long long)q * a.mask_words : nullptr;
+  for (int t0 = 0; t0 < a.S; t0 += 32) {
+    __syncthreads();
+    stage_rows<T, DH>(tk, a.k, a.ldk, it.gbase, a.seq_stride, h, t0, a.S);
+    stage_rows<T, DH>(tv, a.v, a.ldv, it.gbase, a.seq_stride, h, t0, a.S);
+    __syncthreads();
+    const int k = t0 + lane;
+    if (it.valid && k < a.S) {
+      const float s = dot_tile<DH>(qr, tk + lane * (DH + 1)) * a.scale;
+      const bool masked = mrow != nullptr && ((__ldg(mrow + (k >> 5)) >> (k & 31)) & 1u);
+      const float pv = masked ? 0.f : expf(s - lse);
+      float dp = dot_tile<DH>(dor, tv + lane * (DH + 1));
+      if (DROP) dp = mha_keep((uint32_t)p, q, k, rkey, a.thresh) ? dp * a.inv_keep : 0.f;
+      sc[k] = pv * (dp - delta) * a.scale;
+    }
   }
+  if (!it.valid) return;
   __syncwarp();
   float acc[(DH + 31) / 32];
-  weighted_rows<T, DH>(acc, sc, a.k, gbase, a.seq_stride, a.ldk, h, a.S, lane);
+  weighted_rows<T, DH>(acc, sc, a.k, it.gbase, a.seq_stride, a.ldk, h, a.S, lane);
   store_dims<T, DH>(a.dq, qrow, a.lddq, h, acc, lane);
 }
 
@@ -756,38 +807,47 @@ __global__ void __launch_bounds__(kMhaThreads) mha_bwd_dkv_simt_kernel(const Mha
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t rkey = 0u;
   if (DROP) rkey = mha_stream_key(a.key[0], a.key[1], a.site);
-  const long long item = (long long)blockIdx.x * kMhaWarps + warp;
-  if (item >= (long long)a.G * a.H * a.S) return;
-  const int p = (int)(item / a.S), k = (int)(item % a.S), g = p / a.H, h = p % a.H;
-  const long long gbase = group_base(a, g), krow = gbase + (long long)k * a.seq_stride;
-  float* scp = reinterpret_cast<float*>(mha_smem) + (size_t)warp * 2 * S_round;
+  const SimtItem it = simt_item(a);
+  const int p = it.p, k = it.r, h = it.h;
+  const long long krow = it.gbase + (long long)k * a.seq_stride;
+  float* tq = reinterpret_cast<float*>(mha_smem);
+  float* tdo = tq + 32 * (DH + 1);
+  float* scp = tdo + 32 * (DH + 1) + (size_t)warp * 2 * S_round;
   float* scs = scp + S_round;
   float kr[DH], vr[DH];
-  load_row<T, DH>(kr, a.k, krow, a.ldk, h);
-  load_row<T, DH>(vr, a.v, krow, a.ldv, h);
-  for (int q = lane; q < a.S; q += 32) {
-    float xr[DH];
-    const long long qrow = gbase + (long long)q * a.seq_stride;
-    load_row<T, DH>(xr, a.q, qrow, a.ldq, h);
-    const float s = dot_row<DH>(xr, kr) * a.scale;
-    const bool masked = a.mask_bits != nullptr &&
-                        ((__ldg(a.mask_bits + (long long)q * a.mask_words + (k >> 5)) >> (k & 31)) & 1u);
-    const float pv = masked ? 0.f : expf(s - a.lse[(long long)p * a.S + q]);
-    load_row<T, DH>(xr, a.dout, qrow, a.ldo, h);
-    float dp = dot_row<DH>(xr, vr), pk = pv;
-    if (DROP) {
-      const bool keep = mha_keep((uint32_t)p, q, k, rkey, a.thresh);
-      dp = keep ? dp * a.inv_keep : 0.f;
-      pk = keep ? pv * a.inv_keep : 0.f;
-    }
-    scp[q] = pk;
-    scs[q] = pv * (dp - a.delta[(long long)p * a.S + q]) * a.scale;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) kr[i] = vr[i] = 0.f;
+  if (it.valid) {
+    load_row<T, DH>(kr, a.k, krow, a.ldk, h);
+    load_row<T, DH>(vr, a.v, krow, a.ldv, h);
   }
+  for (int t0 = 0; t0 < a.S; t0 += 32) {
+    __syncthreads();
+    stage_rows<T, DH>(tq, a.q, a.ldq, it.gbase, a.seq_stride, h, t0, a.S);
+    stage_rows<T, DH>(tdo, a.dout, a.ldo, it.gbase, a.seq_stride, h, t0, a.S);
+    __syncthreads();
+    const int q = t0 + lane;
+    if (it.valid && q < a.S) {
+      const float s = dot_tile<DH>(kr, tq + lane * (DH + 1)) * a.scale;
+      const bool masked = a.mask_bits != nullptr &&
+                          ((__ldg(a.mask_bits + (long long)q * a.mask_words + (k >> 5)) >> (k & 31)) & 1u);
+      const float pv = masked ? 0.f : expf(s - a.lse[(long long)p * a.S + q]);
+      float dp = dot_tile<DH>(vr, tdo + lane * (DH + 1)), pk = pv;
+      if (DROP) {
+        const bool keep = mha_keep((uint32_t)p, q, k, rkey, a.thresh);
+        dp = keep ? dp * a.inv_keep : 0.f;
+        pk = keep ? pv * a.inv_keep : 0.f;
+      }
+      scp[q] = pk;
+      scs[q] = pv * (dp - a.delta[(long long)p * a.S + q]) * a.scale;
+    }
+  }
+  if (!it.valid) return;
   __syncwarp();
   float acc[(DH + 31) / 32];
-  weighted_rows<T, DH>(acc, scp, a.dout, gbase, a.seq_stride, a.ldo, h, a.S, lane);
+  weighted_rows<T, DH>(acc, scp, a.dout, it.gbase, a.seq_stride, a.ldo, h, a.S, lane);
   store_dims<T, DH>(a.dv, krow, a.lddv, h, acc, lane);
-  weighted_rows<T, DH>(acc, scs, a.q, gbase, a.seq_stride, a.ldq, h, a.S, lane);
+  weighted_rows<T, DH>(acc, scs, a.q, it.gbase, a.seq_stride, a.ldq, h, a.S, lane);
   store_dims<T, DH>(a.dk, krow, a.lddk, h, acc, lane);
 }
 
@@ -874,29 +934,33 @@ template <typename T, int DH, bool DROP> int bwd_tc(const MhaArgs& a, const TcPl
 
 template <typename T, int DH, bool DROP> int fwd_simt(const MhaArgs& a, cudaStream_t st) {
   const int S_round = (a.S + 31) / 32 * 32;
-  const size_t smem = (size_t)kMhaWarps * S_round * sizeof(float);
-  const long long items = (long long)a.G * a.H * a.S;
+  const size_t smem = ((size_t)kMhaWarps * S_round + 32 * (DH + 1)) * sizeof(float);
+  const long long grid = (long long)a.G * a.H * ((a.S + kMhaWarps - 1) / kMhaWarps);
+  if (grid > 0x7fffffffLL) return set_error(MSDA_ERR_UNSUPPORTED, "mha_fwd: too many rows for one launch");
   if (int rc = set_smem(mha_fwd_simt_kernel<T, DH, DROP>, smem)) return rc;
-  mha_fwd_simt_kernel<T, DH, DROP><<<(unsigned)((items + kMhaWarps - 1) / kMhaWarps), kMhaThreads, smem, st>>>(a, S_round);
+  mha_fwd_simt_kernel<T, DH, DROP><<<(unsigned)grid, kMhaThreads, smem, st>>>(a, S_round);
   count_launch();
   return check_launch("mha_fwd");
 }
 template <typename T, int DH, bool DROP> int bwd_simt(const MhaArgs& a, cudaStream_t st) {
   const int S_round = (a.S + 31) / 32 * 32;
-  const size_t smem = (size_t)kMhaWarps * S_round * sizeof(float);
-  const long long items = (long long)a.G * a.H * a.S;
-  const unsigned grid = (unsigned)((items + kMhaWarps - 1) / kMhaWarps);
-  if (int rc = set_smem(mha_bwd_dq_simt_kernel<T, DH, DROP>, smem)) return rc;
-  if (int rc = set_smem(mha_bwd_dkv_simt_kernel<T, DH, DROP>, 2 * smem)) return rc;
-  mha_bwd_dq_simt_kernel<T, DH, DROP><<<grid, kMhaThreads, smem, st>>>(a, S_round);
+  const size_t tiles = 2 * 32 * (DH + 1) * sizeof(float);
+  const size_t smem_a = (size_t)kMhaWarps * S_round * sizeof(float) + tiles;
+  const size_t smem_b = (size_t)kMhaWarps * 2 * S_round * sizeof(float) + tiles;
+  const long long blocks = (long long)a.G * a.H * ((a.S + kMhaWarps - 1) / kMhaWarps);
+  if (blocks > 0x7fffffffLL) return set_error(MSDA_ERR_UNSUPPORTED, "mha_bwd: too many rows for one launch");
+  const unsigned grid = (unsigned)blocks;
+  if (int rc = set_smem(mha_bwd_dq_simt_kernel<T, DH, DROP>, smem_a)) return rc;
+  if (int rc = set_smem(mha_bwd_dkv_simt_kernel<T, DH, DROP>, smem_b)) return rc;
+  mha_bwd_dq_simt_kernel<T, DH, DROP><<<grid, kMhaThreads, smem_a, st>>>(a, S_round);
   count_launch();
   if (int rc = check_launch("mha_bwd (dQ pass)")) return rc;
-  mha_bwd_dkv_simt_kernel<T, DH, DROP><<<grid, kMhaThreads, 2 * smem, st>>>(a, S_round);
+  mha_bwd_dkv_simt_kernel<T, DH, DROP><<<grid, kMhaThreads, smem_b, st>>>(a, S_round);
   count_launch();
   return check_launch("mha_bwd (dK / dV pass)");
 }
 
-constexpr int kSimtMaxS = 3072;     // 8 warps x 2 score rows x 3072 floats = 192 KB
+constexpr int kSimtMaxS = 3072;     // 8 warps x 2 score rows x 3072 floats = 192 KB (+ two 32-token tiles)
 
 bool tc_covers(int dtype, int Dh, int P, int S) {
   if (dtype == MSDA_F32 || (Dh != 32 && Dh != 64)) return false;

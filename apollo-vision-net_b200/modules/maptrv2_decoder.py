@@ -35,11 +35,18 @@ class FusedSelfAttentionMixin:
     the same node when the caller hands it over (``post_norm``).  Parameters and their names are those of
     ``torch.nn.MultiheadAttention`` (checkpoints load unchanged)."""
 
+    # True: the sm_100a core wherever it is the faster engine -- every 16-bit case (tensor-core kernels) and
+    # fp32 sequences of up to 64 tokens; LONG fp32 sequences go to torch's attention, whose fp32 kernels are
+    # 3-4x faster than the one-warp-per-row FMA path (profiles/r02_mha.md).  'always': the core for every
+    # supported case (what the fp32 parity tests run).  False: torch.nn.MultiheadAttention throughout.
     use_fused_core = True
+    fp32_fused_max_tokens = 64
 
     def fused_self_attention_ok(self, x, layout, attn_mask, key_padding_mask=None):
         a = self.attn
         if not (self.use_fused_core and x.is_cuda and key_padding_mask is None and _mask_ok(attn_mask, layout.S)):
+            return False
+        if x.dtype == torch.float32 and layout.S > self.fp32_fused_max_tokens and self.use_fused_core != 'always':
             return False
         if not getattr(a, '_qkv_same_embed_dim', True) or a.in_proj_bias is None or a.bias_k is not None \
                 or a.add_zero_attn or x.dtype != a.in_proj_weight.dtype:

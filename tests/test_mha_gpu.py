@@ -174,7 +174,7 @@ def test_multihead_attention_module_fused_equals_torch_path(dtype):
     go = torch.randn(S, B, C, generator=g)
     mask = _mask(S, 10)
     results = []
-    for fused in (True, False):
+    for fused in ('always', False):
         attn.use_fused_core = fused
         xd = x.to(DEV, dtype).requires_grad_(True)
         pd = pos.to(DEV, dtype).requires_grad_(True)
@@ -201,6 +201,24 @@ def test_multihead_attention_module_fused_equals_torch_path(dtype):
         ref = torch.nn.functional.layer_norm(ref, (C,), norm.weight.detach().cpu().double(),
                                              norm.bias.detach().cpu().double(), norm.eps)
         assert rel_err(results[0][0].view(-1, C), ref) <= 1e-5
+
+
+def test_module_policy_long_fp32_sequences_take_the_library_path():
+    """Default policy: 16-bit -> the core; fp32 -> the core up to 64 tokens, torch's attention beyond (its fp32
+    kernels are faster than the FMA path); 'always' forces the core."""
+    import apollo_vision_net_b200 as pkg
+    import apollo_vision_net_b200.mha as m
+    attn = pkg.build_attention(dict(type='MultiheadAttention', embed_dims=256, num_heads=8)).to(DEV)
+    x32 = torch.zeros(2, 1, 256, device=DEV)
+    assert attn.fused_self_attention_ok(x32, m.sequence_first_layout(20, 4), None)
+    assert not attn.fused_self_attention_ok(x32, m.sequence_first_layout(350, 4), None)
+    attn.use_fused_core = 'always'
+    assert attn.fused_self_attention_ok(x32, m.sequence_first_layout(350, 4), None)
+    attn.use_fused_core = True
+    attn.to(torch.bfloat16)
+    assert attn.fused_self_attention_ok(x32.bfloat16(), m.sequence_first_layout(350, 4), None)
+    assert not attn.fused_self_attention_ok(x32.bfloat16(), m.sequence_first_layout(350, 4), None,
+                                            key_padding_mask=torch.zeros(4, 350, dtype=torch.bool, device=DEV))
 
 
 @pytest.mark.parametrize('train', [False, True], ids=['eval', 'train_dropout'])
@@ -231,7 +249,7 @@ def test_maptrv2_layer_in_place_groupings_equal_the_permuting_path(train):
     shapes = torch.tensor([[Hb, Hb]], device=DEV)
     starts = torch.tensor([0], device=DEV)
     outs = []
-    for fused in (True, False):
+    for fused in ('always', False):
         for a in layer.attentions[:2]:
             a.use_fused_core = fused
         q = query.clone().requires_grad_(True)

@@ -55,6 +55,7 @@ def main():
     shapes = torch.tensor([[H, H]], device=dev)
     starts = torch.tensor([0], device=dev)
     go = torch.randn(6, V * Pn, bs, C, device=dev, dtype=dtype)
+    params = list(dec.parameters()) + list(reg.parameters())
 
     def step():
         inter, _ = dec(query, key=None, value=bev, query_pos=qpos, reference_points=refp, reg_branches=reg,
@@ -63,6 +64,8 @@ def main():
         inter.backward(go)
         query.grad = None
         bev.grad = None
+        for prm in params:         # as a training loop does (zero_grad(set_to_none=True))
+            prm.grad = None
 
     res = {'bev': H, 'dtype': args.dtype, 'train': args.train, 'torch_self_attn': args.torch_self_attn, 'queries': V * Pn, 'xattn_samples_per_layer': V * Pn * 8 * 4}
     for hoist in (True, False):

@@ -38,6 +38,7 @@ mask[:50, 50:] = True
 shapes = torch.tensor([[H, H]], device=dev)
 starts = torch.tensor([0], device=dev)
 go = torch.randn(6, V * Pn, bs, C, device=dev, dtype=dtype)
+params = list(dec.parameters()) + list(reg.parameters())
 
 
 def step():
@@ -47,6 +48,8 @@ def step():
     inter.backward(go)
     query.grad = None
     bev.grad = None
+    for prm in params:             # as a training loop does (zero_grad(set_to_none=True)): no accumulate-into-grad adds
+        prm.grad = None
 
 
 for _ in range(2):
