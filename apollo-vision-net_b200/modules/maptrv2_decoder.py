@@ -42,9 +42,11 @@ class FusedSelfAttentionMixin:
     use_fused_core = True
     fp32_fused_max_tokens = 64
 
-    def fused_self_attention_ok(self, x, layout, attn_mask, key_padding_mask=None):
+    def fused_self_attention_ok(self, x, layout, attn_mask, key_padding_mask=None, pos=None):
         a = self.attn
         if not (self.use_fused_core and x.is_cuda and key_padding_mask is None and _mask_ok(attn_mask, layout.S)):
+            return False
+        if pos is not None and (pos.shape != x.shape or pos.dtype != x.dtype):      # broadcast encodings: torch path
             return False
         if x.dtype == torch.float32 and layout.S > self.fp32_fused_max_tokens and self.use_fused_core != 'always':
             return False
@@ -104,7 +106,7 @@ if not HAVE_MMCV:
             if key is query and value is query and key_pos is query_pos and query.dim() == 3:
                 layout = (batch_first_layout(query.shape[0], query.shape[1]) if self.batch_first
                           else sequence_first_layout(query.shape[0], query.shape[1]))
-                if self.fused_self_attention_ok(query, layout, attn_mask, key_padding_mask):
+                if self.fused_self_attention_ok(query, layout, attn_mask, key_padding_mask, query_pos):
                     return self.fused_self_attention(query, query_pos, layout, attn_mask, identity, post_norm)
             if query_pos is not None:
                 query = query + query_pos
@@ -222,7 +224,7 @@ class MapTRv2DecoupledDetrTransformerDecoderLayer(BaseModule):
             # intra-vector: the sequence axis is the points, one group per (vector, sample)   (:149-185)
             layout = inter_vector_layout(V, Pn, nb) if first else intra_vector_layout(V, Pn, nb)
             if (isinstance(attn, FusedSelfAttentionMixin) and not attn.batch_first and
-                    attn.fused_self_attention_ok(query, layout, mask, query_key_padding_mask)):
+                    attn.fused_self_attention_ok(query, layout, mask, query_key_padding_mask, query_pos)):
                 # attended in place in the (V * Pn, nb, C) activations: no permute / contiguous copies
                 return attn.fused_self_attention(query, query_pos, layout, mask, identity, post_norm)
             extra = {} if post_norm is None else {'post_norm': post_norm}
