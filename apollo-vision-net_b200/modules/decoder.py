@@ -9,8 +9,12 @@ The sampling core is the fused queue kernel with a queue of one (C ABI ``tsa_fwd
 import torch
 import torch.nn as nn
 
+from torch.autograd.function import once_differentiable
+
 from ..fused_ops import QueueDeformAttnFunction
+from ..multi_scale_deformable_attn_function import custom_bwd, custom_fwd
 from ..registry import ATTENTION
+from ..rowops import _take_bias_grad, weight_bias_grad
 from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
@@ -20,23 +24,70 @@ def inverse_sigmoid(x, eps=1e-5):
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
+class HoistedValueProjFunction(torch.autograd.Function):
+    """``[x W_l^T + b_l for l in layers]`` before the layer loop, as one autograd node.
+
+    Written as plain tensor ops (stack, baddbmm, ``out[l]``) the backward pays, per layer, a zero-filled
+    (layers, rows, C) tensor for the select, a copy into it and an accumulation add of the whole stack
+    (6 x 123 MB each way at the 200x200 BEV: ~0.6 ms per decoder step, ``profiles/r02_decoder.md``).  Here every
+    layer's gradient is consumed where it arrives: dW_l = g_l^T x and db_l (the column sums the attention's
+    last pass already produced, when offered) per layer, and dx accumulated by GEMMs with beta = 1."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, x, *params):
+        n = len(params) // 2
+        weights, biases = params[:n], params[n:]
+        # one GEMM per layer with the bias in its epilogue, back to back on one input that stays in L2 (a
+        # batched GEMM would first materialise the broadcast bias as a (layers, rows, C) tensor: 108 us at 200x200)
+        out = torch.empty((n, x.shape[0], weights[0].shape[0]), dtype=x.dtype, device=x.device)
+        for i in range(n):
+            torch.addmm(biases[i], x, weights[i].t(), out=out[i])
+        ctx.save_for_backward(x, *weights)
+        return tuple(out[i] for i in range(n))
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, *grads):
+        x, *weights = ctx.saved_tensors
+        n = len(weights)
+        dx = None
+        dws, dbs = [None] * n, [None] * n
+        for i, (g, w) in enumerate(zip(grads, weights)):
+            if g is None:
+                continue
+            g2 = g.reshape(-1, w.shape[0])
+            if ctx.needs_input_grad[0]:
+                dx = g2 @ w if dx is None else dx.addmm_(g2, w)
+            want_w, want_b = ctx.needs_input_grad[1 + i], ctx.needs_input_grad[1 + n + i]
+            ready = _take_bias_grad(g, w.shape[0]) if want_b else None
+            if ready is not None:
+                dbs[i] = ready.to(w.dtype)
+                want_b = False
+            if want_w:
+                dws[i], db = weight_bias_grad(g2, x, w, want_bias=want_b)
+                dbs[i] = db if want_b else dbs[i]
+            elif want_b:
+                dbs[i] = g2.sum(0)
+        return (dx, *dws, *dbs)
+
+
 def hoist_value_proj(attns, value, batch_first=False):
-    """``[a.value_proj(value) for a in attns]`` as ONE batched GEMM.
+    """``[a.value_proj(value) for a in attns]`` hoisted in front of the layer loop.
 
     Every decoder layer projects the SAME BEV map with its own ``value_proj`` (decoder.py:299-303
     of the reference, once per layer inside the layer loop); the BEV does not change between the
-    layers, so the projections of all layers can be computed before the loop: one launch forward,
-    one batched dX / dW launch backward instead of one each per layer plus the gradient
-    accumulation adds on the BEV.  ``value`` is (HW, bs, C) (``batch_first=False``) or (bs, HW, C);
+    layers, so the projections of all layers can be computed before the loop, with a
+    backward that accumulates the BEV gradient with beta = 1 GEMMs instead of gradient-accumulation adds
+    (:class:`HoistedValueProjFunction`).  ``value`` is (HW, bs, C) (``batch_first=False``) or (bs, HW, C);
     returns a list of batch-major (bs, HW, C) tensors, one per attention module."""
     if not batch_first:
         value = value.permute(1, 0, 2)
     bs, n, C = value.shape
-    w = torch.stack([a.value_proj.weight for a in attns]).transpose(1, 2)      # (layers, C_in, C_out)
-    b = torch.stack([a.value_proj.bias for a in attns]).unsqueeze(1)           # (layers, 1, C_out)
-    x = value.reshape(1, bs * n, C).expand(len(attns), -1, -1)
-    out = torch.baddbmm(b, x, w)                                                 # (layers, bs * n, C_out)
-    return [out[i].view(bs, n, -1) for i in range(len(attns))]
+    outs = HoistedValueProjFunction.apply(value.reshape(bs * n, C), *[a.value_proj.weight for a in attns],
+                                          *[a.value_proj.bias for a in attns])
+    return [o.view(bs, n, -1) for o in outs]
 
 
 def hoisted_projections(layers, args, kwargs):
