@@ -256,3 +256,107 @@ def test_row_kernels_stay_in_bounds(rows, C, dtype, guard):
     assert rel_err(y, ref) <= tol
     assert rel_err(x1.grad, x2.grad) <= tol
     assert rel_err(s, go.to(DEV).float().sum(0)) <= tol
+
+
+# ---- round 2 entry points: mha_fwd / mha_bwd (csrc/mha.cu) and dcnv3_fwd / dcnv3_bwd (csrc/dcnv3.cu) --------------
+@pytest.fixture
+def guard2(monkeypatch):
+    import apollo_vision_net_b200.dcnv3 as dc
+    import apollo_vision_net_b200.mha as mh
+    g = GuardedTorch()
+    for mod in (mh, dc):
+        monkeypatch.setattr(mod, 'torch', g)
+    monkeypatch.setattr(mh, '_mask_cache', {})
+    return g
+
+
+MHA_CASES = [
+    # layout kind, a, b, c, heads, head_dim, dtype, impl, masked, dropout
+    ('seq', 37, 3, 0, 4, 32, torch.bfloat16, 2, True, 0.0),          # ragged: last tile 5 rows, last key block 5 keys
+    ('seq', 37, 3, 0, 4, 32, torch.float32, 1, True, 0.0),
+    ('intra', 11, 20, 2, 8, 32, torch.float16, 2, False, 0.1),       # several problems per CTA, last CTA half full
+    ('inter', 50, 3, 1, 8, 32, torch.bfloat16, 2, True, 0.1),
+    ('batch', 2, 45, 0, 2, 64, torch.bfloat16, 2, True, 0.0),
+    ('seq', 1, 5, 0, 8, 32, torch.bfloat16, 2, False, 0.0),          # one token
+    ('seq', 33, 2, 0, 2, 16, torch.float32, 1, False, 0.1),          # FMA path, head_dim 16
+    ('seq', 300, 1, 0, 8, 32, torch.bfloat16, 2, False, 0.0),        # few problems: half-filled CTAs
+]
+
+
+@pytest.mark.parametrize('case', MHA_CASES)
+def test_self_attention_core_stays_in_bounds(case, guard2):
+    import apollo_vision_net_b200.mha as m
+    import apollo_vision_net_b200.rowops as ro
+    kind, a, b, c, H, Dh, dtype, impl, masked, p = case
+    lay = {'seq': lambda: m.sequence_first_layout(a, b), 'batch': lambda: m.batch_first_layout(a, b),
+           'inter': lambda: m.inter_vector_layout(a, b, c), 'intra': lambda: m.intra_vector_layout(a, b, c)}[kind]()
+    C = H * Dh
+    rows = lay.G * lay.S
+    g = torch.Generator().manual_seed(7)
+    qk = torch.randn(rows, 2 * C, generator=g).to(dtype)
+    v = torch.randn(rows, C, generator=g).to(dtype)
+    go = torch.randn(rows, C, generator=g).to(dtype)
+    mask = None
+    if masked:
+        mask = torch.zeros(lay.S, lay.S, dtype=torch.bool)
+        mask[lay.S // 3:, :lay.S // 3] = True
+        mask[:lay.S // 3, lay.S // 3:] = True
+        mask = mask.to(DEV)
+
+    def run(wrap):
+        ro.reseed_dropout(DEV, 1234)                    # the same masks in both runs
+        ro._drop_site[0] = 100
+        q_, v_ = wrap(qk, True), wrap(v, True)
+        out = m.self_attention_core(q_, v_, lay, H, mask, p, impl)
+        out.backward(wrap(go))
+        return out.detach(), q_.grad, v_.grad
+
+    plain = run(lambda t, rg=False: t.to(DEV).requires_grad_(rg))
+    n_plain = len(guard2.records)
+    got = run(poisoned)
+    assert len(guard2.records) > n_plain
+    guard2.check()
+    _finite(*got)
+    for x, y in zip(got, plain):
+        assert torch.equal(x, y)                         # deterministic kernels: bit-identical to the ordinary run
+
+
+DCN_CASES = [
+    # N, H, W, group, group_channels, kh, kw, stride, pad, dilation, offset_scale, dtype
+    (2, 7, 9, 4, 8, 3, 3, 1, 1, 1, 1.0, torch.float32),
+    (2, 7, 9, 4, 8, 3, 3, 1, 1, 1, 1.0, torch.bfloat16),
+    (1, 1, 1, 2, 16, 3, 3, 1, 1, 1, 1.0, torch.float16),             # one-pixel map: every neighbour outside
+    (1, 9, 6, 1, 6, 3, 3, 2, 2, 2, 3.0, torch.float32),              # scalar fallback kernels, far-away positions
+    (1, 5, 8, 3, 8, 1, 5, 1, 0, 1, 0.5, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize('case', DCN_CASES)
+def test_dcnv3_stays_in_bounds(case, guard2):
+    import apollo_vision_net_b200.dcnv3 as d
+    from oracle.dcnv3_oracle import output_size
+    N, H, W, G, Cg, kh, kw, st, pad, dil, scale, dtype = case
+    Ho, Wo = output_size(H, kh, st, pad, dil), output_size(W, kw, st, pad, dil)
+    K = kh * kw
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, H, W, G * Cg, generator=g).to(dtype)
+    off = (torch.randn(N, Ho, Wo, G * K * 2, generator=g) * 4).to(dtype)          # many positions outside the map
+    msk = torch.softmax(torch.randn(N, Ho, Wo, G, K, generator=g), -1).reshape(N, Ho, Wo, G * K).to(dtype)
+    go = torch.randn(N, Ho, Wo, G * Cg, generator=g).to(dtype)
+    cfg = (kh, kw, st, st, pad, pad, dil, dil, G, Cg, scale)
+
+    def run(wrap):
+        x_, o_, m_ = wrap(x, True), wrap(off, True), wrap(msk, True)
+        out = d.DCNv3Function.apply(x_, o_, m_, *cfg, 256)
+        out.backward(wrap(go))
+        return out.detach(), x_.grad, o_.grad, m_.grad
+
+    plain = run(lambda t, rg=False: t.to(DEV).requires_grad_(rg))
+    n_plain = len(guard2.records)
+    got = run(poisoned)
+    assert len(guard2.records) > n_plain
+    guard2.check()
+    _finite(*got)
+    for a_, b_ in zip(got[:1] + got[2:], plain[:1] + plain[2:]):
+        assert torch.equal(a_, b_)
+    assert rel_err(got[1], plain[1]) <= (1e-6 if dtype == torch.float32 else 1e-2)   # grad_input: atomic order
