@@ -940,6 +940,20 @@ def measure_detmap(args, rank, world, dev, steps, warmup, decoder_only=False):
             '200x200 BEV) -> L2 loss, fwd + bwd (BASELINE configs[3])') if decoder_only else (
         f'encoder ({args.layers} layers, 200x200) + detection decoder (900 queries x 6) + MapTRv2 '
         'decoder (350 x 20 queries x 6, one-to-many) -> L2 loss, fwd + bwd, one frame per rank')
+    kernel_us = None
+    if decoder_only:
+        # our kernels inside this step, timed live with CUDA events around each C-ABI launch (eager steps; a replayed
+        # graph cannot carry events): mha_fwd / mha_bwd = the self-attention core (mha_bwd = its two passes),
+        # tsa_fwd / tsa_bwd = the deformable cross-attention (queue of one), ln_* / colsum = the row kernels
+        timer = _lib.KernelTimer()
+        _lib.set_timer(timer)
+        try:
+            for _ in range(3):
+                step()
+        finally:
+            _lib.set_timer(None)
+        kernel_us = {name: {'launches_per_step': st['launches'] / 3, 'mean_us': round(st['mean_us'], 2)}
+                     for name, st in timer.summary().items()}
     torch_ms = None
     if decoder_only and world == 1:
         # the same step with the self-attentions on torch.nn.MultiheadAttention + the reference's permute copies
@@ -964,7 +978,7 @@ def measure_detmap(args, rank, world, dev, steps, warmup, decoder_only=False):
             torch.cuda.synchronize()
     return {'workload': what, 'self_attention': 'csrc/mha.cu (mma.sync tensor-core core, tokens attended in place, '
                                                 'LayerNorms folded into the blocks)',
-            'ms_per_step_torch_self_attention': torch_ms,
+            'ms_per_step_torch_self_attention': torch_ms, 'kernels': kernel_us,
             'ms_per_step': ms, 'frames_per_s': world * 1e3 / ms, 'cuda_graph': graph is not None,
             'cuda_graph_error': graph_error, 'our_launches_per_step': launches, 'dropout': args.dropout,
             'parallelism': f'dp{world}' if world > 1 else 'single'}
