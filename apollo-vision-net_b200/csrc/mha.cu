@@ -24,8 +24,12 @@
 //    produces dQ and delta = rowsum(dO . O); pass B (a warp owns 16 keys, the score tile is computed
 //    transposed) produces dK and dV -- no atomics, no cross-warp reduction, nothing but lse (S floats per
 //    problem) saved by the forward.
-//  * fp32 models (and shapes the tensor-core path does not cover): one warp per row, plain FMA, the same
-//    three passes.  This is the precision path the fp32 parity tests run against the oracle.
+//  * fp32 models (and shapes the tensor-core path does not cover): a CTA owns 8 consecutive rows of one
+//    problem, one warp per row; the other side of the score matrix streams through shared memory in tiles
+//    of 32 tokens (coalesced loads, "lane = token" reads of a padded tile), plain FMA, the same passes.
+//    This is the precision path the fp32 parity tests run against the oracle; it is 2.5-4x slower than the
+//    library's fp32 attention at 350 tokens, so the module sends long fp32 sequences there
+//    (modules/maptrv2_decoder.py: FusedSelfAttentionMixin).
 //
 // Dropout on the attention weights is counter-based (philox.cuh) and recomputed in the backward.  The
 // mask is a function of (problem, q, k) built so that one Philox call serves the four elements
