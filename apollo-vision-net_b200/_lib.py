@@ -70,7 +70,7 @@ _SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 7          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
+ABI_VERSION = 8          # must equal MSDA_ABI_VERSION of include/msda_b200.h and the loaded library
 
 
 def _stale():

@@ -16,7 +16,25 @@ namespace msda {
 
 constexpr int kRowThreads = 256;
 #ifndef LN_BWD_MINBLOCKS
-#define LN_BWD_MINBLOCKS 4
+#define LN_BWD_MINBLOCKS 3
+#endif
+#ifndef LN_BWD_MINBLOCKS_DROP
+#define LN_BWD_MINBLOCKS_DROP 2
+#endif
+// Rows a warp keeps in flight ahead of the one it is working on (register stages).  A warp's row is only
+// 1 KB of loads (x + residual, or x + dy), so one row ahead leaves ~32 KB in flight per SM -- below what the
+// HBM latency x bandwidth product asks for; see profiles/r02_rowops.md for the sweep.
+#ifndef LN_BWD_HOIST_GAMMA
+#define LN_BWD_HOIST_GAMMA 0
+#endif
+#ifndef LN_FWD_DEPTH
+#define LN_FWD_DEPTH 1
+#endif
+#ifndef LN_FWD_MINBLOCKS
+#define LN_FWD_MINBLOCKS 4
+#endif
+#ifndef LN_BWD_DEPTH
+#define LN_BWD_DEPTH 1
 #endif
 
 template <typename T> struct Vec16IO {
@@ -47,6 +65,11 @@ struct DropArgs {
   uint32_t thresh;                     // round(p * 65536)
   float scale;                         // 1 / (1 - p)
 };
+// (p < 1 is checked by the callers; a p within 2^-17 of 1 would round to 65536, which no 16-bit lane reaches)
+static inline uint32_t drop_thresh(float p) {
+  const uint32_t t = (uint32_t)(p * 65536.f + 0.5f);
+  return t > 65535u ? 65535u : t;
+}
 
 // keep bits (bit j = element 8 * group + j is kept)
 __device__ __forceinline__ uint32_t drop_keep8(unsigned long long group, unsigned long long seed,
@@ -59,6 +82,31 @@ __device__ __forceinline__ uint32_t drop_keep8(unsigned long long group, unsigne
   for (int j = 0; j < 8; ++j) keep |= (((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thresh ? 1u : 0u) << j;
   return keep;
 }
+// the same decisions as predicates, straight from the four words (lane j of word w is kept when its 16 bits
+// are >= thresh: the high lane compares the whole word against thresh << 16, the low lane the word shifted up)
+template <int VEC>
+__device__ __forceinline__ void drop_keep_flags(unsigned long long e0, unsigned long long seed, unsigned long long step,
+                                                const uint32_t site, const uint32_t thresh, bool (&keep)[VEC]) {
+  const unsigned long long group = e0 >> 3;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), site, (uint32_t)step),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  const uint32_t t16 = thresh << 16;                 // thresh <= 65535 (p < 1)
+  if (VEC == 8) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      keep[2 * j] = (w[j] << 16) >= t16;
+      keep[2 * j + 1] = w[j] >= t16;
+    }
+  } else {
+    const bool hi = (e0 & 4) != 0;
+    const uint32_t w0 = hi ? r.z : r.x, w1 = hi ? r.w : r.y;
+    keep[0] = (w0 << 16) >= t16;
+    keep[1] = w0 >= t16;
+    keep[2] = (w1 << 16) >= t16;
+    keep[3] = w1 >= t16;
+  }
+}
 // keep bits of the VEC (4 or 8) consecutive elements starting at element e0 (a multiple of VEC)
 template <int VEC>
 __device__ __forceinline__ uint32_t drop_keep(unsigned long long e0, unsigned long long seed, unsigned long long step,
@@ -67,14 +115,22 @@ __device__ __forceinline__ uint32_t drop_keep(unsigned long long e0, unsigned lo
   return VEC == 8 ? k : (k >> (e0 & 4)) & 0xfu;
 }
 
-// Final stage of the column reductions.  Every CTA adds its partial sums into an fp32 strip in
-// the workspace with reductions at L2 (the strip is all zero on entry); the LAST CTA to finish
-// (ticket counter in the workspace header) converts the strip into the output and zeroes strip and
+// Final stage of the column reductions.  Every CTA adds its partial sums into one of kStrips fp32 strips in
+// the workspace with reductions at L2 (the strips are all zero on entry); the LAST CTA to finish
+// (ticket counter in the workspace header) sums the strips into the output and zeroes strips and
 // counter again, so the workspace is reusable without a memset.  One launch, no serial tail.
-constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the strip
+// Several strips because reductions on one line serialise in L2: with ~600 CTAs adding into a single
+// strip the last of them waited ~5 us for the queue in front of it (profiles/r02_rowops.md).
+constexpr int kWsHeaderFloats = 64;          // 256-byte header in front of the strips
+constexpr int kStrips = 8;                   // workspace: kWsHeaderFloats + kStrips * ncols floats
+
+__device__ __forceinline__ float* my_strip(float* ws, unsigned cta, int ncols) {
+  return ws + kWsHeaderFloats + (size_t)(cta % kStrips) * ncols;
+}
 
 template <typename TO>
-__device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __restrict__ out, int ncols) {
+__device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __restrict__ out, int ncols,
+                                                 unsigned total_ctas) {
   __shared__ bool last;
   // the CTA barrier orders every thread's strip reductions before thread 0's fence (fences are
   // cumulative), which orders them before the ticket: one device-scope fence per CTA, not one per thread
@@ -83,16 +139,21 @@ __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __r
     __threadfence();
     unsigned* counter = reinterpret_cast<unsigned*>(ws);
     const unsigned ticket = atomicAdd(counter, 1u);
-    last = (ticket == gridDim.x - 1);
+    last = (ticket == total_ctas - 1);
     if (last) *counter = 0u;
   }
   __syncthreads();
   if (!last) return;
   __threadfence();
-  float* strip = ws + kWsHeaderFloats;
+  float* strips = ws + kWsHeaderFloats;
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-    out[c] = from_f32<TO>(__ldcg(strip + c));
-    strip[c] = 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kStrips; ++k) {
+      s += __ldcg(strips + (size_t)k * ncols + c);
+      strips[(size_t)k * ncols + c] = 0.f;
+    }
+    out[c] = from_f32<TO>(s);
   }
 }
 
@@ -100,13 +161,15 @@ __device__ __forceinline__ void finalize_columns(float* __restrict__ ws, TO* __r
 // With `residual`: normalises s = x + residual, rounded to T first (bit-identical to a separate
 // add kernel followed by LayerNorm), and writes s to `sum_out` (may alias x) for the backward.
 // DROP: s = dropout(x) + residual (x = the output of the block's last Linear).
+// The loads of a warp's next DEPTH rows are in flight (register stages) while it works on the current one.
 template <typename T, int PER_LANE, bool DROP>
-__global__ void __launch_bounds__(kRowThreads)
+__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? LN_FWD_MINBLOCKS : 1)
 ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ gamma,
               const T* __restrict__ beta, T* sum_out, T* __restrict__ y, float* __restrict__ mean,
               float* __restrict__ rstd, long long rows, int C, float eps, const DropArgs drop) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int NV = PER_LANE / VEC;
+  constexpr int DEPTH = PER_LANE <= 8 ? LN_FWD_DEPTH : 1;
   const int lane = threadIdx.x & 31;
   unsigned long long seed = 0ull, step = 0ull;
   if (DROP) {
@@ -119,68 +182,77 @@ ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ 
   }
   const long long warp = (long long)blockIdx.x * (kRowThreads / 32) + (threadIdx.x >> 5);
   const long long nwarp = (long long)gridDim.x * (kRowThreads / 32);
-  float g[PER_LANE], bb[PER_LANE];
+  constexpr int NVA = NV > 0 ? NV : 1;      // (NV == 0 instances are rejected at dispatch)
+  uint4 gpk[NVA], bpk[NVA];                 // gamma / beta stay packed (registers), unpacked per row
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    float t[VEC];
-    Vec16IO<T>::load(gamma + (v * 32 + lane) * VEC, t);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) g[v * VEC + i] = t[i];
-    Vec16IO<T>::load(beta + (v * 32 + lane) * VEC, t);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) bb[v * VEC + i] = t[i];
+    gpk[v] = ldg128(gamma + (v * 32 + lane) * VEC);
+    bpk[v] = ldg128(beta + (v * 32 + lane) * VEC);
   }
-  // the loads of a warp's next row are issued before the arithmetic of the current one
-  constexpr int NVA = NV > 0 ? NV : 1;      // (NV == 0 instances are rejected at dispatch)
-  uint4 nx[NVA], nr[NVA];
-  auto fetch = [&](long long r) {
+  const float inv_c = 1.0f / (float)C;      // (C is a multiple of 128: the quotient below stays the rounded one
+                                            //  only when C is a power of two -- see mean_of)
+  const bool pow2 = (C & (C - 1)) == 0;
+  auto mean_of = [&](float s) { return pow2 ? s * inv_c : s / (float)C; };
+  uint4 nx[DEPTH][NVA], nr[DEPTH][NVA];
+  auto fetch = [&](int st, long long r) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      nx[v] = *reinterpret_cast<const uint4*>(x + r * C + (v * 32 + lane) * VEC);   // x may alias sum_out
-      if (residual != nullptr) nr[v] = ldg128(residual + r * C + (v * 32 + lane) * VEC);
+      nx[st][v] = *reinterpret_cast<const uint4*>(x + r * C + (v * 32 + lane) * VEC);   // x may alias sum_out
+      if (residual != nullptr) nr[st][v] = ldg128(residual + r * C + (v * 32 + lane) * VEC);
     }
   };
-  if (warp < rows) fetch(warp);
-  for (long long r = warp; r < rows; r += nwarp) {
-    uint4 cx[NVA], cr[NVA];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { cx[v] = nx[v]; cr[v] = nr[v]; }
-    if (r + nwarp < rows) fetch(r + nwarp);
-    float f[PER_LANE];
-    float s = 0.f;
+  for (int st = 0; st < DEPTH; ++st)
+    if (warp + st * nwarp < rows) fetch(st, warp + st * nwarp);
+  for (long long base = warp; base < rows; base += DEPTH * nwarp) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float t[VEC];
-      Vec16<T>::unpack(cx[v], t);
-      if (residual != nullptr) {
-        float rr[VEC];
-        Vec16<T>::unpack(cr[v], rr);
-        if (DROP) {        // (rounded to T like a separate dropout kernel's output)
-          const uint32_t keep = drop_keep<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop);
+    for (int st = 0; st < DEPTH; ++st) {
+      const long long r = base + st * nwarp;
+      if (r >= rows) break;
+      uint4 cx[NVA], cr[NVA];
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) t[i] = ((keep >> i) & 1u) ? to_f32<T>(from_f32<T>(t[i] * drop.scale)) : 0.f;
+      for (int v = 0; v < NV; ++v) { cx[v] = nx[st][v]; cr[v] = nr[st][v]; }
+      if (r + DEPTH * nwarp < rows) fetch(st, r + DEPTH * nwarp);
+      float f[PER_LANE];
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float t[VEC];
+        Vec16<T>::unpack(cx[v], t);
+        if (residual != nullptr) {
+          float rr[VEC];
+          Vec16<T>::unpack(cr[v], rr);
+          if (DROP) {        // (rounded to T like a separate dropout kernel's output)
+            bool keep[VEC];
+            drop_keep_flags<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop.site,
+                                 drop.thresh, keep);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) t[i] = keep[i] ? to_f32<T>(from_f32<T>(t[i] * drop.scale)) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) t[i] = to_f32<T>(from_f32<T>(t[i] + rr[i]));
+          Vec16IO<T>::store(sum_out + r * C + (v * 32 + lane) * VEC, t);
         }
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) t[i] = to_f32<T>(from_f32<T>(t[i] + rr[i]));
-        Vec16IO<T>::store(sum_out + r * C + (v * 32 + lane) * VEC, t);
+        for (int i = 0; i < VEC; ++i) { f[v * VEC + i] = t[i]; s += t[i]; }
       }
+      const float mu = mean_of(warp_sum(s));
+      float q = 0.f;
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { f[v * VEC + i] = t[i]; s += t[i]; }
+      for (int i = 0; i < PER_LANE; ++i) { const float d = f[i] - mu; q = fmaf(d, d, q); }
+      const float rs = rsqrtf(mean_of(warp_sum(q)) + eps);
+      T* yr = y + r * C;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float t[VEC], g[VEC], bb[VEC];
+        Vec16<T>::unpack(gpk[v], g);
+        Vec16<T>::unpack(bpk[v], bb);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) t[i] = (f[v * VEC + i] - mu) * rs * g[i] + bb[i];
+        Vec16IO<T>::store(yr + (v * 32 + lane) * VEC, t);
+      }
+      if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
     }
-    const float mu = warp_sum(s) / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) { const float d = f[i] - mu; q = fmaf(d, d, q); }
-    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
-    T* yr = y + r * C;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float t[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) t[i] = (f[v * VEC + i] - mu) * rs * g[v * VEC + i] + bb[v * VEC + i];
-      Vec16IO<T>::store(yr + (v * 32 + lane) * VEC, t);
-    }
-    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
 }
 
@@ -191,7 +263,7 @@ ln_fwd_kernel(const T* x, const T* __restrict__ residual, const T* __restrict__ 
 // DROP (with DXSUM): the normalised sum was dropout(lin) + residual, so the gradient of the Linear output
 // is dx masked and scaled -- written to `dx_masked` and summed over the rows instead of dx.
 template <typename T, int PER_LANE, bool DXSUM, bool DROP>
-__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? LN_BWD_MINBLOCKS : 1)
+__global__ void __launch_bounds__(kRowThreads, PER_LANE <= 8 ? (DROP ? LN_BWD_MINBLOCKS_DROP : LN_BWD_MINBLOCKS) : 1)
 ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
               float* __restrict__ ws, T* __restrict__ dgamma_dbeta, long long rows, int C,
@@ -213,69 +285,98 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
   uint4 gpk[NVG];                                     // gamma stays packed (registers), unpacked per row
 #pragma unroll
   for (int v = 0; v < NV; ++v) gpk[v] = ldg128(gamma + (v * 32 + lane) * VEC);
+  constexpr bool HOIST = LN_BWD_HOIST_GAMMA != 0 && PER_LANE <= 8;      // ... or once, when registers allow
+  float gf[HOIST ? PER_LANE : 1];
+  if (HOIST) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float t[VEC];
+      Vec16<T>::unpack(gpk[v], t);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) gf[HOIST ? v * VEC + i : 0] = t[i];
+    }
+  }
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) { dg[i] = 0.f; db[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < (DXSUM ? PER_LANE : 1); ++i) dsum[i] = 0.f;
   constexpr int NVA = NV > 0 ? NV : 1;
-  uint4 nx[NVA], nd[NVA];
-  float nmu = 0.f, nrs = 0.f;
-  auto fetch = [&](long long r) {
+  constexpr int DEPTH = PER_LANE <= 8 ? LN_BWD_DEPTH : 1;
+  const float inv_c = 1.0f / (float)C;
+  const bool pow2 = (C & (C - 1)) == 0;               // exact reciprocal: the product equals the quotient
+  auto mean_of = [&](float s) { return pow2 ? s * inv_c : s / (float)C; };
+  uint4 nx[DEPTH][NVA], nd[DEPTH][NVA];
+  float nmu[DEPTH], nrs[DEPTH];
+  auto fetch = [&](int st, long long r) {
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      nx[v] = ldg128(x + r * C + (v * 32 + lane) * VEC);
-      nd[v] = ldg128(dy + r * C + (v * 32 + lane) * VEC);
+      nx[st][v] = ldg128(x + r * C + (v * 32 + lane) * VEC);
+      nd[st][v] = ldg128(dy + r * C + (v * 32 + lane) * VEC);
     }
-    nmu = __ldg(mean + r);
-    nrs = __ldg(rstd + r);
+    nmu[st] = __ldg(mean + r);
+    nrs[st] = __ldg(rstd + r);
   };
-  if (warp < rows) fetch(warp);
-  for (long long r = warp; r < rows; r += nwarp) {
-    const float mu = nmu, rs = nrs;
-    uint4 cx[NVA], cd[NVA];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { cx[v] = nx[v]; cd[v] = nd[v]; }
-    if (r + nwarp < rows) fetch(r + nwarp);
-    float xh[PER_LANE], gd[PER_LANE];
-    float s1 = 0.f, s2 = 0.f;
+  for (int st = 0; st < DEPTH; ++st)
+    if (warp + st * nwarp < rows) fetch(st, warp + st * nwarp);
+  for (long long base = warp; base < rows; base += DEPTH * nwarp) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float tx[VEC], td[VEC], tg[VEC];
-      Vec16<T>::unpack(cx[v], tx);
-      Vec16<T>::unpack(cd[v], td);
-      Vec16<T>::unpack(gpk[v], tg);
+    for (int st = 0; st < DEPTH; ++st) {
+      const long long r = base + st * nwarp;
+      if (r >= rows) break;
+      const float mu = nmu[st], rs = nrs[st];
+      uint4 cx[NVA], cd[NVA];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int k = v * VEC + i;
-        xh[k] = (tx[i] - mu) * rs;
-        gd[k] = td[i] * tg[i];
-        dg[k] = fmaf(td[i], xh[k], dg[k]);
-        db[k] += td[i];
-        s1 += gd[k];
-        s2 = fmaf(gd[k], xh[k], s2);
-      }
-    }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+      for (int v = 0; v < NV; ++v) { cx[v] = nx[st][v]; cd[v] = nd[st][v]; }
+      if (r + DEPTH * nwarp < rows) fetch(st, r + DEPTH * nwarp);
+      float xh[PER_LANE], gd[PER_LANE];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float t[VEC];
+      for (int v = 0; v < NV; ++v) {
+        float tx[VEC], td[VEC], tg[VEC];
+        Vec16<T>::unpack(cx[v], tx);
+        Vec16<T>::unpack(cd[v], td);
+        if (HOIST) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const int k = v * VEC + i;
-        t[i] = rs * (gd[k] - s1 - xh[k] * s2);
-        if (DXSUM && !DROP) dsum[k] += to_f32<T>(from_f32<T>(t[i]));      // what a column sum of dx would read
-      }
-      Vec16IO<T>::store(dx + r * C + (v * 32 + lane) * VEC, t);
-      if (DXSUM && DROP) {
-        const uint32_t keep = drop_keep<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop);
-        float u[VEC];
+          for (int i = 0; i < VEC; ++i) tg[i] = gf[HOIST ? v * VEC + i : 0];
+        } else {
+          Vec16<T>::unpack(gpk[v], tg);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          u[i] = ((keep >> i) & 1u) ? to_f32<T>(from_f32<T>(to_f32<T>(from_f32<T>(t[i])) * drop.scale)) : 0.f;
-          dsum[v * VEC + i] += u[i];
+          const int k = v * VEC + i;
+          xh[k] = (tx[i] - mu) * rs;
+          gd[k] = td[i] * tg[i];
+          dg[k] = fmaf(td[i], xh[k], dg[k]);
+          db[k] += td[i];
+          s1 += gd[k];
+          s2 = fmaf(gd[k], xh[k], s2);
         }
-        Vec16IO<T>::store(dx_masked + r * C + (v * 32 + lane) * VEC, u);
+      }
+      s1 = mean_of(warp_sum(s1));
+      s2 = mean_of(warp_sum(s2));
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        float t[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const int k = v * VEC + i;
+          t[i] = rs * (gd[k] - s1 - xh[k] * s2);
+          if (DXSUM && !DROP) dsum[k] += to_f32<T>(from_f32<T>(t[i]));      // what a column sum of dx would read
+        }
+        Vec16IO<T>::store(dx + r * C + (v * 32 + lane) * VEC, t);
+        if (DXSUM && DROP) {
+          bool keep[VEC];
+          drop_keep_flags<VEC>((unsigned long long)r * C + (v * 32 + lane) * VEC, seed, step, drop.site,
+                               drop.thresh, keep);
+          float u[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            u[i] = keep[i] ? to_f32<T>(from_f32<T>(to_f32<T>(from_f32<T>(t[i])) * drop.scale)) : 0.f;
+            dsum[v * VEC + i] += u[i];
+          }
+          Vec16IO<T>::store(dx_masked + r * C + (v * 32 + lane) * VEC, u);
+        }
       }
     }
   }
@@ -299,9 +400,9 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __rest
       const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)w * NOUT * C + c);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    red_add_f32x4(ws + kWsHeaderFloats + c, s.x, s.y, s.z, s.w);
+    red_add_f32x4(my_strip(ws, blockIdx.x, NOUT * C) + c, s.x, s.y, s.z, s.w);
   }
-  finalize_columns<T>(ws, dgamma_dbeta, NOUT * C);
+  finalize_columns<T>(ws, dgamma_dbeta, NOUT * C, gridDim.x);
 }
 
 // Column sums of a (rows, C) matrix: every CTA reduces its rows, adds into the strip, the last CTA
@@ -324,33 +425,40 @@ colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
   float acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-  auto fetch = [&](long long r, float (&t)[VEC]) {
-    Vec16IO<T>::load(x + r * C + gidx * VEC, t);
+  // (relu_scale == 1: the product is the value itself, already representable in T)
+  auto finish = [&](long long r, const uint4& xr, const uint4& yr, float (&t)[VEC]) {
+    Vec16<T>::unpack(xr, t);
     if (RELU) {
       float m[VEC];
-      Vec16IO<T>::load(y + r * C + gidx * VEC, m);
+      Vec16<T>::unpack(yr, m);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i)
-        t[i] = m[i] > 0.f ? (relu_scale == 1.f ? t[i] : to_f32<T>(from_f32<T>(t[i] * relu_scale))) : 0.f;
+      for (int i = 0; i < VEC; ++i) t[i] = m[i] > 0.f ? to_f32<T>(from_f32<T>(t[i] * relu_scale)) : 0.f;
       Vec16IO<T>::store(dx + r * C + gidx * VEC, t);
     }
   };
   if (rl < row_lanes) {
     const long long step = (long long)gridDim.x * row_lanes;
     long long r = (long long)blockIdx.x * row_lanes + rl;
-    // four independent 16-byte loads in flight per thread
+    // four rows per trip: all their loads (x, and y with RELU) are issued before the first is consumed
     for (; r + 3 * step < rows; r += 4 * step) {
+      uint4 xr[4], yr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xr[k] = ldg128(x + (r + k * step) * C + gidx * VEC);
+        if (RELU) yr[k] = ldg128(y + (r + k * step) * C + gidx * VEC);
+        else yr[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
       float t0[VEC], t1[VEC], t2[VEC], t3[VEC];
-      fetch(r, t0);
-      fetch(r + step, t1);
-      fetch(r + 2 * step, t2);
-      fetch(r + 3 * step, t3);
+      finish(r, xr[0], yr[0], t0);
+      finish(r + step, xr[1], yr[1], t1);
+      finish(r + 2 * step, xr[2], yr[2], t2);
+      finish(r + 3 * step, xr[3], yr[3], t3);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
     }
     for (; r < rows; r += step) {
       float t[VEC];
-      fetch(r, t);
+      finish(r, ldg128(x + r * C + gidx * VEC), RELU ? ldg128(y + r * C + gidx * VEC) : make_uint4(0u, 0u, 0u, 0u), t);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[i] += t[i];
     }
@@ -365,23 +473,23 @@ colsum_kernel(const T* __restrict__ x, const T* __restrict__ y, T* __restrict__ 
         const float4 v = *reinterpret_cast<const float4*>(sm + (size_t)w * C + c);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
-      red_add_f32x4(ws + kWsHeaderFloats + c, s.x, s.y, s.z, s.w);
+      red_add_f32x4(my_strip(ws, blockIdx.x, C) + c, s.x, s.y, s.z, s.w);
     }
   } else {
     for (int c = threadIdx.x; c < C; c += kRowThreads) {
       float s = 0.f;
       for (int w = 0; w < row_lanes; ++w) s += sm[(size_t)w * C + c];
-      atomicAdd(ws + kWsHeaderFloats + c, s);
+      atomicAdd(my_strip(ws, blockIdx.x, C) + c, s);
     }
   }
-  finalize_columns<TO>(ws, out, C);
+  finalize_columns<TO>(ws, out, C, gridDim.x);
 }
 
-static int row_grid() {
+static int row_grid(int per_sm = 4) {
   int dev = 0, n = 148;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  return n * 4;
+  return n * per_sm;
 }
 
 int rowops_partial_rows() { return row_grid(); }
@@ -393,8 +501,10 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
                      float* mean, float* rstd, void* dx, float* partial, void* dgb, long long rows, int C,
                      float eps, const void* residual, void* sum_out, bool dxsum, const RowDropout& rd,
                      void* dx_masked, cudaStream_t st) {
+  // one wave of CTAs: as many per SM as the kernel's launch bound keeps resident
   const long long need = (rows + kRowThreads / 32 - 1) / (kRowThreads / 32);
-  const int grid = (int)(need < row_grid() ? need : row_grid());
+  const int fgrid_max = row_grid(PER_LANE <= 8 ? LN_FWD_MINBLOCKS : 4);
+  const int grid = (int)(need < fgrid_max ? need : fgrid_max);
   if (grid <= 0) return MSDA_OK;
   const bool dropping = rd.key != nullptr && rd.p > 0.f;
   DropArgs da{};
@@ -402,7 +512,7 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
     da.key_src = static_cast<const unsigned long long*>(rd.key);
     da.key_save = static_cast<unsigned long long*>(rd.key_save);
     da.site = rd.site;
-    da.thresh = (uint32_t)(rd.p * 65536.f + 0.5f);
+    da.thresh = drop_thresh(rd.p);
     da.scale = 1.f / (1.f - rd.p);
   }
   if (!bwd) {
@@ -423,7 +533,8 @@ static int ln_launch(bool bwd, const void* x, const void* dy, const void* gamma,
   // 7 000 queries) fewer CTAs, eight rows per warp, keep that fixed cost from dominating
   // (4 / 8 / 16 / 32 rows per warp: MapTRv2 decoder step 4.11 / 4.02 / 4.45 / 5.00 ms -- 4 to 8 is flat)
   const long long want = (rows + 8 * (kRowThreads / 32) - 1) / (8 * (kRowThreads / 32));
-  const int bgrid = (int)(want < row_grid() ? (want > 0 ? want : 1) : row_grid());
+  const int bgrid_max = row_grid(PER_LANE <= 8 ? (dropping ? LN_BWD_MINBLOCKS_DROP : LN_BWD_MINBLOCKS) : 4);
+  const int bgrid = (int)(want < bgrid_max ? (want > 0 ? want : 1) : bgrid_max);
   kfn<<<bgrid, kRowThreads, smem, st>>>(
       static_cast<const T*>(x), static_cast<const T*>(dy), static_cast<const T*>(gamma), mean, rstd,
       static_cast<T*>(dx), partial, static_cast<T*>(dgb), rows, C, static_cast<T*>(dx_masked), da);
@@ -460,21 +571,37 @@ grad_scale_kernel(const T* __restrict__ g, long long n, float limit, float* __re
   constexpr int VEC = Vec16<T>::N;
   float m = 0.f;
   const long long nv = n / VEC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto take = [&](const uint4& raw) {
     float t[VEC];
-    Vec16IO<T>::load(g + i * VEC, t);
+    Vec16<T>::unpack(raw, t);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) m = fmaxf(m, fabsf(t[k]));
+  };
+  for (; i + 3 * stride < nv; i += 4 * stride) {             // four independent 16-byte loads in flight
+    const uint4 r0 = ldg128(g + i * VEC), r1 = ldg128(g + (i + stride) * VEC);
+    const uint4 r2 = ldg128(g + (i + 2 * stride) * VEC), r3 = ldg128(g + (i + 3 * stride) * VEC);
+    take(r0);
+    take(r1);
+    take(r2);
+    take(r3);
   }
+  for (; i < nv; i += stride) take(ldg128(g + i * VEC));
   if (blockIdx.x == 0)
     for (long long i = nv * VEC + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(to_f32<T>(g[i])));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   unsigned* wsu = reinterpret_cast<unsigned*>(ws);
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(wsu + 1, __float_as_uint(m));   // non-negative floats order like uints
+  // one atomic per CTA (same-address atomics serialise in L2: one per warp cost ~5 us of a 13 us launch)
+  __shared__ float wmax[8];
   __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wmax[w]);
+    if (m > 0.f) atomicMax(wsu + 1, __float_as_uint(m));       // non-negative floats order like uints
     __threadfence();
     const unsigned ticket = atomicAdd(wsu, 1u);
     last = ticket == gridDim.x - 1;
@@ -569,36 +696,21 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
     for (int k = 0; k < 8; ++k) part[threadIdx.x][k] = csum[k];
     __syncthreads();
     const int C = cgroups * 8;
+    float* strip = my_strip(ws, blockIdx.y * gridDim.x + blockIdx.x, C);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int grp = c >> 3, k = c & 7;
       float s = 0.f;
       for (int th = grp; th < 256; th += cgroups) s += part[th][k];
-      atomicAdd(ws + kWsHeaderFloats + c, s);
+      atomicAdd(strip + c, s);
     }
-    // ticket over the whole (x, y) grid
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      unsigned* counter = reinterpret_cast<unsigned*>(ws);
-      const unsigned ticket = atomicAdd(counter, 1u);
-      last = (ticket == gridDim.x * gridDim.y - 1);
-      if (last) *counter = 0u;
-    }
-    __syncthreads();
-    if (last) {
-      __threadfence();
-      float* strip = ws + kWsHeaderFloats;
-      for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        colsum_out[c] = from_f32<TO>(__ldcg(strip + c));
-        strip[c] = 0.f;
-      }
-    }
+    finalize_columns<TO>(ws, colsum_out, C, gridDim.x * gridDim.y);       // ticket over the whole (x, y) grid
   }
 }
 
 int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, cudaStream_t st) {
-  const int grid = row_grid();
+  const long long need = (n / 8 + 255) / 256;
+  // a read-only stream: eight CTAs per SM keep enough 16-byte loads in flight (two per SM: 16.6 us, four: 13 us)
+  const int grid = (int)(need < row_grid(8) ? (need > 0 ? need : 1) : row_grid(8));
   if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, limit, ws);
   else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, limit, ws);
   else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, limit, ws);
@@ -672,22 +784,38 @@ relu_dropout_kernel(T* __restrict__ x, unsigned char* __restrict__ mask_out, lon
     drop.key_save[1] = step;
   }
   const long long chunks = n / VEC, stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += stride) {
-    const uint32_t keep = drop_keep<VEC>((unsigned long long)i * VEC, seed, step, drop);
-    if (mask_out != nullptr) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mask_out != nullptr) {                       // test hook: the keep mask itself
+    for (; i < chunks; i += stride) {
+      const uint32_t keep = drop_keep<VEC>((unsigned long long)i * VEC, seed, step, drop);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) mask_out[i * VEC + k] = (unsigned char)((keep >> k) & 1u);
-    } else {
-      float t[VEC];
-      Vec16<T>::unpack(*reinterpret_cast<const uint4*>(x + i * VEC), t);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float v = RELU ? fmaxf(t[k], 0.f) : t[k];
-        t[k] = ((keep >> k) & 1u) ? v * drop.scale : 0.f;
-      }
-      *reinterpret_cast<uint4*>(x + i * VEC) = Vec16<T>::pack(t);
     }
+    return;
   }
+  auto finish = [&](long long c, const uint4& raw) {
+    bool keep[VEC];
+    drop_keep_flags<VEC>((unsigned long long)c * VEC, seed, step, drop.site, drop.thresh, keep);
+    float t[VEC];
+    Vec16<T>::unpack(raw, t);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float v = RELU ? fmaxf(t[k], 0.f) : t[k];
+      t[k] = keep[k] ? v * drop.scale : 0.f;
+    }
+    *reinterpret_cast<uint4*>(x + c * VEC) = Vec16<T>::pack(t);
+  };
+  for (; i + 3 * stride < chunks; i += 4 * stride) {         // four independent 16-byte loads in flight
+    const uint4 r0 = *reinterpret_cast<const uint4*>(x + i * VEC);
+    const uint4 r1 = *reinterpret_cast<const uint4*>(x + (i + stride) * VEC);
+    const uint4 r2 = *reinterpret_cast<const uint4*>(x + (i + 2 * stride) * VEC);
+    const uint4 r3 = *reinterpret_cast<const uint4*>(x + (i + 3 * stride) * VEC);
+    finish(i, r0);
+    finish(i + stride, r1);
+    finish(i + 2 * stride, r2);
+    finish(i + 3 * stride, r3);
+  }
+  for (; i < chunks; i += stride) finish(i, *reinterpret_cast<const uint4*>(x + i * VEC));
 }
 
 int launch_relu_dropout(void* x, void* mask_out, long long n, int dtype, const RowDropout& rd, cudaStream_t st) {
@@ -699,7 +827,7 @@ int launch_relu_dropout(void* x, void* mask_out, long long n, int dtype, const R
   da.key_src = static_cast<const unsigned long long*>(rd.key);
   da.key_save = static_cast<unsigned long long*>(rd.key_save);
   da.site = rd.site;
-  da.thresh = (uint32_t)(rd.p * 65536.f + 0.5f);
+  da.thresh = drop_thresh(rd.p);
   da.scale = 1.f / (1.f - rd.p);
   const long long chunks = n / vec;
   if (chunks == 0) return MSDA_OK;

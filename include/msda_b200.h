@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 7
+#define MSDA_ABI_VERSION 8
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
 #define MSDA_F32  0
@@ -248,7 +248,7 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *     (Nk*M*Dh); the last tail_elems (tail_pixels*M*Dh) of each also sum tail_copies replica maps.
  *     colsum_out (C,) out_dtype or NULL: additionally the sums over all rows of the (n / C, C) view of
  *     `out` -- the bias gradient of the value projection -- saving a pass over the tensor; `partial` is
- *     the row kernels' zero-initialised scratch (64 + C floats, see below); C = 8 * (a divisor of 256).
+ *     the row kernels' zero-initialised scratch (64 + 8 * C floats, see below); C = 8 * (a divisor of 256).
  *     overflow_flag (may be NULL): a device int32 that is OR-ed with 1 when a non-finite accumulator
  *     slot is met -- a sticky word the host can poll at its leisure (defence in depth behind the
  *     scale bound above; nothing synchronises on the good path). */
@@ -265,10 +265,11 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
  *
  *   x, y, dy, dx  (rows, C) dtype;  gamma, beta (C,) dtype;  mean, rstd (rows,) fp32
  *   dgamma_dbeta  (2, C) dtype out: row 0 = d gamma, row 1 = d beta
- *   partial       fp32 scratch of 64 + 2 * C floats, ALL ZERO on entry and left all zero: a ticket
- *                 counter plus an fp32 strip that every CTA reduces its partial sums into; the
- *                 last CTA to finish converts the strip into the output (one launch); one
- *                 scratch buffer per stream
+ *   partial       fp32 scratch of 64 + 8 * 2 * C floats (ABI 8; 64 + 8 * n * C for a kernel with n output
+ *                 rows), ALL ZERO on entry and left all zero: a ticket counter plus eight fp32 strips;
+ *                 every CTA reduces its partial sums into one of them (reductions on one line serialise
+ *                 in L2, hence several strips) and the last CTA to finish sums the strips into the
+ *                 output (one launch); one scratch buffer per stream
  *   C must be 128, 256, 512 or 1024 for LayerNorm; a multiple of 16 bytes per row for colsum.
  * ------------------------------------------------------------------------------- */
 int rowops_workspace_rows(void);
@@ -283,7 +284,7 @@ int ln_bwd(const void* x, const void* dy, const void* gamma, const float* mean, 
  *     normalised; bit-identical to an add kernel followed by ln_fwd.
  *   ln_bwd_dxsum: ln_bwd that also returns the column sums of dx -- the bias gradient of the Linear
  *     layer that produced x -- as a third row: dgamma_dbeta_dxsum is (3, C), partial holds
- *     64 + 3 * C floats.                                                                       */
+ *     64 + 8 * 3 * C floats.                                                                      */
 int ln_residual_fwd(const void* x, const void* residual, const void* gamma, const void* beta,
                     void* sum_out, void* y, float* mean, float* rstd, int64_t rows, int C, float eps,
                     int dtype, void* stream);
