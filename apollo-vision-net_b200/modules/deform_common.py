@@ -74,19 +74,25 @@ class DeformAttnBase(BaseModule):
         self._is_init = True
 
 
-    def project_coords(self, query):
+    def project_coords(self, query, junction=None):
         """``sampling_offsets(query)`` and ``attention_weights(query)`` as ONE GEMM over the
         concatenated weights: returns (..., 3n) with the raw offsets
         of a query in columns [0, 2n) and its raw attention logits in [2n, 3n).  The parameters stay
         the reference's two Linear layers (checkpoint layout unchanged); the fused kernels read both
         column blocks in place and return one gradient tensor of the same layout, so the backward
-        is one dX GEMM, one dW GEMM and one bias reduction instead of two of each."""
+        is one dX GEMM, one dW GEMM and one bias reduction instead of two of each.  ``junction``: the query is
+        also the residual of the block (:class:`rowops.Junction`)."""
+        w, b = self.coords_weight()
+        return linear(query, w, b, junction)
+
+    def coords_weight(self):
+        """(weight, bias) of the merged offsets | logits projection."""
         w = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
         b = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-        return linear(query, w, b)
+        return w, b
 
 
-def finish_block(mod, output, identity, post_norm=None):
+def finish_block(mod, output, identity, post_norm=None, junction=None):
     """Tail of an attention block: ``dropout(output_proj(output)) + identity`` (reference
     temporal_self_attention.py:285-289, spatial_cross_attention.py:171-173, decoder.py:353-358),
     optionally followed by the layer's next LayerNorm (``post_norm``).  With the norm given the
@@ -97,7 +103,7 @@ def finish_block(mod, output, identity, post_norm=None):
     drop = mod.dropout
     if post_norm is not None and batch_first:
         return linear_add_layernorm(output, mod.output_proj, identity, post_norm,
-                                    p=drop.p if mod.training else 0.0)
+                                    p=drop.p if mod.training else 0.0, junction=junction)
     if post_norm is not None and output.dim() == 3 and output.shape[0] == 1:
         # sequence-first caller with one sample: (1, Nq, C) and (Nq, 1, C) hold the same rows in the same order
         return linear_add_layernorm(output.permute(1, 0, 2), mod.output_proj, identity, post_norm,

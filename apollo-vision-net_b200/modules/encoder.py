@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from .._lib import nvtx_range
 from ..fused_ops import BevGeometry, bev_point_sampling
-from ..rowops import LayerNorm, Linear, ReLU, advance_dropout_step, linear_add_layernorm
+from ..rowops import Junction, LayerNorm, Linear, ReLU, advance_dropout_step, linear, linear_add_layernorm
 from ..registry import (TRANSFORMER_LAYER, TRANSFORMER_LAYER_SEQUENCE, BaseModule, build_attention,
                         build_transformer_layer)
 
@@ -66,10 +66,12 @@ class FFN(BaseModule):
         if post_norm is not None and self.add_identity and len(self.layers) == 3:
             fc1, act, drop1 = self.layers[0]
             p1 = drop1.p if self.training else 0.0
-            h = fc1(x)
+            # x is also the residual: its two gradients meet in fc1's dX GEMM (rowops.Junction)
+            tok = Junction() if (res is x and isinstance(fc1, Linear) and torch.is_grad_enabled()) else None
+            h = linear(x, fc1.weight, fc1.bias, tok) if tok is not None else fc1(x)
             h = act.forward_dropout(h, p1) if hasattr(act, 'forward_dropout') else drop1(act(h))
             return linear_add_layernorm(h, self.layers[1], res, post_norm,
-                                        p=last_drop.p if self.training else 0.0)
+                                        p=last_drop.p if self.training else 0.0, junction=tok)
         out = self.layers(x)
         if self.add_identity:
             out = res + out

@@ -19,7 +19,7 @@ import torch.nn as nn
 
 from ..fused_ops import SpatialCrossAttnFunction, hit_bits_from_mask
 from ..registry import ATTENTION, BaseModule, build_attention, xavier_init
-from ..rowops import Linear, linear_add_layernorm
+from ..rowops import Junction, Linear, linear_add_layernorm
 from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
@@ -148,13 +148,15 @@ class SpatialCrossAttention(BaseModule):
         num_cams, l, bs_v, _ = value.shape
         value = value.permute(2, 0, 1, 3).reshape(bs * self.num_cams, l, self.embed_dims)
         v = da.value_proj(value).view(bs * self.num_cams, l, da.num_heads, -1)
-        coords = da.project_coords(query)          # offsets | logits of a query, one GEMM
+        # the query is also the block's residual: its two gradients meet in the projection's dX GEMM
+        tok = Junction() if (post_norm is not None and query is inp_residual and torch.is_grad_enabled()) else None
+        coords = da.project_coords(query, tok)     # offsets | logits of a query, one GEMM
         slots = SpatialCrossAttnFunction.apply(v, spatial_shapes, level_start_index, coords, None,
                                                reference_points_cam, mask_u8, hit_bits,
                                                self.num_cams, self._grid_w(bev_h, bev_w, num_query), lists)
         # (the residual is added without a permute whatever batch_first says, reference :171-173)
         if post_norm is not None:
             return linear_add_layernorm(slots.to(query.dtype), self.output_proj, inp_residual, post_norm,
-                                        p=self.dropout.p if self.training else 0.0)
+                                        p=self.dropout.p if self.training else 0.0, junction=tok)
         out = self.dropout(self.output_proj(slots.to(query.dtype))) + inp_residual
         return out if post_norm is None else post_norm(out)

@@ -13,6 +13,7 @@ import torch.nn as nn
 
 from ..fused_ops import QueueDeformAttnFunction
 from ..registry import ATTENTION
+from ..rowops import Junction, paired_query_linear
 from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
@@ -42,7 +43,11 @@ class TemporalSelfAttention(DeformAttnBase):
             value = torch.stack([query, query], 1).reshape(bs * 2, len_bev, c)
         if identity is None:
             identity = query
-        if query_pos is not None:
+        # batch-first callers keep the positional sum for the projection below, which writes it straight into
+        # its concatenated input and meets the residual's gradient in its dX GEMM (rowops.Junction)
+        raw_query, raw_pos = query, query_pos
+        defer_pos = self.batch_first and query.is_cuda and torch.is_grad_enabled()
+        if query_pos is not None and not defer_pos:
             query = query + query_pos
         if not self.batch_first:
             query = query.permute(1, 0, 2)
@@ -55,12 +60,17 @@ class TemporalSelfAttention(DeformAttnBase):
         # value[:bs] pairs every query with the same cell of the first queue entry; under BEV row
         # sharding the queries are the slice ``row_slice`` of the value's cells
         paired = value[:bs] if row_slice is None else value[:bs, row_slice[0]:row_slice[1]]
-        query = torch.cat([paired, query], -1)
+        if defer_pos:
+            tok = Junction() if (post_norm is not None and identity is raw_query) else None
+            w, b = self.coords_weight()
+            coords = paired_query_linear(paired, raw_query, raw_pos, w, b, tok)
+        else:
+            tok = None
+            coords = self.project_coords(torch.cat([paired, query], -1))
         value = self.value_proj(value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.reshape(bs * Q, num_value, M, -1)
-        coords = self.project_coords(query)             # offsets | logits of a query, one GEMM
         n = M * Q * L * P
 
         grid_w = int(bev_w) if (bev_h and bev_w and int(bev_h) * int(bev_w) == num_query) else 0
@@ -88,4 +98,4 @@ class TemporalSelfAttention(DeformAttnBase):
             raise ValueError('Last dim of reference_points must be 2 or 4, '
                              f'but get {reference_points.shape[-1]} instead.')
 
-        return finish_block(self, output.to(query.dtype), identity, post_norm)
+        return finish_block(self, output.to(query.dtype), identity, post_norm, junction=tok)

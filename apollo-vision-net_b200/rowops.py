@@ -137,6 +137,52 @@ class LayerNorm(nn.LayerNorm):
         return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
 
 
+class Junction:
+    """The gradient junction at the input of a residual block, made explicit.
+
+    A post-norm block uses its input twice: as the residual of its tail (``LinearAddLayerNormFunction``) and
+    as the input of the branch's first Linear layer.  autograd would add the two gradients with a separate
+    kernel (60 MB of traffic for a 20 MB tensor, 17 times per encoder step).  With a junction shared by the
+    two nodes the tail's backward parks the residual gradient here instead of returning it, and the first
+    Linear's backward -- which by data dependence always runs later in the same pass -- accumulates its
+    ``dy @ W`` onto it through the GEMM's beta = 1 epilogue and returns the sum as THE gradient of the input.
+    A gradient that was parked and never collected raises at the end of the backward pass."""
+
+    __slots__ = ('ds', 'consumers', 'checked')
+
+    def __init__(self):
+        self.ds = None
+        self.consumers = 0
+        self.checked = False
+
+    def park(self, ds):
+        self.ds = ds
+        if not self.checked:
+            self.checked = True
+            torch.autograd.Variable._execution_engine.queue_callback(self._check)
+
+    def take(self):
+        ds, self.ds = self.ds, None
+        return ds
+
+    def _check(self):
+        self.checked = False
+        if self.ds is not None:
+            self.ds = None
+            raise RuntimeError('a residual gradient parked at a Junction was never collected: the branch of the '
+                               'block did not run its backward (detached branch?)')
+
+
+def _accumulate_dx(junction, dy2, weight, shape):
+    """``dy2 @ weight`` as the input gradient of a Linear layer, added onto a parked residual gradient when
+    the layer's input is a block's junction (one GEMM with beta = 1, no separate add kernel)."""
+    ds = junction.take() if junction is not None else None
+    if ds is not None and ds.is_contiguous() and ds.dtype == dy2.dtype and ds.numel() == dy2.shape[0] * weight.shape[1]:
+        return ds.view(dy2.shape[0], weight.shape[1]).addmm_(dy2, weight).view(shape)
+    dx = (dy2 @ weight).view(shape)
+    return dx if ds is None else dx + ds.view(shape)
+
+
 class LinearAddLayerNormFunction(Function):
     """y = LayerNorm(x W^T + b + residual): the post-norm tail of an attention / FFN block as one
     autograd node.  Forward: cuBLAS GEMM, then one kernel for the residual add and the
@@ -146,8 +192,10 @@ class LinearAddLayerNormFunction(Function):
 
     @staticmethod
     @custom_fwd(cast_inputs=None)
-    def forward(ctx, x, weight, bias, residual, gamma, beta, eps, p=0.0):
-        """``p`` > 0: y = LayerNorm(dropout(x W^T + b) + residual) with the mask drawn in the kernel."""
+    def forward(ctx, x, weight, bias, residual, gamma, beta, eps, p=0.0, junction=None):
+        """``p`` > 0: y = LayerNorm(dropout(x W^T + b) + residual) with the mask drawn in the kernel.
+        ``junction``: park the residual's gradient there (see :class:`Junction`) instead of returning it."""
+        ctx.junction = junction if (junction is not None and junction.consumers > 0) else None
         C = weight.shape[0]
         x2 = x.reshape(-1, x.shape[-1])
         rows = x2.shape[0]
@@ -200,10 +248,14 @@ class LinearAddLayerNormFunction(Function):
         x_shape, res_shape = ctx.shapes
         dx = (dlin @ weight).view(x_shape) if ctx.needs_input_grad[0] else None
         dw = weight_bias_grad(dlin, x2, weight, want_bias=False)[0] if ctx.needs_input_grad[1] else None
-        return dx, dw, out3[2], ds.view(res_shape), out3[0], out3[1], None, None
+        dres = ds.view(res_shape)
+        if ctx.junction is not None and ctx.needs_input_grad[3]:
+            ctx.junction.park(ds)
+            dres = None
+        return dx, dw, out3[2], dres, out3[0], out3[1], None, None, None
 
 
-def linear_add_layernorm(x, linear_mod, residual, norm, p=0.0):
+def linear_add_layernorm(x, linear_mod, residual, norm, p=0.0, junction=None):
     """``norm(dropout_p(linear_mod(x)) + residual)`` through :class:`LinearAddLayerNormFunction` when
     the tensors qualify (CUDA, one dtype, supported width, affine LayerNorm over the last dim with a
     bias-carrying Linear); the plain composition otherwise.  ``p``: dropout probability of the training
@@ -217,7 +269,8 @@ def linear_add_layernorm(x, linear_mod, residual, norm, p=0.0):
     if not ok:
         out = linear_mod(x)
         return norm((F.dropout(out, p, True) if p > 0 else out) + residual)
-    return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps, float(p))
+    return LinearAddLayerNormFunction.apply(x, w, b, residual, norm.weight, norm.bias, norm.eps, float(p),
+                                            junction)
 
 
 # ---- bias gradients that a producer kernel already has -----------------------------------------
@@ -373,9 +426,13 @@ class LinearFunction(Function):
 
     @staticmethod
     @custom_fwd(cast_inputs=None)
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, junction=None):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.junction = None
+        if junction is not None and ctx.needs_input_grad[0]:
+            junction.consumers += 1
+            ctx.junction = junction
         # write into a freshly allocated tensor of the final shape: the result must not be a
         # view (callers apply in-place activations to it, e.g. the FFN's ReLU(inplace=True))
         out = torch.empty(x.shape[:-1] + (weight.shape[0],), dtype=x.dtype, device=x.device)
@@ -396,7 +453,7 @@ class LinearFunction(Function):
         x2 = x.reshape(-1, x.shape[-1])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = (dy2 @ weight).view(x.shape)
+            dx = _accumulate_dx(ctx.junction, dy2, weight, x.shape)
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         ready = _take_bias_grad(dy, weight.shape[0]) if want_b else None
         if ready is not None:                               # the producer of dy already summed its rows
@@ -408,13 +465,82 @@ class LinearFunction(Function):
         elif want_b:
             dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
             db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear(x, weight, bias=None):
-    """``F.linear`` whose backward computes the bias gradient with the column-sum kernel."""
+class PairedQueryLinearFunction(Function):
+    """``[paired | query + pos] W^T + b`` -- the offsets / weights projection of TemporalSelfAttention, whose
+    input is the previous BEV's cell next to the positioned query (temporal_self_attention.py:199-204).
+    The sum is written straight into the right half of the concatenated input (no separate ``cat``); the
+    backward computes only the halves of dX somebody needs (``paired`` is history: no gradient) and, when
+    ``query`` is the block's residual, accumulates the query half onto the parked residual gradient
+    (:class:`Junction`) -- unless ``pos`` wants its own gradient, which is that half alone."""
+
+    @staticmethod
+    @custom_fwd(cast_inputs=None)
+    def forward(ctx, paired, query, pos, weight, bias, junction=None):
+        C = query.shape[-1]
+        rows = query.numel() // C
+        cat = torch.empty(query.shape[:-1] + (2 * C,), dtype=query.dtype, device=query.device)
+        cat[..., :C].copy_(paired)
+        if pos is not None:
+            torch.add(query, pos, out=cat[..., C:])
+        else:
+            cat[..., C:].copy_(query)
+        out = torch.empty(query.shape[:-1] + (weight.shape[0],), dtype=query.dtype, device=query.device)
+        torch.addmm(bias, cat.view(rows, 2 * C), weight.t(), out=out.view(rows, weight.shape[0]))
+        ctx.save_for_backward(cat, weight)
+        ctx.shapes = (paired.shape, query.shape, None if pos is None else pos.shape)
+        ctx.junction = None
+        if junction is not None and ctx.needs_input_grad[1]:
+            junction.consumers += 1
+            ctx.junction = junction
+        return out
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd
+    def backward(ctx, dy):
+        cat, weight = ctx.saved_tensors
+        paired_shape, query_shape, pos_shape = ctx.shapes
+        O = weight.shape[0]
+        C = cat.shape[-1] // 2
+        dy2 = dy.reshape(-1, O)
+        d_paired = d_query = d_pos = dw = db = None
+        if ctx.needs_input_grad[0]:
+            d_paired = (dy2 @ weight[:, :C]).view(paired_shape)
+        w_q = weight[:, C:]
+        if pos_shape is not None and ctx.needs_input_grad[2]:
+            dq = (dy2 @ w_q).view(query_shape)
+            d_pos = dq
+            if ctx.needs_input_grad[1]:
+                ds = ctx.junction.take() if ctx.junction is not None else None
+                d_query = dq if ds is None else dq + ds.view(query_shape)
+        elif ctx.needs_input_grad[1]:
+            d_query = _accumulate_dx(ctx.junction, dy2, w_q, query_shape)
+        if ctx.needs_input_grad[3]:
+            dw, db = weight_bias_grad(dy2, cat.view(-1, 2 * C), weight, want_bias=ctx.needs_input_grad[4])
+        elif ctx.needs_input_grad[4]:
+            dy2c = dy2 if dy2.is_contiguous() else dy2.contiguous()
+            db = column_sum(dy2c, weight.dtype) if _colsum_supported(dy2c) else dy2.sum(0)
+        return d_paired, d_query, d_pos, dw, db, None
+
+
+def paired_query_linear(paired, query, pos, weight, bias, junction=None):
+    """See :class:`PairedQueryLinearFunction`; the plain composition when the tensors do not qualify."""
+    if (query.is_cuda and torch.is_grad_enabled() and query.dtype == weight.dtype == paired.dtype and
+            query.dtype in _DTYPE_CODE and bias is not None and paired.shape == query.shape and
+            (pos is None or (pos.shape == query.shape and pos.dtype == query.dtype))):
+        return PairedQueryLinearFunction.apply(paired, query, pos, weight, bias, junction)
+    q = query if pos is None else query + pos
+    return linear(torch.cat([paired, q], -1), weight, bias)
+
+
+def linear(x, weight, bias=None, junction=None):
+    """``F.linear`` whose backward computes the bias gradient with the column-sum kernel.  ``junction``: ``x``
+    is also the residual of the block's tail, whose gradient this layer's backward collects (:class:`Junction`)."""
     if x.is_cuda and torch.is_grad_enabled() and x.dtype == weight.dtype and x.dtype in _DTYPE_CODE:
-        return LinearFunction.apply(x, weight, bias)
+        return LinearFunction.apply(x, weight, bias, junction)
     return F.linear(x, weight, bias)
 
 
