@@ -41,6 +41,7 @@ _SIGNATURES = {
     'tsa_fwd': (_c_int, [_c_vp] * 7 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_vp]),
     'tsa_bwd': (_c_int, [_c_vp] * 10 + [_c_int] * 9 + [_c_f, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_vp, _c_vp]),
     'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp]),
+    'grad_amax_scale_zero': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp, _c_i64, _c_vp]),
     'unscale_cast': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_vp]),
     'rowops_workspace_rows': (_c_int, []),
     'ln_fwd': (_c_int, [_c_vp] * 6 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),

@@ -448,7 +448,15 @@ int relu_bwd_colsum(const void* dy, const void* y, void* dx, void* colsum_out, f
 int grad_amax_scale(const void* g, int64_t n, int dtype, float limit, float* ws, void* stream) {
   if (n < 0 || !ws || (n > 0 && !g) || !(limit > 0.f))
     return set_error(MSDA_ERR_BAD_ARGUMENT, "grad_amax_scale: bad argument");
-  return launch_grad_scale(g, n, dtype, limit, ws, static_cast<cudaStream_t>(stream));
+  return launch_grad_scale(g, n, dtype, limit, ws, nullptr, 0, static_cast<cudaStream_t>(stream));
+}
+
+int grad_amax_scale_zero(const void* g, int64_t n, int dtype, float limit, float* ws, void* zero, int64_t zero_bytes,
+                         void* stream) {
+  if (n < 0 || !ws || (n > 0 && !g) || !(limit > 0.f) || zero_bytes < 0 || (zero_bytes > 0 && !zero) ||
+      zero_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(zero) & 15) != 0)
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "grad_amax_scale_zero: bad argument (zero: 16-byte aligned, a multiple of 16 bytes)");
+  return launch_grad_scale(g, n, dtype, limit, ws, zero, zero_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,

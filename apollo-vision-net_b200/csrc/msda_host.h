@@ -105,7 +105,8 @@ constexpr int kWgHeaderFloats = 64;      // ticket counter in front of the linea
 long long wgrad_workspace_floats(int O, int I);
 int launch_wgrad(const void* dy, const void* x, void* dW, void* db, float* ws, long long N, int O, int I,
                  int dtype, cudaStream_t st);
-int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, cudaStream_t st);
+int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, void* zero, long long zero_bytes,
+                      cudaStream_t st);
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,
                         float* ws, void* colsum_out, int C, int* overflow, cudaStream_t st);

@@ -567,8 +567,14 @@ static int ln_dispatch(bool bwd, const void* x, const void* dy, const void* gamm
 // ws layout (floats): [0] ticket counter, [1] running max bits, [16] scale out.
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_scale_kernel(const T* __restrict__ g, long long n, float limit, float* __restrict__ ws) {
+grad_scale_kernel(const T* __restrict__ g, long long n, float limit, float* __restrict__ ws,
+                  uint4* __restrict__ zero, long long zero_chunks) {
   constexpr int VEC = Vec16<T>::N;
+  // the accumulator the scale is for starts at zero: cleared here (16-byte chunks), beside the read-only
+  // stream of the maximum, instead of by a fill launch of its own
+  for (long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x; z < zero_chunks;
+       z += (long long)gridDim.x * blockDim.x)
+    zero[z] = make_uint4(0u, 0u, 0u, 0u);
   float m = 0.f;
   const long long nv = n / VEC;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -707,13 +713,17 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
   }
 }
 
-int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, cudaStream_t st) {
-  const long long need = (n / 8 + 255) / 256;
+int launch_grad_scale(const void* g, long long n, int dtype, float limit, float* ws, void* zero, long long zero_bytes,
+                      cudaStream_t st) {
+  const long long zc = zero != nullptr ? zero_bytes / 16 : 0;
+  const long long work = n / 8 > zc ? n / 8 : zc;
+  const long long need = (work + 255) / 256;
   // a read-only stream: eight CTAs per SM keep enough 16-byte loads in flight (two per SM: 16.6 us, four: 13 us)
   const int grid = (int)(need < row_grid(8) ? (need > 0 ? need : 1) : row_grid(8));
-  if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, limit, ws);
-  else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, limit, ws);
-  else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, limit, ws);
+  uint4* z = static_cast<uint4*>(zero);
+  if (dtype == MSDA_F32) grad_scale_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), n, limit, ws, z, zc);
+  else if (dtype == MSDA_BF16) grad_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), n, limit, ws, z, zc);
+  else grad_scale_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(g), n, limit, ws, z, zc);
   count_launch();
   return check_launch("grad_amax_scale");
 }

@@ -219,16 +219,24 @@ def _accumulator(value, g_out, num_levels=1, rows_per_slot=0, replicas=True):
         ws = torch.zeros(64, dtype=torch.float32, device=dev)
         _scale_ws[key] = ws
     limit = min(4.0, 32768.0 / max(1, int(rows_per_slot)))
+    # the launch that finds max|g_out| also clears the accumulator (no fill launch of its own)
+    acc = torch.empty(value.shape, dtype=torch.float16, device=dev)
+    fused_zero = (acc.numel() * 2) % 16 == 0 and acc.data_ptr() % 16 == 0
     with torch.cuda.device(dev):
-        _lib.call('grad_amax_scale', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
-                  float(limit), ws.data_ptr(), _stream_ptr(value))
+        if fused_zero:
+            _lib.call('grad_amax_scale_zero', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
+                      float(limit), ws.data_ptr(), acc.data_ptr(), acc.numel() * 2, _stream_ptr(value))
+        else:
+            acc.zero_()
+            _lib.call('grad_amax_scale', g_out.data_ptr(), g_out.numel(), _DTYPE_CODE[g_out.dtype],
+                      float(limit), ws.data_ptr(), _stream_ptr(value))
     maps, Nk, M, Dh = value.shape
     tail, tail_px = None, 0
     if replicas and num_levels > 1 and Nk >= 4 * _TAIL_FRACTION and (M * Dh) % 8 == 0 and \
             os.environ.get('APOLLO_B200_TAIL_REPLICAS', '1') != '0':
         tail_px = Nk // _TAIL_FRACTION
         tail = torch.zeros((_TAIL_COPIES, maps, tail_px, M, Dh), dtype=torch.float16, device=dev)
-    return torch.zeros(value.shape, dtype=torch.float16, device=dev), _lib.F16, ws[16:17], tail, tail_px
+    return acc, _lib.F16, ws[16:17], tail, tail_px
 
 
 def _finish_accumulator(acc, code, scale, value, tail=None, tail_px=0):

@@ -252,6 +252,31 @@ class BEVFormerEncoder(BaseModule):
             return geo
         return geo.reference_points_cam, geo.bev_mask
 
+    def _hoisted_sca_values(self, key, value, bs):
+        """Every layer's SpatialCrossAttention projects the SAME camera features with its own ``value_proj``
+        (spatial_cross_attention.py:338-343, once per layer).  When the features want a gradient the
+        projections of all layers are taken in front of the layer loop as ONE autograd node
+        (:class:`decoder.HoistedValueProjFunction`), whose backward accumulates the feature gradient with
+        beta = 1 GEMMs -- otherwise autograd adds six 95 MB gradients with five separate kernels.  Returns a
+        list of (bs * num_cams * Nk, C) tensors, or None (every layer then projects for itself)."""
+        from .decoder import HoistedValueProjFunction
+        from .spatial_cross_attention import MSDeformableAttention3D, SpatialCrossAttention
+        if (len(self.layers) < 2 or not torch.is_tensor(value) or value.dim() != 4 or not value.is_cuda or
+                not (torch.is_grad_enabled() and value.requires_grad) or (key is not None and key is not value)):
+            return None
+        found = []
+        for layer in self.layers:
+            mods = [a for a in getattr(layer, 'attentions', []) if isinstance(a, SpatialCrossAttention)]
+            if len(mods) != 1 or not isinstance(mods[0].deformable_attention, MSDeformableAttention3D):
+                return None
+            vp = mods[0].deformable_attention.value_proj
+            if vp.bias is None or vp.weight.dtype != value.dtype or vp.weight.shape != (value.shape[-1],) * 2:
+                return None
+            found.append(vp)
+        num_cams, l, bs_v, C = value.shape
+        flat = value.permute(2, 0, 1, 3).reshape(bs_v * num_cams * l, C)
+        return list(HoistedValueProjFunction.apply(flat, *[vp.weight for vp in found], *[vp.bias for vp in found]))
+
     def forward(self, bev_query, key, value, *args, bev_z=None, bev_h=None, bev_w=None,
                 bev_pos=None, spatial_shapes=None, level_start_index=None, valid_ratios=None,
                 prev_bev=None, shift=0., img_metas=None, lidar2img=None, img_shape=None,
@@ -321,7 +346,10 @@ class BEVFormerEncoder(BaseModule):
             geo = geo.rows(q0, q1)
             kwargs = dict(kwargs, row_slice=(q0, q1))
 
-        for layer in self.layers:
+        projected = self._hoisted_sca_values(key, value, bs)
+        for li, layer in enumerate(self.layers):
+            if projected is not None:
+                kwargs['_sca_projected_value'] = projected[li]
             output = layer(bev_query, key, value, *args, bev_pos=bev_pos, ref_2d=hybird_ref_2d,
                            ref_3d=ref_3d, bev_h=shard_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
                            level_start_index=level_start_index,

@@ -146,8 +146,12 @@ class SpatialCrossAttention(BaseModule):
             hit_bits = hit_bits_from_mask(mask_b)
             mask_u8 = mask_b.contiguous().view(torch.uint8)
         num_cams, l, bs_v, _ = value.shape
-        value = value.permute(2, 0, 1, 3).reshape(bs * self.num_cams, l, self.embed_dims)
-        v = da.value_proj(value).view(bs * self.num_cams, l, da.num_heads, -1)
+        projected = kwargs.get('_sca_projected_value')
+        if projected is not None:                  # hoisted in front of the layer loop (encoder._hoisted_sca_values)
+            v = projected.view(bs * self.num_cams, l, da.num_heads, -1)
+        else:
+            value = value.permute(2, 0, 1, 3).reshape(bs * self.num_cams, l, self.embed_dims)
+            v = da.value_proj(value).view(bs * self.num_cams, l, da.num_heads, -1)
         # the query is also the block's residual: its two gradients meet in the projection's dX GEMM
         tok = Junction() if (post_norm is not None and query is inp_residual and torch.is_grad_enabled()) else None
         coords = da.project_coords(query, tok)     # offsets | logits of a query, one GEMM

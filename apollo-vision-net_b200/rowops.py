@@ -471,8 +471,7 @@ class LinearFunction(Function):
 class PairedQueryLinearFunction(Function):
     """``[paired | query + pos] W^T + b`` -- the offsets / weights projection of TemporalSelfAttention, whose
     input is the previous BEV's cell next to the positioned query (temporal_self_attention.py:199-204).
-    The sum is written straight into the right half of the concatenated input (no separate ``cat``); the
-    backward computes only the halves of dX somebody needs (``paired`` is history: no gradient) and, when
+    The backward computes only the halves of dX somebody needs (``paired`` is history: no gradient) and, when
     ``query`` is the block's residual, accumulates the query half onto the parked residual gradient
     (:class:`Junction`) -- unless ``pos`` wants its own gradient, which is that half alone."""
 
@@ -481,12 +480,9 @@ class PairedQueryLinearFunction(Function):
     def forward(ctx, paired, query, pos, weight, bias, junction=None):
         C = query.shape[-1]
         rows = query.numel() // C
-        cat = torch.empty(query.shape[:-1] + (2 * C,), dtype=query.dtype, device=query.device)
-        cat[..., :C].copy_(paired)
-        if pos is not None:
-            torch.add(query, pos, out=cat[..., C:])
-        else:
-            cat[..., C:].copy_(query)
+        # (one vectorised add and one cat: writing the sum straight into the right half of the buffer takes
+        # torch's strided element-wise kernels, 52 us against 28 us for the pair at 40 000 x 256)
+        cat = torch.cat([paired, query if pos is None else query + pos], -1)
         out = torch.empty(query.shape[:-1] + (weight.shape[0],), dtype=query.dtype, device=query.device)
         torch.addmm(bias, cat.view(rows, 2 * C), weight.t(), out=out.view(rows, weight.shape[0]))
         ctx.save_for_backward(cat, weight)

@@ -253,6 +253,10 @@ int tsa_bwd(const void* value, const int64_t* shapes, const int64_t* starts,
  *     slot is met -- a sticky word the host can poll at its leisure (defence in depth behind the
  *     scale bound above; nothing synchronises on the good path). */
 int grad_amax_scale(const void* g, int64_t n, int dtype, float limit, float* ws, void* stream);
+/* The same, and `zero` (zero_bytes, a multiple of 16, 16-byte aligned) is cleared by the same launch: the
+ * accumulator the scale is for, instead of a fill launch of its own (ABI 8). */
+int grad_amax_scale_zero(const void* g, int64_t n, int dtype, float limit, float* ws, void* zero,
+                         int64_t zero_bytes, void* stream);
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
                  void* colsum_out, float* partial, int C, int32_t* overflow_flag, void* stream);
