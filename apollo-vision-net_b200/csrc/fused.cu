@@ -42,6 +42,16 @@ constexpr int kFusedThreads = 256;
 #ifndef FUSED_BWD_MINBLOCKS
 #define FUSED_BWD_MINBLOCKS 3
 #endif
+// The fixed-shape TSA forward (short rows: latency bound, not L1 bound, and 49 registers once its shapes are
+// constants) runs five CTAs per SM: 78.9 -> 67.7 us; six (40 registers): 73.7 us.  The fixed-shape SCA forward
+// does not care (235.6 us at four and at five), the backward kernels lose at two or four
+// (tsa_bwd 169 -> 197 us either way): profiles/r02_fixed_shapes.md.
+#ifndef FUSED_TSA_FWD_MINBLOCKS
+#define FUSED_TSA_FWD_MINBLOCKS 5
+#endif
+#ifndef FUSED_TSA_BWD_MINBLOCKS
+#define FUSED_TSA_BWD_MINBLOCKS FUSED_BWD_MINBLOCKS
+#endif
 #define FUSED_PRAGMA(x) _Pragma(#x)
 #define FUSED_UNROLL(n) FUSED_PRAGMA(unroll n)
 enum { MODE_SCA = 0, MODE_TSA = 1 };
@@ -283,7 +293,7 @@ __device__ __forceinline__ void stage_row(const FusedArgs& a, const FusedLevels&
 }
 
 template <typename T, typename CT, int TPH, int MODE, int FIX>
-__global__ void __launch_bounds__(kFusedThreads, FUSED_FWD_MINBLOCKS)
+__global__ void __launch_bounds__(kFusedThreads, (MODE == 1 && FIX != 0) ? FUSED_TSA_FWD_MINBLOCKS : FUSED_FWD_MINBLOCKS)
 fused_fwd_kernel(const FusedArgs a_in) {
   const FusedArgs a = fix_shape<MODE, FIX, true>(a_in);
   constexpr int VEC = Vec16<T>::N;
@@ -497,7 +507,7 @@ fused_fwd_kernel(const FusedArgs a_in) {
 }
 
 template <typename T, typename CT, int TPH, int MODE, bool ACC_HALF, int FIX>
-__global__ void __launch_bounds__(kFusedThreads, FUSED_BWD_MINBLOCKS)
+__global__ void __launch_bounds__(kFusedThreads, (MODE == 1 && FIX != 0) ? FUSED_TSA_BWD_MINBLOCKS : FUSED_BWD_MINBLOCKS)
 fused_bwd_kernel(const FusedArgs a_in) {
   const FusedArgs a = fix_shape<MODE, FIX, false>(a_in);
   constexpr int VEC = Vec16<T>::N;
