@@ -43,6 +43,7 @@ _SIGNATURES = {
     'grad_amax_scale': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp]),
     'grad_amax_scale_zero': (_c_int, [_c_vp, _c_i64, _c_int, _c_f, _c_vp, _c_vp, _c_i64, _c_vp]),
     'unscale_cast': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_vp]),
+    'unscale_cast_strided': (_c_int, [_c_vp, _c_vp, _c_vp, _c_i64, _c_int, _c_vp, _c_int, _c_i64, _c_i64, _c_vp, _c_vp, _c_int, _c_vp, _c_i64, _c_vp]),
     'rowops_workspace_rows': (_c_int, []),
     'ln_fwd': (_c_int, [_c_vp] * 6 + [_c_i64, _c_int, _c_f, _c_int, _c_vp]),
     'ln_bwd': (_c_int, [_c_vp] * 8 + [_c_i64, _c_int, _c_int, _c_vp]),

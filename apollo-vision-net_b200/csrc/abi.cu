@@ -462,6 +462,19 @@ int grad_amax_scale_zero(const void* g, int64_t n, int dtype, float limit, float
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
                  void* colsum_out, float* partial, int C, int32_t* overflow_flag, void* stream) {
+  return unscale_cast_strided(acc_f16, out, scale, n, out_dtype, tail, tail_copies, map_elems, tail_elems, colsum_out,
+                              partial, C, overflow_flag, 0, stream);
+}
+
+int unscale_cast_strided(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
+                         const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
+                         void* colsum_out, float* partial, int C, int32_t* overflow_flag, int64_t out_row_stride,
+                         void* stream) {
+  if (out_row_stride != 0 &&
+      (C <= 0 || C % 8 != 0 || n % C != 0 || out_row_stride < C || out_row_stride % 8 != 0 ||
+       (reinterpret_cast<uintptr_t>(out) & 15) != 0 || (tail && tail_copies > 0)))
+    return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast_strided: rows of C = 8k columns, a row stride >= C that is a "
+                     "multiple of 8, a 16-byte aligned output and no tail replicas");
   if (colsum_out) {
     const int64_t m = (tail && tail_copies > 0) ? map_elems : n;
     if (!partial || C <= 0 || C % 8 != 0 || 256 % (C / 8) != 0 || m % C != 0 || n % 8 != 0)
@@ -475,7 +488,7 @@ int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, 
     return set_error(MSDA_ERR_BAD_ARGUMENT, "unscale_cast: inconsistent tail replica sizes");
   if (n == 0) return MSDA_OK;
   return launch_unscale_cast(acc_f16, out, scale, n, out_dtype, tail, tail_copies, map_elems, tail_elems,
-                             partial, colsum_out, C, overflow_flag, static_cast<cudaStream_t>(stream));
+                             partial, colsum_out, C, overflow_flag, out_row_stride, static_cast<cudaStream_t>(stream));
 }
 
 int bev_flatten_level(const void* feat, const void* cams_embeds, const void* level_embed, void* feat_flatten,

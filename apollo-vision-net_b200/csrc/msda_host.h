@@ -109,6 +109,6 @@ int launch_grad_scale(const void* g, long long n, int dtype, float limit, float*
                       cudaStream_t st);
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,
-                        float* ws, void* colsum_out, int C, int* overflow, cudaStream_t st);
+                        float* ws, void* colsum_out, int C, int* overflow, long long out_ld, cudaStream_t st);
 
 }  // namespace msda

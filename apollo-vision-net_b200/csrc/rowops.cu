@@ -633,8 +633,10 @@ template <typename TO, bool COLSUM>
 __global__ void __launch_bounds__(256)
 unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const float* __restrict__ scale, long long n,
                     const __half* __restrict__ tail, int copies, long long map_elems, long long tail_elems,
-                    float* __restrict__ ws, TO* __restrict__ colsum_out, int cgroups, int* __restrict__ overflow) {
+                    float* __restrict__ ws, TO* __restrict__ colsum_out, int cgroups, int* __restrict__ overflow,
+                    long long out_ld) {
   const float inv = 1.0f / __ldg(scale);             // power of two: exact
+  const int cg_shift = (cgroups > 0 && (cgroups & (cgroups - 1)) == 0) ? __ffs(cgroups) - 1 : -1;
   bool bad = false;                                  // a saturated (inf / NaN) accumulator slot was seen
   // grid: x over the 16-byte chunks of a value map, y over the maps (one map of n elements
   // when there are no tail replicas)
@@ -667,11 +669,22 @@ unscale_cast_kernel(const __half* __restrict__ acc, TO* __restrict__ out, const 
 #pragma unroll
         for (int k = 0; k < 8; ++k) csum[k] += v[k];
       }
+      // out_ld != 0: `out` is a column block of a wider matrix -- row r of the (n / C, C) view (C = 8 * cgroups)
+      // starts at out + r * out_ld (the feature-gradient GEMMs of the hoisted value projections read the
+      // blocks of all layers as one matrix)
+      TO* dst = o + i * 8;
+      if (out_ld != 0) {
+        const long long cg = map * chunks + i;
+        // (a 64-bit division per 16-byte chunk made the pass issue bound: 38 -> 59 us at 47 M elements)
+        const long long row = cg_shift >= 0 ? (cg >> cg_shift) : cg / cgroups;
+        const int col = cg_shift >= 0 ? (int)(cg & (cgroups - 1)) : (int)(cg % cgroups);
+        dst = out + row * out_ld + col * 8;
+      }
       if constexpr (sizeof(TO) == 2) {
-        *reinterpret_cast<uint4*>(o + i * 8) = Vec16<TO>::pack(v);
+        *reinterpret_cast<uint4*>(dst) = Vec16<TO>::pack(v);
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[i * 8 + k] = from_f32<TO>(v[k]);
+        for (int k = 0; k < 8; ++k) dst[k] = from_f32<TO>(v[k]);
       }
     };
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -731,18 +744,18 @@ int launch_grad_scale(const void* g, long long n, int dtype, float limit, float*
 template <typename TO>
 static void unscale_launch(dim3 grid, cudaStream_t st, const __half* a, void* out, const float* scale, long long n,
                            const __half* t, int copies, long long map_elems, long long tail_elems, float* ws,
-                           void* colsum_out, int cgroups, int* overflow) {
+                           void* colsum_out, int cgroups, int* overflow, long long out_ld) {
   if (colsum_out)
     unscale_cast_kernel<TO, true><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
-                                                         tail_elems, ws, static_cast<TO*>(colsum_out), cgroups, overflow);
+                                                         tail_elems, ws, static_cast<TO*>(colsum_out), cgroups, overflow, out_ld);
   else
     unscale_cast_kernel<TO, false><<<grid, 256, 0, st>>>(a, static_cast<TO*>(out), scale, n, t, copies, map_elems,
-                                                          tail_elems, nullptr, nullptr, 1, overflow);
+                                                          tail_elems, nullptr, nullptr, out_ld != 0 ? cgroups : 1, overflow, out_ld);
 }
 
 int launch_unscale_cast(const void* acc16, void* out, const float* scale, long long n, int out_dtype,
                         const void* tail, int copies, long long map_elems, long long tail_elems,
-                        float* ws, void* colsum_out, int C, int* overflow, cudaStream_t st) {
+                        float* ws, void* colsum_out, int C, int* overflow, long long out_ld, cudaStream_t st) {
   const __half* a = static_cast<const __half*>(acc16);
   const __half* t = static_cast<const __half*>(tail);
   if (!t || copies <= 0) { t = nullptr; copies = 0; map_elems = n; tail_elems = 0; }
@@ -755,9 +768,9 @@ int launch_unscale_cast(const void* acc16, void* out, const float* scale, long l
   if (gx > need) gx = need > 0 ? need : 1;
   const dim3 grid((unsigned)gx, (unsigned)(maps < 65535 ? maps : 65535));
   const int cgroups = C / 8;
-  if (out_dtype == MSDA_F32) unscale_launch<float>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
-  else if (out_dtype == MSDA_BF16) unscale_launch<__nv_bfloat16>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
-  else unscale_launch<__half>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow);
+  if (out_dtype == MSDA_F32) unscale_launch<float>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow, out_ld);
+  else if (out_dtype == MSDA_BF16) unscale_launch<__nv_bfloat16>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow, out_ld);
+  else unscale_launch<__half>(grid, st, a, out, scale, n, t, copies, map_elems, tail_elems, ws, colsum_out, cgroups, overflow, out_ld);
   count_launch();
   return check_launch("unscale_cast");
 }

@@ -242,20 +242,26 @@ def _accumulator(value, g_out, num_levels=1, rows_per_slot=0, replicas=True):
 def _finish_accumulator(acc, code, scale, value, tail=None, tail_px=0):
     if code == _lib.F32:
         return acc.to(value.dtype)
-    out = torch.empty(value.shape, dtype=value.dtype, device=value.device)
     maps, Nk, M, Dh = value.shape
     C = M * Dh
+    # a value tensor that is one of several hoisted projections of the same input gets its gradient written
+    # as a column block of their common matrix (rowops.GradSlots)
+    block = rowops.grad_slot(value) if (tail is None and C % 8 == 0 and acc.numel() % C == 0) else None
+    if block is not None:
+        out, out_ld = block.view(maps, Nk, M, Dh), block.stride(0)
+    else:
+        out, out_ld = torch.empty(value.shape, dtype=value.dtype, device=value.device), 0
     # the same pass returns the column sums of the (maps * Nk, C) view: the bias gradient of the value
     # projection that produced `value` (rowops.offer_bias_grad hands it to that Linear's backward)
     with_sums = C % 8 == 0 and 256 % (C // 8) == 0 and acc.numel() % 8 == 0
     sums = torch.empty(C, dtype=value.dtype, device=value.device) if with_sums else None
     ws = rowops._workspace(value.device, C) if with_sums else None
     with torch.cuda.device(value.device):
-        _lib.call('unscale_cast', acc.data_ptr(), out.data_ptr(), scale.data_ptr(), acc.numel(),
+        _lib.call('unscale_cast_strided', acc.data_ptr(), out.data_ptr(), scale.data_ptr(), acc.numel(),
                   _DTYPE_CODE[value.dtype], None if tail is None else tail.data_ptr(),
                   0 if tail is None else tail.shape[0], Nk * M * Dh, tail_px * M * Dh,
                   None if sums is None else sums.data_ptr(), None if ws is None else ws.data_ptr(), C,
-                  _overflow_flag(value.device).data_ptr(), _stream_ptr(value))
+                  _overflow_flag(value.device).data_ptr(), int(out_ld), _stream_ptr(value))
     if with_sums:
         rowops.offer_bias_grad(out, sums)
     return out

@@ -14,7 +14,7 @@ from torch.autograd.function import once_differentiable
 from ..fused_ops import QueueDeformAttnFunction
 from ..multi_scale_deformable_attn_function import custom_bwd, custom_fwd
 from ..registry import ATTENTION
-from ..rowops import _take_bias_grad, weight_bias_grad
+from ..rowops import GradSlots, _take_bias_grad, register_grad_slot, weight_bias_grad
 from .deform_common import DeformAttnBase, finish_block, msda_apply
 
 
@@ -35,7 +35,10 @@ class HoistedValueProjFunction(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(cast_inputs=None)
-    def forward(ctx, x, *params):
+    def forward(ctx, x, side_by_side, *params):
+        """``side_by_side``: offer the consumers of the outputs column blocks of one (rows, n * C) matrix to write
+        the outputs' gradients into (``rowops.GradSlots``; the fused attention backward takes them): the input
+        gradient is then ONE GEMM over K = n * C and the weight gradients ONE GEMM with n * C output rows."""
         n = len(params) // 2
         weights, biases = params[:n], params[n:]
         # one GEMM per layer with the bias in its epilogue, back to back on one input that stays in L2 (a
@@ -44,6 +47,11 @@ class HoistedValueProjFunction(torch.autograd.Function):
         for i in range(n):
             torch.addmm(biases[i], x, weights[i].t(), out=out[i])
         ctx.save_for_backward(x, *weights)
+        ctx.slots = None
+        if side_by_side and x.is_cuda:
+            ctx.slots = GradSlots(n, x.shape[0], weights[0].shape[0], x.dtype, x.device)
+            for i in range(n):
+                register_grad_slot(out[i], ctx.slots, i)
         return tuple(out[i] for i in range(n))
 
     @staticmethod
@@ -54,13 +62,35 @@ class HoistedValueProjFunction(torch.autograd.Function):
         n = len(weights)
         dx = None
         dws, dbs = [None] * n, [None] * n
+        slots, ctx.slots = ctx.slots, None
+        C = weights[0].shape[0]
+        if (slots is not None and slots.buffer is not None and all(slots.filled) and
+                all(g is not None and g.dim() == 2 and g.untyped_storage().data_ptr() ==
+                    slots.buffer.untyped_storage().data_ptr() and g.storage_offset() == i * C and
+                    g.stride() == slots.buffer.stride() and g.shape == (slots.rows, C)
+                    for i, g in enumerate(grads))):
+            # every gradient sits in its column block of the common matrix G (rows, n * C):
+            # dx = G [W_0; ...; W_{n-1}] and [dW_0; ...; dW_{n-1}] = G^T x, one GEMM each
+            G = slots.buffer
+            if ctx.needs_input_grad[0]:
+                dx = G @ torch.cat(list(weights), 0)
+            if any(ctx.needs_input_grad[2 + i] for i in range(n)):
+                dW = G.t() @ x
+                for i in range(n):
+                    if ctx.needs_input_grad[2 + i]:
+                        dws[i] = dW[i * C:(i + 1) * C]
+            for i, g in enumerate(grads):
+                if ctx.needs_input_grad[2 + n + i]:
+                    ready = _take_bias_grad(g, C)
+                    dbs[i] = ready.to(weights[i].dtype) if ready is not None else g.sum(0)
+            return (dx, None, *dws, *dbs)
         for i, (g, w) in enumerate(zip(grads, weights)):
             if g is None:
                 continue
             g2 = g.reshape(-1, w.shape[0])
             if ctx.needs_input_grad[0]:
                 dx = g2 @ w if dx is None else dx.addmm_(g2, w)
-            want_w, want_b = ctx.needs_input_grad[1 + i], ctx.needs_input_grad[1 + n + i]
+            want_w, want_b = ctx.needs_input_grad[2 + i], ctx.needs_input_grad[2 + n + i]
             ready = _take_bias_grad(g, w.shape[0]) if want_b else None
             if ready is not None:
                 dbs[i] = ready.to(w.dtype)
@@ -70,7 +100,7 @@ class HoistedValueProjFunction(torch.autograd.Function):
                 dbs[i] = db if want_b else dbs[i]
             elif want_b:
                 dbs[i] = g2.sum(0)
-        return (dx, *dws, *dbs)
+        return (dx, None, *dws, *dbs)
 
 
 def hoist_value_proj(attns, value, batch_first=False):
@@ -85,7 +115,7 @@ def hoist_value_proj(attns, value, batch_first=False):
     if not batch_first:
         value = value.permute(1, 0, 2)
     bs, n, C = value.shape
-    outs = HoistedValueProjFunction.apply(value.reshape(bs * n, C), *[a.value_proj.weight for a in attns],
+    outs = HoistedValueProjFunction.apply(value.reshape(bs * n, C), False, *[a.value_proj.weight for a in attns],
                                           *[a.value_proj.bias for a in attns])
     return [o.view(bs, n, -1) for o in outs]
 

@@ -275,7 +275,10 @@ class BEVFormerEncoder(BaseModule):
             found.append(vp)
         num_cams, l, bs_v, C = value.shape
         flat = value.permute(2, 0, 1, 3).reshape(bs_v * num_cams * l, C)
-        return list(HoistedValueProjFunction.apply(flat, *[vp.weight for vp in found], *[vp.bias for vp in found]))
+        # (side by side: the fused SCA backward writes every layer's value gradient into its column block of one
+        # matrix, so the feature gradient and the six weight gradients are one GEMM each)
+        return list(HoistedValueProjFunction.apply(flat, True, *[vp.weight for vp in found],
+                                                   *[vp.bias for vp in found]))
 
     def forward(self, bev_query, key, value, *args, bev_z=None, bev_h=None, bev_w=None,
                 bev_pos=None, spatial_shapes=None, level_start_index=None, valid_ratios=None,

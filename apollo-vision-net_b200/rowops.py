@@ -283,23 +283,82 @@ def linear_add_layernorm(x, linear_mod, residual, norm, p=0.0, junction=None):
 _bias_grads = {}
 
 
+# ---- side-by-side gradient blocks of hoisted projections ------------------------------------------
+# Several Linear layers project the SAME input (the camera features, once per encoder layer).  When their outputs'
+# gradients are written as column blocks of ONE (rows, layers * C) matrix, the input gradient is a single GEMM
+# over K = layers * C and the weight gradients a single GEMM with layers * C output rows -- instead of one GEMM
+# pair per layer plus accumulation.  The producer of such a gradient (fused_ops._finish_accumulator) asks here
+# whether the tensor whose gradient it is about to write has a slot.
+class GradSlots:
+    """(rows, n * C) buffer, allocated when the first gradient arrives; block l belongs to output l."""
+
+    def __init__(self, n, rows, C, dtype, device):
+        self.n, self.rows, self.C, self.dtype, self.device = n, rows, C, dtype, device
+        self.buffer = None
+        self.filled = [False] * n
+
+    def block(self, l):
+        if self.buffer is None:
+            self.buffer = torch.empty((self.rows, self.n * self.C), dtype=self.dtype, device=self.device)
+        self.filled[l] = True
+        return self.buffer[:, l * self.C:(l + 1) * self.C]
+
+
+_grad_slots = {}
+
+
+def register_grad_slot(out, slots, l):
+    import weakref
+    if len(_grad_slots) > 256:
+        for k in [k for k, (r, _) in _grad_slots.items() if r() is None]:
+            del _grad_slots[k]
+    _grad_slots[(out.untyped_storage().data_ptr(), out.storage_offset())] = (weakref.ref(slots), l)
+
+
+def grad_slot(t):
+    """The column block ``t``'s gradient should be written into ((rows, C) view, row stride = the buffer's
+    width), or None."""
+    ent = _grad_slots.get((t.untyped_storage().data_ptr(), t.storage_offset())) if _grad_slots else None
+    if ent is None:
+        return None
+    slots = ent[0]()
+    if slots is None or t.numel() != slots.rows * slots.C or t.dtype != slots.dtype or not t.is_contiguous():
+        return None
+    return slots.block(ent[1])
+
+
 def offer_bias_grad(grad, colsum):
     """``colsum`` = sum over all rows of ``grad`` viewed as (-1, colsum.numel())."""
     import weakref
     if len(_bias_grads) > 64:                               # entries nobody collected
         for k in [k for k, (r, *_) in _bias_grads.items() if r() is None]:
             del _bias_grads[k]
-    _bias_grads[grad.untyped_storage().data_ptr()] = (weakref.ref(grad), grad._version, grad.numel(), colsum)
+    # (a view's root keeps the memory alive and shares the version counter with it; the view object itself
+    # may be gone by the time the consumer runs)
+    root = grad._base if grad._base is not None else grad
+    _bias_grads[(grad.untyped_storage().data_ptr(), grad.storage_offset())] = (
+        weakref.ref(root), grad._version, grad.numel(), colsum, grad.dtype, _rows_layout(grad, colsum.numel()))
+
+
+def _rows_layout(t, C):
+    """Strides of the (rows, C) view of ``t``; None when ``t`` is not such a view."""
+    try:
+        return t.view(-1, C).stride()
+    except RuntimeError:
+        return None
 
 
 def _take_bias_grad(dy, C):
-    ent = _bias_grads.pop(dy.untyped_storage().data_ptr(), None) if _bias_grads else None
+    ent = _bias_grads.pop((dy.untyped_storage().data_ptr(), dy.storage_offset()), None) if _bias_grads else None
     if ent is None:
         return None
-    ref, version, numel, colsum = ent
+    ref, version, numel, colsum, dtype, layout = ent
     g = ref()
-    if (g is None or g._version != version or numel != dy.numel() or colsum.numel() != C or
-            not dy.is_contiguous() or dy.storage_offset() != g.storage_offset() or dy.dtype != g.dtype):
+    # honoured only while the offered memory is alive and unmodified and the consumer's tensor covers exactly the
+    # offered bytes: same start (the key), same number of elements, same (rows, C) layout -- which may be a column
+    # block of a wider matrix (grad_slot())
+    if (g is None or g._version != version or numel != dy.numel() or colsum.numel() != C or dy.dtype != dtype or
+            layout is None or _rows_layout(dy, C) != layout):
         return None
     return colsum
 

@@ -260,6 +260,14 @@ int grad_amax_scale_zero(const void* g, int64_t n, int dtype, float limit, float
 int unscale_cast(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
                  const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
                  void* colsum_out, float* partial, int C, int32_t* overflow_flag, void* stream);
+/* The same with `out` a column block of a wider row-major matrix (ABI 8): row r of the (n / C, C) view of the
+ * result is written at out + r * out_row_stride elements (0 = contiguous; no tail replicas in this form).
+ * The hoisted value projections of the encoder collect the gradients of all layers' projections side by side
+ * this way, so that the feature gradient and the weight gradients are one GEMM each. */
+int unscale_cast_strided(const void* acc_f16, void* out, const float* scale, int64_t n, int out_dtype,
+                         const void* tail, int tail_copies, int64_t map_elems, int64_t tail_elems,
+                         void* colsum_out, float* partial, int C, int32_t* overflow_flag,
+                         int64_t out_row_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Row-wise companions of the attention kernels inside a BEVFormer layer (SURVEY.md section
