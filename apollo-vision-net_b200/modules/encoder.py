@@ -280,6 +280,30 @@ class BEVFormerEncoder(BaseModule):
         return list(HoistedValueProjFunction.apply(flat, True, *[vp.weight for vp in found],
                                                    *[vp.bias for vp in found]))
 
+    def _hoisted_tsa_values(self, pair):
+        """With history the TSA value -- the (bs * 2, HW, C) pair [prev_bev, bev_query] -- is the same tensor in every
+        layer (reference :317-320 builds it once in front of the loop), each layer projecting it with its own
+        ``value_proj``.  In training the projections are hoisted like the SCA ones: the six weight gradients
+        (and the pair's gradient, when it wants one) become one GEMM each."""
+        from .decoder import HoistedValueProjFunction
+        from .temporal_self_attention import TemporalSelfAttention
+        if (len(self.layers) < 2 or pair is None or not pair.is_cuda or not torch.is_grad_enabled() or
+                not self.training):
+            return None
+        found = []
+        for layer in self.layers:
+            mods = [a for a in getattr(layer, 'attentions', []) if isinstance(a, TemporalSelfAttention)]
+            if len(mods) != 1 or not mods[0].batch_first:
+                return None
+            vp = mods[0].value_proj
+            if (vp.bias is None or vp.weight.dtype != pair.dtype or vp.weight.shape != (pair.shape[-1],) * 2 or
+                    not vp.weight.requires_grad):
+                return None
+            found.append(vp)
+        flat = pair.reshape(-1, pair.shape[-1])
+        outs = HoistedValueProjFunction.apply(flat, True, *[vp.weight for vp in found], *[vp.bias for vp in found])
+        return [o.view(pair.shape) for o in outs]
+
     def forward(self, bev_query, key, value, *args, bev_z=None, bev_h=None, bev_w=None,
                 bev_pos=None, spatial_shapes=None, level_start_index=None, valid_ratios=None,
                 prev_bev=None, shift=0., img_metas=None, lidar2img=None, img_shape=None,
@@ -350,9 +374,12 @@ class BEVFormerEncoder(BaseModule):
             kwargs = dict(kwargs, row_slice=(q0, q1))
 
         projected = self._hoisted_sca_values(key, value, bs)
+        tsa_projected = self._hoisted_tsa_values(prev_bev)
         for li, layer in enumerate(self.layers):
             if projected is not None:
                 kwargs['_sca_projected_value'] = projected[li]
+            if tsa_projected is not None:
+                kwargs['_tsa_projected_value'] = tsa_projected[li]
             output = layer(bev_query, key, value, *args, bev_pos=bev_pos, ref_2d=hybird_ref_2d,
                            ref_3d=ref_3d, bev_h=shard_h, bev_w=bev_w, spatial_shapes=spatial_shapes,
                            level_start_index=level_start_index,

@@ -67,7 +67,11 @@ class TemporalSelfAttention(DeformAttnBase):
         else:
             tok = None
             coords = self.project_coords(torch.cat([paired, query], -1))
-        value = self.value_proj(value)
+        projected = kwargs.get('_tsa_projected_value')
+        if projected is not None and projected.shape == value.shape:
+            value = projected                      # hoisted in front of the layer loop (encoder._hoisted_tsa_values)
+        else:
+            value = self.value_proj(value)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], 0.0)
         value = value.reshape(bs * Q, num_value, M, -1)
