@@ -32,6 +32,9 @@
 extern "C" {
 #endif
 
+/* 8: the row kernels' `partial` scratch holds eight reduction strips (64 + 8 * n * C floats); new entries
+ *    grad_amax_scale_zero (scale + accumulator clear in one launch) and unscale_cast_strided (result written as a
+ *    column block of a wider matrix).  Signatures of the older entries are unchanged since 7. */
 #define MSDA_ABI_VERSION 8
 
 /* element types of `value` / `out` (and optionally of locations / weights) */
